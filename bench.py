@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""Headline benchmark: graphs/s of whole-model GNN inference on QM9-shaped graphs.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU C++ testbench
+
+Workload = BASELINE.json configs[1]: GIN 3-layer hidden=128 (sum aggregation, skip connections,
+add|mean|max pooling, 384->64->64->19 MLP head) on 1M QM9-shaped synthetic graphs (~18 nodes,
+~38 directed edges, 11 features) PER GPU (independent graphs shard across ranks with no
+collective => weak scaling).  A step = one pass of the whole hot path (tables -> 3 convs ->
+pooling -> head) over the rank's batch.
+
+  value      whole-job graphs/s with inputs resident in HBM, CUDA events on the library's stream,
+             max over ranks.  The batch (1.1 GB) is larger than L2 (126 MB): no flush needed.
+  e2e        the same through the public host-buffer API (Engine.run): pinned host inputs,
+             H2D + kernels + D2H inside the timed region.
+  roofline   dominant kernel class, timed live with CUDA events (gnnb_model_profile_read).
+  cpu_baseline  the reference's own generated <name>_top (oracle/_ref, g++ -O3) on one host
+             core over a bounded prefix of the same batch.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "graphs_per_sec"
+UNIT = "graphs/s"
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def algorithmic_flops_per_batch(w, batch) -> float:
+    """SURVEY 8(d) formulas, evaluated on the actual batch."""
+    n, e, g = batch.total_nodes, batch.total_edges, batch.n_graphs
+    fl = 0.0
+    for layer in range(w.num_layers):
+        fi = w.in_dim if layer == 0 else w.hidden_dim
+        fo = w.hidden_dim
+        if w.conv == "gcn":
+            fl += 2.0 * (e + n) * fi + 2.0 * n * fi * fo
+        elif w.conv == "gin":
+            fl += 2.0 * e * fi + 2.0 * n * (fi * fo + fo * fo)
+        elif w.conv == "sage":
+            fl += 2.0 * e * fi + 4.0 * n * fi * fo
+        elif w.conv == "pna":
+            fl += 2.0 * e * 2 * fi * fi + 10.0 * e * fi + 2.0 * n * (13 * fi * fo + fo * fo)
+    fl += float(len(w.pools)) * n * w.hidden_dim
+    dims = [w.hidden_dim * len(w.pools)] + [w.mlp_hidden_dim] * w.mlp_hidden_layers + [w.out_dim]
+    fl += 2.0 * g * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    return fl
+
+
+def gemm_flops_per_batch(w, batch) -> float:
+    n, g = batch.total_nodes, batch.n_graphs
+    fl = 0.0
+    for layer in range(w.num_layers):
+        fi = w.in_dim if layer == 0 else w.hidden_dim
+        fo = w.hidden_dim
+        fl += {"gcn": 2.0 * n * fi * fo, "gin": 2.0 * n * (fi * fo + fo * fo),
+               "sage": 4.0 * n * fi * fo,
+               "pna": 2.0 * n * (2 * fi * fi + 13 * fi * fo + fo * fo)}[w.conv]
+    dims = [w.hidden_dim * len(w.pools)] + [w.mlp_hidden_dim] * w.mlp_hidden_layers + [w.out_dim]
+    fl += 2.0 * g * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    return fl
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.dev = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.dev)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ts, line in self.lines:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def _ref_worker(args):
+    name, params, xs, coos, nptr, eptr, repeat = args
+    sys.path.insert(0, str(ROOT / "oracle"))
+    from oracle import RefModel
+    from gnn_builder_b200.data import GraphBatch
+
+    ref = RefModel(name)
+    ref.set_params(params)
+    batch = GraphBatch(xs, coos, nptr, eptr)
+    ref(*batch.graph(0))  # untimed parameter load, like the reference testbench (tb:170-172)
+    t0 = time.perf_counter()
+    for _ in range(repeat):
+        for g in range(batch.n_graphs):
+            ref(*batch.graph(g))
+    return time.perf_counter() - t0, batch.n_graphs * repeat
+
+
+def _port_worker(args):
+    name, desc, params, xs, coos, nptr, eptr, repeat = args
+    sys.path.insert(0, str(ROOT / "oracle"))
+    from oracle import Oracle
+    from gnn_builder_b200.data import GraphBatch
+
+    orc = Oracle()
+    batch = GraphBatch(xs, coos, nptr, eptr)
+    t0 = time.perf_counter()
+    for _ in range(repeat):
+        orc.model_forward_batch(desc, list(params.values()), batch)
+    return time.perf_counter() - t0, batch.n_graphs * repeat
+
+
+def reference_available(name) -> bool:
+    return (ROOT / "oracle" / "_ref" / "models" / name / f"lib{name}.so").exists()
+
+
+def cpu_reference_rate(w, model, batch, n_procs: int, graphs_per_proc: int, repeat: int = 1):
+    """graphs/s of the reference CPU implementation: n_procs independent single-threaded
+    processes (the generated top is not re-entrant), each over its own slice of the batch."""
+    import multiprocessing as mp
+
+    params = model.named_parameter_arrays()
+    kind = "reference" if reference_available(w.name) else "port"
+    jobs = []
+    for p in range(n_procs):
+        g0 = (p * graphs_per_proc) % max(1, batch.n_graphs - graphs_per_proc)
+        sl = batch.slice(g0, g0 + graphs_per_proc)
+        common = (np.ascontiguousarray(sl.x), np.ascontiguousarray(sl.coo),
+                  np.ascontiguousarray(sl.node_ptr), np.ascontiguousarray(sl.edge_ptr), repeat)
+        if kind == "reference":
+            jobs.append((w.name, params) + common)
+        else:
+            jobs.append((w.name, model.describe(), params) + common)
+    fn = _ref_worker if kind == "reference" else _port_worker
+    t0 = time.perf_counter()
+    if n_procs == 1:
+        res = [fn(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(n_procs) as pool:
+            res = pool.map(fn, jobs)
+    wall = time.perf_counter() - t0
+    graphs = sum(r[1] for r in res)
+    busy = max(r[0] for r in res)
+    return graphs / busy, kind, graphs, busy, wall
+
+
+def run_reference_arm(args, w):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    import gnn_builder_b200 as gnnb
+
+    model = gnnb.build_model(w, pna_delta=w.pna_delta, seed=0)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    n_procs = max(1, min(cores, 64))
+    per_proc = args.ref_graphs
+    batch = gnnb.make_molecular_batch(max(per_proc * 4, per_proc + 1), w.mu_nodes, w.mu_edges,
+                                      w.in_dim, seed=w.seed)
+    rates = []
+    kind = "port"
+    for step in range(args.warmup + args.steps):
+        rate, kind, graphs, busy, wall = cpu_reference_rate(w, model, batch, n_procs, per_proc)
+        if step >= args.warmup:
+            rates.append((graphs, busy))
+    total_graphs = sum(g for g, _ in rates)
+    total_time = sum(t for _, t in rates)
+    value = total_graphs / total_time
+    sample = (f"{n_procs} single-threaded processes x {per_proc} graphs per step, "
+              f"{'reference <name>_top compiled g++ -O3 (oracle/_ref)' if kind == 'reference' else 'oracle C port'}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total_time / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(w, args, per_gpu_graphs=args.graphs),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_procs, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(w, args, per_gpu_graphs):
+    return {
+        "workload": f"{w.name}: {w.conv.upper()} {w.num_layers}-layer hidden={w.hidden_dim} "
+                    f"pools={'|'.join(w.pools)} head {w.hidden_dim * len(w.pools)}->"
+                    f"{w.mlp_hidden_dim}x{w.mlp_hidden_layers}->{w.out_dim}, QM9-shaped graphs "
+                    f"(mu_nodes={w.mu_nodes}, mu_edges={w.mu_edges}, feats={w.in_dim})",
+        "graphs_per_gpu": per_gpu_graphs,
+        "sharding": "independent graphs per rank, no collective",
+        "l2_policy": "inputs (1.1 GB per GPU at 1M graphs) larger than L2; no flush",
+    }
+
+
+# ------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gnnb", choices=["gnnb", "reference"])
+    ap.add_argument("--workload", default="c2_gin_qm9")
+    ap.add_argument("--graphs", type=int, default=0, help="graphs per GPU (default: the config's)")
+    ap.add_argument("--path", default="auto", choices=["auto", "fused", "layerwise"])
+    ap.add_argument("--ref-graphs", type=int, default=400,
+                    help="graphs per process per step of the reference arm")
+    ap.add_argument("--cpu-baseline-graphs", type=int, default=8000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    from gnn_builder_b200.configs import WORKLOADS
+
+    w = WORKLOADS[args.workload]
+    if args.graphs <= 0:
+        args.graphs = w.n_graphs
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+        return
+
+    import torch
+
+    import gnn_builder_b200 as gnnb
+
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v: float) -> float:
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- workload: this rank's shard of independent graphs
+    model = gnnb.build_model(w, pna_delta=w.pna_delta, seed=0)
+    batch = gnnb.make_molecular_batch(args.graphs, w.mu_nodes, w.mu_edges, w.in_dim,
+                                      seed=w.seed + 1000 * rank, max_nodes=w.max_nodes)
+    G, T, E = batch.n_graphs, batch.total_nodes, batch.total_edges
+    max_n = int(np.diff(batch.node_ptr).max())
+    max_e = int(np.diff(batch.edge_ptr).max())
+    eng = gnnb.Engine(model, max_nodes=max_n, max_edges=max_e, device=local_rank,
+                      path={"auto": gnnb.PATH_AUTO, "fused": gnnb.PATH_FUSED,
+                            "layerwise": gnnb.PATH_LAYERWISE}[args.path])
+
+    # pinned host copies (e2e) and device-resident copies (value)
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+
+    hx, hcoo = pinned(batch.x), pinned(batch.coo)
+    hn, he = pinned(batch.node_ptr), pinned(batch.edge_ptr)
+    hout = torch.empty((G, w.out_dim), dtype=torch.float32, pin_memory=True)
+    host_batch = gnnb.GraphBatch(hx.numpy(), hcoo.numpy(), hn.numpy(), he.numpy())
+    dx, dcoo = hx.cuda(non_blocking=True), hcoo.cuda(non_blocking=True)
+    dn, de = hn.cuda(non_blocking=True), he.cuda(non_blocking=True)
+    dout = torch.empty((G, w.out_dim), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(eng.stream)
+
+    def step_device():
+        eng.run_device(dx, dcoo, dn, de, dout, G, T, E)
+
+    # ---- device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        step_device()
+    eng.synchronize()
+    launches_per_step = eng.last_launches
+    path_used = {gnnb.PATH_FUSED: "fused", gnnb.PATH_LAYERWISE: "layerwise"}[eng.last_path]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    t_wall0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        ev1.record(stream)
+    eng.synchronize()
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_per_step = ms_total / args.steps
+    total_graphs = sum_over_ranks(float(G))
+    value = total_graphs / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the public host-buffer API (`e2e`)
+    for _ in range(min(args.warmup, 2)):
+        eng.run(host_batch, out=hout.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.run(host_batch, out=hout.numpy())
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    barrier()
+    h2d = int(batch.x.nbytes + batch.coo.nbytes + batch.node_ptr.nbytes + batch.edge_ptr.nbytes)
+    d2h = int(G * w.out_dim * 4)
+    e2e_value = total_graphs / e2e_s
+
+    # ---- live per-kernel-class timing for the roofline
+    eng.set_profile(True)
+    prof_steps = 2
+    for _ in range(prof_steps):
+        step_device()
+    prof = eng.read_profile()
+    eng.set_profile(False)
+    peaks_fp = ROOT / "MEASURED_PEAKS.json"
+    peaks = json.loads(peaks_fp.read_text()) if peaks_fp.exists() else {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    dominant = max(prof, key=lambda k: prof[k]["ms"])
+    dom_ms = prof[dominant]["ms"] / prof_steps
+    alg_bytes = batch.algorithmic_bytes(w.out_dim)
+    alg_flops = algorithmic_flops_per_batch(w, batch)
+    sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    fp32_peak_tflops = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    if dominant in ("gemm", "fused"):
+        fl = gemm_flops_per_batch(w, batch) if dominant == "gemm" else alg_flops
+        achieved = fl / (dom_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": dominant, "achieved": achieved,
+                    "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                    "traffic": None, "peak_source": peak_src + ", bf16 sustained",
+                    "kernel_ms": dom_ms,
+                    "note": "molecular graphs are compute/latency bound, not HBM bound (SURVEY "
+                            "8d); the node transform currently runs on the fp32 FMA pipe",
+                    "fp32_fma_peak_tflops": fp32_peak_tflops,
+                    "frac_of_fp32_fma_peak": achieved / fp32_peak_tflops}
+    else:
+        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                    "peak_source": peak_src, "kernel_ms": dom_ms}
+    roofline["hbm_algorithmic_gbs_whole_step"] = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    roofline["class_ms_per_step"] = {k: v["ms"] / prof_steps for k, v in prof.items()}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_cpu = min(args.cpu_baseline_graphs, G)
+        rate, kind, graphs, busy, _ = cpu_reference_rate(w, model, batch, 1, n_cpu)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
+                        "sample": f"first {n_cpu} graphs of the same batch, one pass, "
+                                  f"{busy:.1f} s on one host core"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(w, args, G), path=path_used,
+                           nodes_per_gpu=T, edges_per_gpu=E),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,389 @@
+// CSR (by destination) neighbor aggregation -- the gather/reduce half of every conv of
+// gnn_builder_lib.h:  gcn_conv_agg (lib:1213-1289), gin_conv_agg (1389-1437), sage_conv_agg
+// (2161-2209), pna_conv_agg (1750-1834), lg/simple (2350-2549).
+//
+// Kernel (2) of the design: a (sub-)warp per destination row, lanes across the feature dimension
+// with float4 (16 B) gathers of each neighbor row, so one neighbor row of F=128 floats is one
+// fully coalesced 512 B warp request; neighbor loop unrolled x4 so four independent gathers are
+// in flight per lane.  Rows are bucketed by in-degree: rows above `heavy_threshold` are skipped
+// here and handled by a CTA-per-row kernel that splits the neighbor list across its 8 warps and
+// reduces the partials in shared memory in a fixed order (deterministic).
+//
+// HBM roofline: algorithmic bytes per layer = E*(4F + 4 [nbr idx] + 4 [dinv/deg]) +
+// N*(4F self + 4F_out write + 8 [offset, degree]).  Neighbors are visited in table order, so in
+// STRICT mode (no FMA contraction, reference scaling formula) sums round exactly like the
+// reference's sum_incremental accumulators.
+#include "kernels.h"
+
+namespace gnnb {
+
+namespace {
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<1> {
+    float v[1];
+    __device__ __forceinline__ void load(const float *p) { v[0] = __ldg(p); }
+    __device__ __forceinline__ void store(float *p) const { p[0] = v[0]; }
+};
+template <>
+struct Vec<4> {
+    float v[4];
+    __device__ __forceinline__ void load(const float *p)
+    {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void store(float *p) const
+    {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+
+template <int MODE, bool STRICT>
+__device__ __forceinline__ float neighbor_scale(const AggArgs &a, int deg_v, float dinv_v, int u)
+{
+    if (MODE == AGG_GCN) {
+        if (STRICT) {
+            const float di = __fadd_rn(1.0f, (float)deg_v);
+            const float dj = __fadd_rn(1.0f, (float)__ldg(a.in_deg + u));
+            return __fdiv_rn(1.0f, __fsqrt_rn(__fmul_rn(di, dj)));  // lib:1249-1252
+        }
+        return __ldg(a.dinv + u);  // rsqrt(1+d_u); the rsqrt(1+d_v) factor is applied once at the end
+    }
+    if (MODE == AGG_LG) {
+        return __fdiv_rn(1.0f, __fsqrt_rn((float)(deg_v * __ldg(a.in_deg + u))));  // lib:2386
+    }
+    return 1.0f;
+}
+
+template <int VEC, int MODE, bool STRICT>
+__device__ __forceinline__ void accumulate(Vec<VEC> &acc, const Vec<VEC> &x, float scale)
+{
+#pragma unroll
+    for (int i = 0; i < VEC; i++) {
+        if (MODE == AGG_GCN || MODE == AGG_LG)
+            acc.v[i] = mac<STRICT>(acc.v[i], x.v[i], scale);
+        else
+            acc.v[i] = __fadd_rn(acc.v[i], x.v[i]);
+    }
+}
+
+// partial sum over neighbors [k0, k1) of row v for the feature chunk starting at column c
+template <int VEC, int MODE, bool STRICT>
+__device__ __forceinline__ void gather_range(const AggArgs &a, int off, int k0, int k1, int deg_v,
+                                             float dinv_v, int c, Vec<VEC> &acc)
+{
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {
+        int u[4];
+        Vec<VEC> x[4];
+        float sc[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) u[j] = __ldg(a.nbr + off + k + j);
+#pragma unroll
+        for (int j = 0; j < 4; j++) x[j].load(a.x + (size_t)u[j] * a.ldx + c);
+#pragma unroll
+        for (int j = 0; j < 4; j++) sc[j] = neighbor_scale<MODE, STRICT>(a, deg_v, dinv_v, u[j]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) accumulate<VEC, MODE, STRICT>(acc, x[j], sc[j]);
+    }
+    for (; k < k1; k++) {
+        const int u = __ldg(a.nbr + off + k);
+        Vec<VEC> x;
+        x.load(a.x + (size_t)u * a.ldx + c);
+        accumulate<VEC, MODE, STRICT>(acc, x, neighbor_scale<MODE, STRICT>(a, deg_v, dinv_v, u));
+    }
+}
+
+// self term / normalisation and store
+template <int VEC, int MODE, bool STRICT>
+__device__ __forceinline__ void finish_row(const AggArgs &a, int v, int deg_v, float dinv_v, int c,
+                                           Vec<VEC> &acc)
+{
+    if (MODE == AGG_GCN) {
+        Vec<VEC> xs;
+        xs.load(a.x + (size_t)v * a.ldx + c);
+        if (STRICT) {
+            const float di = __fadd_rn(1.0f, (float)deg_v);
+            const float ss = __fdiv_rn(1.0f, __fsqrt_rn(__fmul_rn(di, di)));  // lib:1266-1267
+#pragma unroll
+            for (int i = 0; i < VEC; i++)
+                acc.v[i] = __fadd_rn(acc.v[i], __fmul_rn(xs.v[i], ss));
+        } else {
+            const float ss = dinv_v * dinv_v;
+#pragma unroll
+            for (int i = 0; i < VEC; i++) acc.v[i] = fmaf(xs.v[i], ss, acc.v[i] * dinv_v);
+        }
+    } else if (MODE == AGG_GIN) {
+        Vec<VEC> xs;
+        xs.load(a.x + (size_t)v * a.ldx + c);
+        const float s = __fadd_rn(1.0f, a.eps);  // lib:1522
+#pragma unroll
+        for (int i = 0; i < VEC; i++) acc.v[i] = __fadd_rn(acc.v[i], __fmul_rn(xs.v[i], s));
+    } else if (MODE == AGG_MEAN) {
+        if (deg_v > 0) {
+            const float d = (float)deg_v;
+#pragma unroll
+            for (int i = 0; i < VEC; i++) acc.v[i] = __fdiv_rn(acc.v[i], d);  // lib:661
+        }
+    }
+    acc.store(a.out + (size_t)v * a.ldo + c);
+}
+
+// LPR lanes cooperate on one destination row; 32/LPR rows per warp.
+template <int VEC, int LPR, int MODE, bool STRICT>
+__global__ void __launch_bounds__(256) agg_rows_kernel(const AggArgs a)
+{
+    constexpr int ROWS_PER_WARP = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int lg = lane % LPR;
+    const int sub = lane / LPR;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int64_t warp_stride = (int64_t)gridDim.x * warps_per_block;
+    for (int64_t row0 = warp_global * ROWS_PER_WARP; row0 < a.n; row0 += warp_stride * ROWS_PER_WARP) {
+        const int v = (int)row0 + sub;
+        if (v >= a.n) continue;
+        const int deg_v = __ldg(a.in_deg + v);
+        if (a.n_heavy > 0 && deg_v > a.heavy_threshold) continue;  // CTA-per-row kernel does these
+        const int off = __ldg(a.offsets + v);
+        const float dinv_v = (MODE == AGG_GCN && !STRICT) ? __ldg(a.dinv + v) : 0.0f;
+        for (int c = lg * VEC; c < a.F; c += LPR * VEC) {
+            Vec<VEC> acc;
+#pragma unroll
+            for (int i = 0; i < VEC; i++) acc.v[i] = 0.0f;
+            gather_range<VEC, MODE, STRICT>(a, off, 0, deg_v, deg_v, dinv_v, c, acc);
+            finish_row<VEC, MODE, STRICT>(a, v, deg_v, dinv_v, c, acc);
+        }
+    }
+}
+
+// One CTA (8 warps) per heavy row: the neighbor list is split into 8 contiguous ranges.
+template <int VEC, int MODE>
+__global__ void __launch_bounds__(256) agg_heavy_kernel(const AggArgs a)
+{
+    extern __shared__ float partial[];  // [8][F]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int h = blockIdx.x; h < a.n_heavy; h += gridDim.x) {
+        const int v = __ldg(a.heavy_rows + h);
+        const int deg_v = __ldg(a.in_deg + v);
+        const int off = __ldg(a.offsets + v);
+        const float dinv_v = (MODE == AGG_GCN) ? __ldg(a.dinv + v) : 0.0f;
+        const int per = (deg_v + 7) / 8;
+        const int k0 = min(deg_v, warp * per), k1 = min(deg_v, (warp + 1) * per);
+        for (int c = lane * VEC; c < a.F; c += 32 * VEC) {
+            Vec<VEC> acc;
+#pragma unroll
+            for (int i = 0; i < VEC; i++) acc.v[i] = 0.0f;
+            gather_range<VEC, MODE, false>(a, off, k0, k1, deg_v, dinv_v, c, acc);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) partial[warp * a.F + c + i] = acc.v[i];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int c = lane * VEC; c < a.F; c += 32 * VEC) {
+                Vec<VEC> acc;
+#pragma unroll
+                for (int i = 0; i < VEC; i++) {
+                    float s = 0.0f;
+#pragma unroll
+                    for (int w = 0; w < 8; w++) s += partial[w * a.F + c + i];
+                    acc.v[i] = s;
+                }
+                finish_row<VEC, MODE, false>(a, v, deg_v, dinv_v, c, acc);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int VEC, int LPR, bool STRICT>
+int launch_mode(const AggArgs &a, int grid, cudaStream_t s)
+{
+    switch (a.mode) {
+    case AGG_GCN: agg_rows_kernel<VEC, LPR, AGG_GCN, STRICT><<<grid, 256, 0, s>>>(a); break;
+    case AGG_GIN: agg_rows_kernel<VEC, LPR, AGG_GIN, STRICT><<<grid, 256, 0, s>>>(a); break;
+    case AGG_MEAN: agg_rows_kernel<VEC, LPR, AGG_MEAN, STRICT><<<grid, 256, 0, s>>>(a); break;
+    case AGG_SUM: agg_rows_kernel<VEC, LPR, AGG_SUM, STRICT><<<grid, 256, 0, s>>>(a); break;
+    case AGG_LG: agg_rows_kernel<VEC, LPR, AGG_LG, STRICT><<<grid, 256, 0, s>>>(a); break;
+    default: set_error("unknown aggregation mode"); return GNNB_ERR_INVALID;
+    }
+    return GNNB_OK;
+}
+
+template <int VEC, bool STRICT>
+int launch_lpr(const AggArgs &a, int lpr, int grid, cudaStream_t s)
+{
+    switch (lpr) {
+    case 1: return launch_mode<VEC, 1, STRICT>(a, grid, s);
+    case 2: return launch_mode<VEC, 2, STRICT>(a, grid, s);
+    case 4: return launch_mode<VEC, 4, STRICT>(a, grid, s);
+    case 8: return launch_mode<VEC, 8, STRICT>(a, grid, s);
+    case 16: return launch_mode<VEC, 16, STRICT>(a, grid, s);
+    default: return launch_mode<VEC, 32, STRICT>(a, grid, s);
+    }
+}
+
+template <int VEC>
+int launch_heavy(const AggArgs &a, cudaStream_t s)
+{
+    const int grid = a.n_heavy < kNumSMs * 4 ? a.n_heavy : kNumSMs * 4;
+    const size_t smem = sizeof(float) * 8 * (size_t)a.F;
+    switch (a.mode) {
+    case AGG_GCN: agg_heavy_kernel<VEC, AGG_GCN><<<grid, 256, smem, s>>>(a); break;
+    case AGG_GIN: agg_heavy_kernel<VEC, AGG_GIN><<<grid, 256, smem, s>>>(a); break;
+    case AGG_MEAN: agg_heavy_kernel<VEC, AGG_MEAN><<<grid, 256, smem, s>>>(a); break;
+    case AGG_SUM: agg_heavy_kernel<VEC, AGG_SUM><<<grid, 256, smem, s>>>(a); break;
+    default: set_error("heavy-row path: unsupported mode"); return GNNB_ERR_INVALID;
+    }
+    return GNNB_OK;
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+int launch_agg(const AggArgs &a_in, bool strict, cudaStream_t s, int *launches)
+{
+    AggArgs a = a_in;
+    if (a.n <= 0) return GNNB_OK;
+    GNNB_REQUIRE(a.F > 0, "aggregation: feature size must be positive");
+    if (strict) a.n_heavy = 0;
+    if (a.mode == AGG_GCN && !strict)
+        GNNB_REQUIRE(a.dinv != nullptr, "gcn aggregation needs the dinv table in fast mode");
+    const bool v4 = (a.F % 4 == 0) && (a.ldx % 4 == 0) && (a.ldo % 4 == 0) && aligned16(a.x) &&
+                    aligned16(a.out);
+    const int vec = v4 ? 4 : 1;
+    int lpr = 1;
+    while (lpr < 32 && lpr * vec < a.F) lpr *= 2;
+    const int rows_per_block = 8 * (32 / lpr);
+    int64_t grid64 = ceil_div64(a.n, rows_per_block);
+    const int64_t cap = (int64_t)kNumSMs * 8 * 4;  // 8 resident CTAs/SM x 4 waves, grid-stride
+    int grid = (int)(grid64 < cap ? grid64 : cap);
+    int rc;
+    if (vec == 4)
+        rc = strict ? launch_lpr<4, true>(a, lpr, grid, s) : launch_lpr<4, false>(a, lpr, grid, s);
+    else
+        rc = strict ? launch_lpr<1, true>(a, lpr, grid, s) : launch_lpr<1, false>(a, lpr, grid, s);
+    GNNB_TRY(rc);
+    GNNB_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+    if (a.n_heavy > 0) {
+        GNNB_REQUIRE(a.heavy_rows != nullptr, "heavy row list missing");
+        GNNB_TRY(vec == 4 ? launch_heavy<4>(a, s) : launch_heavy<1>(a, s));
+        GNNB_CUDA(cudaGetLastError());
+        if (launches) ++*launches;
+    }
+    return GNNB_OK;
+}
+
+// ------------------------------------------------------------------------------------ PNA
+//
+// lib:1750-1834 with the legal rewrite W_pre.[x_v || x_u] + b = (W_self.x_v + b) + W_nbr.x_u
+// (SURVEY section 7): `ab` holds A = X.W_nbr^T in columns [0,F) and B = X.W_self^T + b_pre in
+// columns [F,2F), so the per-edge transformed message is t = A_u + B_v and the aggregation is a
+// pure gather-reduce: max, min, mean and Welford variance (lib:677-705, population variance,
+// std = sqrt(var + 1e-5); 0/0 = NaN for in-degree 0 exactly like the reference float build).
+// The three degree scalers (lib:1973-1984, 2081-2089) are applied here and the 12F concat
+// written in the reference's order (lib:1857-1875 minus the leading self block).
+namespace {
+
+template <int VEC, int LPR>
+__global__ void __launch_bounds__(256) pna_agg_kernel(const PnaAggArgs a)
+{
+    constexpr int ROWS_PER_WARP = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int lg = lane % LPR, sub = lane / LPR;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int64_t warp_stride = (int64_t)gridDim.x * warps_per_block;
+    const int F = a.F, ld = 2 * a.F;
+    for (int64_t row0 = warp_global * ROWS_PER_WARP; row0 < a.n; row0 += warp_stride * ROWS_PER_WARP) {
+        const int v = (int)row0 + sub;
+        if (v >= a.n) continue;
+        const int deg = __ldg(a.in_deg + v);
+        const int off = __ldg(a.offsets + v);
+        const int clamped = deg < 1 ? 1 : deg;
+        const float lg1 = logf((float)(clamped + 1));
+        const float amp = __fdiv_rn(lg1, a.delta), att = __fdiv_rn(a.delta, lg1);
+        for (int c = lg * VEC; c < F; c += LPR * VEC) {
+            Vec<VEC> b, vmax, vmin, vsum, wmean, wm2;
+            b.load(a.ab + (size_t)v * ld + F + c);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) {
+                vmax.v[i] = 0.0f; vmin.v[i] = 0.0f; vsum.v[i] = 0.0f;
+                wmean.v[i] = 0.0f; wm2.v[i] = 0.0f;
+            }
+            for (int k = 0; k < deg; k++) {
+                const int u = __ldg(a.nbr + off + k);
+                Vec<VEC> t;
+                t.load(a.ab + (size_t)u * ld + c);
+                const float cnt = (float)(k + 1);
+#pragma unroll
+                for (int i = 0; i < VEC; i++) {
+                    const float tv = __fadd_rn(t.v[i], b.v[i]);
+                    vmax.v[i] = (k == 0) ? tv : fmaxf(vmax.v[i], tv);
+                    vmin.v[i] = (k == 0) ? tv : fminf(vmin.v[i], tv);
+                    vsum.v[i] = __fadd_rn(vsum.v[i], tv);
+                    const float d = __fsub_rn(tv, wmean.v[i]);                    // lib:693
+                    wmean.v[i] = __fadd_rn(wmean.v[i], __fdiv_rn(d, cnt));        // lib:694
+                    wm2.v[i] = __fadd_rn(wm2.v[i], __fmul_rn(d, __fsub_rn(tv, wmean.v[i])));
+                }
+            }
+            Vec<VEC> o[12];
+#pragma unroll
+            for (int i = 0; i < VEC; i++) {
+                const float mean = deg > 0 ? __fdiv_rn(vsum.v[i], (float)deg) : 0.0f;
+                const float var = __fdiv_rn(wm2.v[i], (float)deg);                 // lib:702
+                const float sd = __fsqrt_rn(__fadd_rn(var, 1e-5f));                // lib:703
+                const float q[4] = {vmax.v[i], vmin.v[i], mean, sd};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    o[j].v[i] = q[j];
+                    o[4 + j].v[i] = __fmul_rn(amp, q[j]);
+                    o[8 + j].v[i] = __fmul_rn(att, q[j]);
+                }
+            }
+            float *dst = a.cat12 + (size_t)v * 12 * F + c;
+#pragma unroll
+            for (int j = 0; j < 12; j++) o[j].store(dst + (size_t)j * F);
+        }
+    }
+}
+
+template <int VEC>
+int launch_pna_lpr(const PnaAggArgs &a, int lpr, int grid, cudaStream_t s)
+{
+    switch (lpr) {
+    case 1: pna_agg_kernel<VEC, 1><<<grid, 256, 0, s>>>(a); break;
+    case 2: pna_agg_kernel<VEC, 2><<<grid, 256, 0, s>>>(a); break;
+    case 4: pna_agg_kernel<VEC, 4><<<grid, 256, 0, s>>>(a); break;
+    case 8: pna_agg_kernel<VEC, 8><<<grid, 256, 0, s>>>(a); break;
+    case 16: pna_agg_kernel<VEC, 16><<<grid, 256, 0, s>>>(a); break;
+    default: pna_agg_kernel<VEC, 32><<<grid, 256, 0, s>>>(a); break;
+    }
+    return GNNB_OK;
+}
+
+}  // namespace
+
+int launch_pna_agg(const PnaAggArgs &a, cudaStream_t s, int *launches)
+{
+    if (a.n <= 0) return GNNB_OK;
+    const bool v4 = (a.F % 4 == 0) && aligned16(a.ab) && aligned16(a.cat12);
+    const int vec = v4 ? 4 : 1;
+    int lpr = 1;
+    while (lpr < 32 && lpr * vec < a.F) lpr *= 2;
+    const int rows_per_block = 8 * (32 / lpr);
+    int64_t grid64 = ceil_div64(a.n, rows_per_block);
+    const int64_t cap = (int64_t)kNumSMs * 8 * 4;
+    const int grid = (int)(grid64 < cap ? grid64 : cap);
+    GNNB_TRY(vec == 4 ? launch_pna_lpr<4>(a, lpr, grid, s) : launch_pna_lpr<1>(a, lpr, grid, s));
+    GNNB_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+    return GNNB_OK;
+}
+
+}  // namespace gnnb

@@ -1,0 +1,90 @@
+// Host-side launchers of the CUDA kernels (internal).
+#pragma once
+
+#include "common.cuh"
+
+namespace gnnb {
+
+// ---------------------------------------------------------------- graph tables (tables.cu)
+struct TableWorkspace {
+    DeviceBuf keys_in, keys_out, vals_in, vals_out, cub_tmp, heavy_rows, counters;
+};
+
+// edge_list [E][2] local ids; node_ptr/edge_ptr (device int64, G+1 entries) translate them to
+// ids in the batch union (pass nullptr for a single graph).  Writes in/out degree, offsets
+// (n entries), neighbor_table (e entries) and, when non-null, edge_index_table.
+// node_base/edge_base: values of node_ptr[0]/edge_ptr[0] when the pointers address a sub-range
+// (chunk) of a larger batch whose x / edge_list pointers were advanced accordingly.
+int build_tables(const int32_t *edge_list, const int64_t *node_ptr, const int64_t *edge_ptr,
+                 int64_t node_base, int64_t edge_base, int n_graphs, int n, int e, int32_t *in_deg, int32_t *out_deg, int32_t *offsets,
+                 int32_t *nbr, int32_t *edge_index, TableWorkspace &ws, cudaStream_t s,
+                 int *launches);
+// degree tables only (lib:1051-1083)
+int build_degree_tables(const int32_t *edge_list, int n, int e, int32_t *in_deg, int32_t *out_deg,
+                        cudaStream_t s, int *launches);
+// offsets + neighbor table from given in-degree (lib:1086-1166)
+int build_neighbor_tables(const int32_t *edge_list, const int32_t *in_deg, int n, int e,
+                          int32_t *offsets, int32_t *nbr, int32_t *edge_index, TableWorkspace &ws,
+                          cudaStream_t s, int *launches);
+// rows with in-degree > threshold, compacted into ws.heavy_rows; count returned through host ptr
+int find_heavy_rows(const int32_t *in_deg, int n, int threshold, TableWorkspace &ws,
+                    int *n_heavy_host, cudaStream_t s, int *launches);
+// dinv[i] = 1 / sqrt(1 + in_deg[i])
+int compute_dinv(const int32_t *in_deg, float *dinv, int n, cudaStream_t s, int *launches);
+
+// ---------------------------------------------------------------- aggregation (agg.cu)
+enum AggMode { AGG_GCN = 0, AGG_GIN = 1, AGG_MEAN = 2, AGG_SUM = 3, AGG_LG = 4 };
+
+struct AggArgs {
+    int mode;
+    const float *x;        // [n][ldx]
+    int ldx;
+    int F;
+    float *out;            // [n][ldo]
+    int ldo;
+    const int32_t *offsets, *nbr, *in_deg;
+    const float *dinv;     // AGG_GCN fast mode only
+    int n;
+    float eps;             // AGG_GIN
+    const int32_t *heavy_rows;  // optional list of rows handled by the CTA-per-row kernel
+    int n_heavy;
+    int heavy_threshold;
+};
+int launch_agg(const AggArgs &a, bool strict, cudaStream_t s, int *launches);
+
+struct PnaAggArgs {
+    const float *ab;       // [n][2F]: cols [0,F) = x.W_nbr^T, cols [F,2F) = x.W_self^T + b_pre
+    int F;
+    float *cat12;          // [n][12F]: (max,min,mean,std) x (identity, amplification, attenuation)
+    const int32_t *offsets, *nbr, *in_deg;
+    int n;
+    float delta;
+};
+int launch_pna_agg(const PnaAggArgs &a, cudaStream_t s, int *launches);
+
+// ---------------------------------------------------------------- GEMM (gemm.cu)
+// C[M][N] = act( A1[M][K1].W1t[K1][N] (+ A2[M][K2].W2t[K2][N]) + bias (+ skip) )
+// weights are pre-transposed: Wt[k][n], row stride ldw (multiple of 4, zero padded)
+struct GemmArgs {
+    const float *A1; int lda1; int K1; const float *W1t; int ldw1;
+    const float *A2; int lda2; int K2; const float *W2t; int ldw2;
+    int second_separate;        // STRICT only: A2.W2t is a separate bias-free sum added last (SAGE)
+    const float *bias;          // [N] or null
+    const float *skip; int ldskip;  // added before the activation, or null
+    int act;
+    float *C; int ldc;
+    int M; int N;
+};
+int launch_gemm(const GemmArgs &g, bool strict, cudaStream_t s, int *launches);
+// Wt[k][n] (ld = ldw) from W[n][k] (reference layout); pads columns n..ldw with zeros
+int launch_transpose_weight(const float *W, float *Wt, int out_size, int in_size, int ldw,
+                            cudaStream_t s, int *launches);
+
+// ---------------------------------------------------------------- pooling / misc (pool.cu)
+// pooled[g][p*F + f] for pools[p] over rows node_ptr[g]..node_ptr[g+1]
+int launch_pool(const float *x, int ldx, int F, const int64_t *node_ptr, int64_t node_base,
+                int n_graphs, int64_t total_nodes, const int *pools, int num_pools, float *pooled,
+                DeviceBuf &tmp, cudaStream_t s, int *launches);
+int launch_activation(int act, const float *x, float *y, size_t n, cudaStream_t s, int *launches);
+
+}  // namespace gnnb

@@ -1,0 +1,406 @@
+// Layer-function entry points: the C-ABI twins of the reference's template functions
+// (gnn_builder_lib.h), same argument order and array layouts, dimensions as runtime ints.
+// They exist so that every function of the hot path can be parity-tested in isolation against
+// the reference; each call stages host buffers, runs the same kernels the model path uses on
+// the default stream, and returns when the results are back.
+#include <vector>
+
+#include "kernels.h"
+
+namespace gnnb {
+
+bool is_device_pointer(const void *p);
+
+namespace {
+
+// Maps caller buffers (host or device) to device pointers for the duration of one call.
+class Stage {
+  public:
+    ~Stage()
+    {
+        for (void *p : owned_) cudaFree(p);
+    }
+    template <typename T>
+    int in(const T *p, size_t count, const T **dev)
+    {
+        *dev = nullptr;
+        if (p == nullptr || count == 0) { *dev = p; return GNNB_OK; }
+        if (is_device_pointer(p)) { *dev = p; return GNNB_OK; }
+        void *d = nullptr;
+        GNNB_CUDA(cudaMalloc(&d, count * sizeof(T)));
+        owned_.push_back(d);
+        GNNB_CUDA(cudaMemcpy(d, p, count * sizeof(T), cudaMemcpyHostToDevice));
+        *dev = static_cast<const T *>(d);
+        return GNNB_OK;
+    }
+    template <typename T>
+    int out(T *p, size_t count, T **dev)
+    {
+        *dev = nullptr;
+        if (p == nullptr || count == 0) { *dev = p; return GNNB_OK; }
+        if (is_device_pointer(p)) { *dev = p; return GNNB_OK; }
+        void *d = nullptr;
+        GNNB_CUDA(cudaMalloc(&d, count * sizeof(T)));
+        owned_.push_back(d);
+        back_.push_back({p, d, count * sizeof(T)});
+        *dev = static_cast<T *>(d);
+        return GNNB_OK;
+    }
+    template <typename T>
+    int scratch(size_t count, T **dev)
+    {
+        void *d = nullptr;
+        GNNB_CUDA(cudaMalloc(&d, (count ? count : 1) * sizeof(T)));
+        owned_.push_back(d);
+        *dev = static_cast<T *>(d);
+        return GNNB_OK;
+    }
+    int finish()
+    {
+        GNNB_CUDA(cudaDeviceSynchronize());
+        for (const Back &b : back_) GNNB_CUDA(cudaMemcpy(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost));
+        return GNNB_OK;
+    }
+
+  private:
+    struct Back { void *host; void *dev; size_t bytes; };
+    std::vector<void *> owned_;
+    std::vector<Back> back_;
+};
+
+struct TempWs {
+    TableWorkspace ws;
+    ~TempWs()
+    {
+        DeviceBuf *b[] = {&ws.keys_in, &ws.keys_out, &ws.vals_in, &ws.vals_out, &ws.cub_tmp,
+                          &ws.heavy_rows, &ws.counters};
+        for (DeviceBuf *x : b) x->release();
+    }
+};
+
+// W[out][in] (reference layout, host or device) -> packed Wt[in][ldw] on the device
+int pack_weight(Stage &st, const float *W, int out, int in, const float **Wt, int *ldw)
+{
+    const float *dW;
+    GNNB_TRY(st.in(W, (size_t)out * in, &dW));
+    float *t;
+    *ldw = round_up(out, 4);
+    GNNB_TRY(st.scratch((size_t)in * *ldw, &t));
+    GNNB_TRY(launch_transpose_weight(dW, t, out, in, *ldw, 0, nullptr));
+    *Wt = t;
+    return GNNB_OK;
+}
+
+GemmArgs simple_gemm(const float *A, int lda, int K, const float *Wt, int ldw, const float *bias,
+                     float *C, int ldc, int M, int N, int act)
+{
+    GemmArgs g{};
+    g.A1 = A; g.lda1 = lda; g.K1 = K; g.W1t = Wt; g.ldw1 = ldw;
+    g.ldw2 = 4;
+    g.bias = bias; g.act = act; g.C = C; g.ldc = ldc; g.M = M; g.N = N;
+    return g;
+}
+
+struct ConvCommon {
+    const float *x; float *y; const int32_t *off, *nbr, *ind;
+};
+
+int stage_conv(Stage &st, int n, int e, const float *x_in, float *x_out, const int32_t *offsets,
+               const int32_t *nbr, const int32_t *in_deg, int fi, int fo, ConvCommon *c)
+{
+    GNNB_REQUIRE(n >= 0 && e >= 0 && fi > 0 && fo > 0, "bad conv dimensions");
+    GNNB_TRY(st.in(x_in, (size_t)n * fi, &c->x));
+    GNNB_TRY(st.out(x_out, (size_t)n * fo, &c->y));
+    GNNB_TRY(st.in(offsets, (size_t)n, &c->off));
+    GNNB_TRY(st.in(nbr, (size_t)e, &c->nbr));
+    GNNB_TRY(st.in(in_deg, (size_t)n, &c->ind));
+    return GNNB_OK;
+}
+
+int pool_common(int kind, int n, const float *x, float *pooled, int emb)
+{
+    GNNB_REQUIRE(n >= 0 && emb > 0 && pooled != nullptr, "bad pooling arguments");
+    Stage st;
+    const float *dx;
+    float *dp;
+    GNNB_TRY(st.in(x, (size_t)n * emb, &dx));
+    GNNB_TRY(st.out(pooled, (size_t)emb, &dp));
+    int64_t *np;
+    GNNB_TRY(st.scratch(2, &np));
+    const int64_t h[2] = {0, n};
+    GNNB_CUDA(cudaMemcpy(np, h, sizeof(h), cudaMemcpyHostToDevice));
+    DeviceBuf tmp;
+    const int pools[1] = {kind};
+    int rc = launch_pool(dx, emb, emb, np, 0, 1, n, pools, 1, dp, tmp, 0, nullptr);
+    if (rc == GNNB_OK) rc = st.finish();
+    tmp.release();
+    return rc;
+}
+
+}  // namespace
+}  // namespace gnnb
+
+using namespace gnnb;
+
+extern "C" int gnnb_compute_degree_tables(const int32_t *edge_list, int32_t *in_degree_table,
+                                          int32_t *out_degree_table, int num_nodes, int num_edges)
+{
+    GNNB_REQUIRE(num_nodes >= 0 && num_edges >= 0, "negative size");
+    Stage st;
+    const int32_t *coo;
+    int32_t *ind, *outd;
+    GNNB_TRY(st.in(edge_list, 2 * (size_t)num_edges, &coo));
+    GNNB_TRY(st.out(in_degree_table, (size_t)num_nodes, &ind));
+    GNNB_TRY(st.out(out_degree_table, (size_t)num_nodes, &outd));
+    GNNB_TRY(build_degree_tables(coo, num_nodes, num_edges, ind, outd, 0, nullptr));
+    return st.finish();
+}
+
+extern "C" int gnnb_compute_neighbor_and_edge_index_tables(
+    const int32_t *edge_list, const int32_t *in_degree_table, const int32_t *out_degree_table,
+    int32_t *neighbor_table_offsets, int32_t *neighbor_table, int32_t *edge_index_table,
+    int num_nodes, int num_edges)
+{
+    (void)out_degree_table;  // threaded through by the reference but never read (lib:1086-1166)
+    GNNB_REQUIRE(num_nodes >= 0 && num_edges >= 0, "negative size");
+    Stage st;
+    TempWs t;
+    const int32_t *coo, *ind;
+    int32_t *off, *nbr, *eidx = nullptr;
+    GNNB_TRY(st.in(edge_list, 2 * (size_t)num_edges, &coo));
+    GNNB_TRY(st.in(in_degree_table, (size_t)num_nodes, &ind));
+    GNNB_TRY(st.out(neighbor_table_offsets, (size_t)num_nodes, &off));
+    GNNB_TRY(st.out(neighbor_table, (size_t)num_edges, &nbr));
+    if (edge_index_table) GNNB_TRY(st.out(edge_index_table, (size_t)num_edges, &eidx));
+    GNNB_TRY(build_neighbor_tables(coo, ind, num_nodes, num_edges, off, nbr, eidx, t.ws, 0, nullptr));
+    return st.finish();
+}
+
+extern "C" int gnnb_compute_neighbor_tables(const int32_t *edge_list, const int32_t *in_degree_table,
+                                            const int32_t *out_degree_table,
+                                            int32_t *neighbor_table_offsets, int32_t *neighbor_table,
+                                            int num_nodes, int num_edges)
+{
+    return gnnb_compute_neighbor_and_edge_index_tables(edge_list, in_degree_table, out_degree_table,
+                                                       neighbor_table_offsets, neighbor_table,
+                                                       nullptr, num_nodes, num_edges);
+}
+
+extern "C" int gnnb_linear(const float *x, float *y, const float *weight, const float *bias,
+                           int rows, int in_size, int out_size, int math)
+{
+    GNNB_REQUIRE(rows >= 0 && in_size > 0 && out_size > 0, "bad linear dimensions");
+    Stage st;
+    const float *dx, *db, *Wt;
+    float *dy;
+    int ldw;
+    GNNB_TRY(st.in(x, (size_t)rows * in_size, &dx));
+    GNNB_TRY(st.in(bias, (size_t)out_size, &db));
+    GNNB_TRY(st.out(y, (size_t)rows * out_size, &dy));
+    GNNB_TRY(pack_weight(st, weight, out_size, in_size, &Wt, &ldw));
+    GemmArgs g = simple_gemm(dx, in_size, in_size, Wt, ldw, db, dy, out_size, rows, out_size,
+                             GNNB_ACT_IDENTITY);
+    GNNB_TRY(launch_gemm(g, math == GNNB_MATH_STRICT, 0, nullptr));
+    return st.finish();
+}
+
+extern "C" int gnnb_apply_activation(int act, const float *x, float *y, size_t n)
+{
+    GNNB_REQUIRE(act >= 0 && act <= GNNB_ACT_COS, "unknown activation");
+    Stage st;
+    const float *dx;
+    float *dy;
+    GNNB_TRY(st.in(x, n, &dx));
+    GNNB_TRY(st.out(y, n, &dy));
+    GNNB_TRY(launch_activation(act, dx, dy, n, 0, nullptr));
+    return st.finish();
+}
+
+extern "C" int gnnb_gcn_conv(int num_nodes, int num_edges, const float *x_in, float *x_out,
+                             const int32_t *edge_list, const int32_t *neighbor_table_offsets,
+                             const int32_t *neighbor_table, const int32_t *in_degree_table,
+                             const int32_t *out_degree_table, const float *weight, const float *bias,
+                             int emb_in, int emb_out, int math)
+{
+    (void)edge_list; (void)out_degree_table;  // unused by the reference body as well
+    const bool strict = math == GNNB_MATH_STRICT;
+    Stage st;
+    ConvCommon c;
+    GNNB_TRY(stage_conv(st, num_nodes, num_edges, x_in, x_out, neighbor_table_offsets,
+                        neighbor_table, in_degree_table, emb_in, emb_out, &c));
+    const float *Wt, *db;
+    int ldw;
+    GNNB_TRY(pack_weight(st, weight, emb_out, emb_in, &Wt, &ldw));
+    GNNB_TRY(st.in(bias, (size_t)emb_out, &db));
+    float *agg, *dinv = nullptr;
+    const int lda = round_up(emb_in, 4);
+    GNNB_TRY(st.scratch((size_t)num_nodes * lda, &agg));
+    if (!strict) {
+        GNNB_TRY(st.scratch((size_t)num_nodes, &dinv));
+        GNNB_TRY(compute_dinv(c.ind, dinv, num_nodes, 0, nullptr));
+    }
+    AggArgs a{};
+    a.mode = AGG_GCN; a.x = c.x; a.ldx = emb_in; a.F = emb_in; a.out = agg; a.ldo = lda;
+    a.offsets = c.off; a.nbr = c.nbr; a.in_deg = c.ind; a.dinv = dinv; a.n = num_nodes;
+    GNNB_TRY(launch_agg(a, strict, 0, nullptr));
+    GemmArgs g = simple_gemm(agg, lda, emb_in, Wt, ldw, db, c.y, emb_out, num_nodes, emb_out,
+                             GNNB_ACT_IDENTITY);
+    GNNB_TRY(launch_gemm(g, strict, 0, nullptr));
+    return st.finish();
+}
+
+extern "C" int gnnb_gin_conv(int num_nodes, int num_edges, const float *x_in, float *x_out,
+                             const int32_t *edge_list, const int32_t *neighbor_table_offsets,
+                             const int32_t *neighbor_table, const int32_t *in_degree_table,
+                             const int32_t *out_degree_table, const float *mlp_0_weight,
+                             const float *mlp_0_bias, const float *mlp_1_weight,
+                             const float *mlp_1_bias, float gin_eps, int emb_in, int hidden,
+                             int emb_out, int math)
+{
+    (void)edge_list; (void)out_degree_table;
+    GNNB_REQUIRE(hidden > 0, "bad hidden size");
+    const bool strict = math == GNNB_MATH_STRICT;
+    Stage st;
+    ConvCommon c;
+    GNNB_TRY(stage_conv(st, num_nodes, num_edges, x_in, x_out, neighbor_table_offsets,
+                        neighbor_table, in_degree_table, emb_in, emb_out, &c));
+    const float *W0t, *W1t, *b0, *b1;
+    int ld0, ld1;
+    GNNB_TRY(pack_weight(st, mlp_0_weight, hidden, emb_in, &W0t, &ld0));
+    GNNB_TRY(pack_weight(st, mlp_1_weight, emb_out, hidden, &W1t, &ld1));
+    GNNB_TRY(st.in(mlp_0_bias, (size_t)hidden, &b0));
+    GNNB_TRY(st.in(mlp_1_bias, (size_t)emb_out, &b1));
+    float *agg, *hid;
+    const int lda = round_up(emb_in, 4), ldh = round_up(hidden, 4);
+    GNNB_TRY(st.scratch((size_t)num_nodes * lda, &agg));
+    GNNB_TRY(st.scratch((size_t)num_nodes * ldh, &hid));
+    AggArgs a{};
+    a.mode = AGG_GIN; a.x = c.x; a.ldx = emb_in; a.F = emb_in; a.out = agg; a.ldo = lda;
+    a.offsets = c.off; a.nbr = c.nbr; a.in_deg = c.ind; a.n = num_nodes; a.eps = gin_eps;
+    GNNB_TRY(launch_agg(a, strict, 0, nullptr));
+    GemmArgs g0 = simple_gemm(agg, lda, emb_in, W0t, ld0, b0, hid, ldh, num_nodes, hidden,
+                              GNNB_ACT_RELU);
+    GNNB_TRY(launch_gemm(g0, strict, 0, nullptr));
+    GemmArgs g1 = simple_gemm(hid, ldh, hidden, W1t, ld1, b1, c.y, emb_out, num_nodes, emb_out,
+                              GNNB_ACT_IDENTITY);
+    GNNB_TRY(launch_gemm(g1, strict, 0, nullptr));
+    return st.finish();
+}
+
+extern "C" int gnnb_sage_conv(int num_nodes, int num_edges, const float *x_in, float *x_out,
+                              const int32_t *edge_list, const int32_t *neighbor_table_offsets,
+                              const int32_t *neighbor_table, const int32_t *in_degree_table,
+                              const int32_t *out_degree_table, const float *neighbor_lin_weight,
+                              const float *neighbor_lin_bias, const float *self_lin_weight,
+                              int emb_in, int emb_out, int math)
+{
+    (void)edge_list; (void)out_degree_table;
+    const bool strict = math == GNNB_MATH_STRICT;
+    Stage st;
+    ConvCommon c;
+    GNNB_TRY(stage_conv(st, num_nodes, num_edges, x_in, x_out, neighbor_table_offsets,
+                        neighbor_table, in_degree_table, emb_in, emb_out, &c));
+    const float *Wlt, *Wrt, *bl;
+    int ldl, ldr;
+    GNNB_TRY(pack_weight(st, neighbor_lin_weight, emb_out, emb_in, &Wlt, &ldl));
+    GNNB_TRY(pack_weight(st, self_lin_weight, emb_out, emb_in, &Wrt, &ldr));
+    GNNB_TRY(st.in(neighbor_lin_bias, (size_t)emb_out, &bl));
+    float *agg;
+    const int lda = round_up(emb_in, 4);
+    GNNB_TRY(st.scratch((size_t)num_nodes * lda, &agg));
+    AggArgs a{};
+    a.mode = AGG_MEAN; a.x = c.x; a.ldx = emb_in; a.F = emb_in; a.out = agg; a.ldo = lda;
+    a.offsets = c.off; a.nbr = c.nbr; a.in_deg = c.ind; a.n = num_nodes;
+    GNNB_TRY(launch_agg(a, strict, 0, nullptr));
+    GemmArgs g = simple_gemm(agg, lda, emb_in, Wlt, ldl, bl, c.y, emb_out, num_nodes, emb_out,
+                             GNNB_ACT_IDENTITY);
+    g.A2 = c.x; g.lda2 = emb_in; g.K2 = emb_in; g.W2t = Wrt; g.ldw2 = ldr;
+    g.second_separate = 1;
+    GNNB_TRY(launch_gemm(g, strict, 0, nullptr));
+    return st.finish();
+}
+
+extern "C" int gnnb_pna_conv(int num_nodes, int num_edges, const float *x_in, float *x_out,
+                             const int32_t *edge_list, const int32_t *neighbor_table_offsets,
+                             const int32_t *neighbor_table, const int32_t *in_degree_table,
+                             const int32_t *out_degree_table, const float *transform_lin_weight,
+                             const float *transform_lin_bias, const float *apply_lin_weight,
+                             const float *apply_lin_bias, const float *final_lin_weight,
+                             const float *final_lin_bias, float pna_avg_degree_log, int emb_in,
+                             int emb_out)
+{
+    (void)edge_list; (void)out_degree_table;
+    Stage st;
+    ConvCommon c;
+    GNNB_TRY(stage_conv(st, num_nodes, num_edges, x_in, x_out, neighbor_table_offsets,
+                        neighbor_table, in_degree_table, emb_in, emb_out, &c));
+    const int F = emb_in, n = num_nodes;
+    // host-side split of W_pre = [W_self | W_nbr] needs the weights on the host
+    std::vector<float> wpre((size_t)F * 2 * F), bpre(F), wpost((size_t)emb_out * 13 * F);
+    auto fetch = [](const float *src, float *dst, size_t cnt) -> int {
+        GNNB_CUDA(cudaMemcpy(dst, src, cnt * sizeof(float), cudaMemcpyDefault));
+        return GNNB_OK;
+    };
+    GNNB_TRY(fetch(transform_lin_weight, wpre.data(), wpre.size()));
+    GNNB_TRY(fetch(transform_lin_bias, bpre.data(), bpre.size()));
+    GNNB_TRY(fetch(apply_lin_weight, wpost.data(), wpost.size()));
+    const int ld_ab = round_up(2 * F, 4), ld_o = round_up(emb_out, 4);
+    std::vector<float> wab((size_t)F * ld_ab, 0.0f), bab((size_t)2 * F, 0.0f);
+    std::vector<float> wself((size_t)F * ld_o, 0.0f), wagg((size_t)12 * F * ld_o, 0.0f);
+    for (int k = 0; k < F; k++)
+        for (int o = 0; o < F; o++) {
+            wab[(size_t)k * ld_ab + o] = wpre[(size_t)o * 2 * F + F + k];      // W_nbr^T
+            wab[(size_t)k * ld_ab + F + o] = wpre[(size_t)o * 2 * F + k];      // W_self^T
+        }
+    for (int o = 0; o < F; o++) bab[F + o] = bpre[o];
+    for (int o = 0; o < emb_out; o++) {
+        for (int k = 0; k < F; k++) wself[(size_t)k * ld_o + o] = wpost[(size_t)o * 13 * F + k];
+        for (int k = 0; k < 12 * F; k++) wagg[(size_t)k * ld_o + o] = wpost[(size_t)o * 13 * F + F + k];
+    }
+    const float *d_wab, *d_bab, *d_wself, *d_wagg, *d_bpost, *d_blin, *Wlint;
+    int ldlin;
+    GNNB_TRY(st.in(wab.data(), wab.size(), &d_wab));
+    GNNB_TRY(st.in(bab.data(), bab.size(), &d_bab));
+    GNNB_TRY(st.in(wself.data(), wself.size(), &d_wself));
+    GNNB_TRY(st.in(wagg.data(), wagg.size(), &d_wagg));
+    GNNB_TRY(st.in(apply_lin_bias, (size_t)emb_out, &d_bpost));
+    GNNB_TRY(st.in(final_lin_bias, (size_t)emb_out, &d_blin));
+    GNNB_TRY(pack_weight(st, final_lin_weight, emb_out, emb_out, &Wlint, &ldlin));
+    float *ab, *cat12, *hid;
+    GNNB_TRY(st.scratch((size_t)n * 2 * F + 4, &ab));
+    GNNB_TRY(st.scratch((size_t)n * 12 * F + 4, &cat12));
+    GNNB_TRY(st.scratch((size_t)n * ld_o, &hid));
+    GemmArgs g0 = simple_gemm(c.x, F, F, d_wab, ld_ab, d_bab, ab, 2 * F, n, 2 * F, GNNB_ACT_IDENTITY);
+    GNNB_TRY(launch_gemm(g0, false, 0, nullptr));
+    PnaAggArgs pa{};
+    pa.ab = ab; pa.F = F; pa.cat12 = cat12; pa.offsets = c.off; pa.nbr = c.nbr; pa.in_deg = c.ind;
+    pa.n = n; pa.delta = pna_avg_degree_log;
+    GNNB_TRY(launch_pna_agg(pa, 0, nullptr));
+    GemmArgs g1 = simple_gemm(c.x, F, F, d_wself, ld_o, d_bpost, hid, ld_o, n, emb_out,
+                              GNNB_ACT_IDENTITY);
+    g1.A2 = cat12; g1.lda2 = 12 * F; g1.K2 = 12 * F; g1.W2t = d_wagg; g1.ldw2 = ld_o;
+    GNNB_TRY(launch_gemm(g1, false, 0, nullptr));
+    GemmArgs g2 = simple_gemm(hid, ld_o, emb_out, Wlint, ldlin, d_blin, c.y, emb_out, n, emb_out,
+                              GNNB_ACT_IDENTITY);
+    GNNB_TRY(launch_gemm(g2, false, 0, nullptr));
+    return st.finish();
+}
+
+extern "C" int gnnb_global_add_pool(int num_nodes, int num_edges, const float *x, float *pooled,
+                                    int emb)
+{
+    (void)num_edges;
+    return pool_common(GNNB_POOL_ADD, num_nodes, x, pooled, emb);
+}
+extern "C" int gnnb_global_mean_pool(int num_nodes, int num_edges, const float *x, float *pooled,
+                                     int emb)
+{
+    (void)num_edges;
+    return pool_common(GNNB_POOL_MEAN, num_nodes, x, pooled, emb);
+}
+extern "C" int gnnb_global_max_pool(int num_nodes, int num_edges, const float *x, float *pooled,
+                                    int emb)
+{
+    (void)num_edges;
+    return pool_common(GNNB_POOL_MAX, num_nodes, x, pooled, emb);
+}

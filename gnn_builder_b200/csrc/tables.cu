@@ -1,0 +1,237 @@
+// Degree / neighbor tables: gnn_builder_lib.h:1051-1166 on the GPU.
+//
+// Reference semantics: in/out degree histograms of the COO list; offsets = exclusive scan of the
+// in-degree (n entries, no sentinel); neighbor_table = sources grouped by destination, STABLE in
+// COO order (the serial cursor walk of lib:1113-1123).  Here: one pass of integer atomics for the
+// histograms, an exclusive scan, and a stable LSD radix sort of (destination -> source) pairs --
+// a stable sort by destination is exactly the cursor walk's output, so the tables are bit-exact
+// for any graph size.  (The fused molecular kernel builds its tables in shared memory instead,
+// see fused.cu.)  The scan and the radix sort are cub:: device primitives from the CUDA toolkit.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "kernels.h"
+
+namespace gnnb {
+
+namespace {
+
+__device__ __forceinline__ int find_segment(const int64_t *__restrict__ ptr, int n_seg, int64_t i)
+{
+    // largest g with ptr[g] <= i   (ptr has n_seg + 1 entries, ptr[0] = 0)
+    int lo = 0, hi = n_seg;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(ptr + mid) <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// keys = destination (union ids), vals = source (union ids) or the edge index
+template <bool COUNT, bool VAL_IS_EDGE_INDEX>
+__global__ void edge_prepare_kernel(const int32_t *__restrict__ edge_list,
+                                    const int64_t *__restrict__ node_ptr,
+                                    const int64_t *__restrict__ edge_ptr, int64_t node_base,
+                                    int64_t edge_base, int n_graphs, int e,
+                                    uint32_t *__restrict__ keys, int32_t *__restrict__ vals,
+                                    int32_t *__restrict__ in_deg, int32_t *__restrict__ out_deg)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
+        const int2 sd = __ldg(reinterpret_cast<const int2 *>(edge_list) + i);
+        int src = sd.x, dst = sd.y;
+        if (node_ptr != nullptr) {
+            const int g = find_segment(edge_ptr, n_graphs, (int64_t)i + edge_base);
+            const int base = (int)(__ldg(node_ptr + g) - node_base);
+            src += base;
+            dst += base;
+        }
+        if (keys) {
+            keys[i] = (uint32_t)dst;
+            vals[i] = VAL_IS_EDGE_INDEX ? i : src;
+        }
+        if (COUNT) {
+            atomicAdd(in_deg + dst, 1);
+            atomicAdd(out_deg + src, 1);
+        }
+    }
+}
+
+__global__ void gather_sources_kernel(const int32_t *__restrict__ edge_list,
+                                      const int32_t *__restrict__ edge_index, int e,
+                                      int32_t *__restrict__ nbr)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x)
+        nbr[i] = __ldg(edge_list + 2 * (size_t)__ldg(edge_index + i));
+}
+
+__global__ void heavy_rows_kernel(const int32_t *__restrict__ in_deg, int n, int threshold,
+                                  int32_t *__restrict__ rows, int32_t *__restrict__ counter)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (__ldg(in_deg + i) > threshold) rows[atomicAdd(counter, 1)] = i;
+}
+
+__global__ void dinv_kernel(const int32_t *__restrict__ in_deg, float *__restrict__ dinv, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dinv[i] = 1.0f / sqrtf(1.0f + (float)__ldg(in_deg + i));
+}
+
+inline int grid_for(int64_t work, int block)
+{
+    int64_t g = ceil_div64(work, block);
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+int bits_for(int n)
+{
+    int b = 1;
+    while (b < 32 && (1ll << b) < (int64_t)n) ++b;
+    return b;
+}
+
+int scan_offsets(const int32_t *in_deg, int32_t *offsets, int n, TableWorkspace &ws, cudaStream_t s,
+                 int *launches)
+{
+    size_t tmp = 0;
+    GNNB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in_deg, offsets, n, s));
+    GNNB_TRY(ws.cub_tmp.ensure(tmp));
+    GNNB_CUDA(cub::DeviceScan::ExclusiveSum(ws.cub_tmp.ptr, tmp, in_deg, offsets, n, s));
+    if (launches) *launches += 2;
+    return GNNB_OK;
+}
+
+int sort_pairs(TableWorkspace &ws, int e, int n, int32_t *vals_out, cudaStream_t s, int *launches)
+{
+    size_t tmp = 0;
+    const int end_bit = bits_for(n);
+    GNNB_TRY(ws.keys_out.ensure(sizeof(uint32_t) * (size_t)e));
+    GNNB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, ws.keys_in.as<uint32_t>(),
+                                              ws.keys_out.as<uint32_t>(), ws.vals_in.as<int32_t>(),
+                                              vals_out, e, 0, end_bit, s));
+    GNNB_TRY(ws.cub_tmp.ensure(tmp));
+    GNNB_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_tmp.ptr, tmp, ws.keys_in.as<uint32_t>(),
+                                              ws.keys_out.as<uint32_t>(), ws.vals_in.as<int32_t>(),
+                                              vals_out, e, 0, end_bit, s));
+    if (launches) *launches += 1 + 2 * ((end_bit + 7) / 8);
+    return GNNB_OK;
+}
+
+}  // namespace
+
+int build_degree_tables(const int32_t *edge_list, int n, int e, int32_t *in_deg, int32_t *out_deg,
+                        cudaStream_t s, int *launches)
+{
+    if (n > 0) {
+        GNNB_CUDA(cudaMemsetAsync(in_deg, 0, sizeof(int32_t) * (size_t)n, s));
+        GNNB_CUDA(cudaMemsetAsync(out_deg, 0, sizeof(int32_t) * (size_t)n, s));
+    }
+    if (e > 0) {
+        edge_prepare_kernel<true, false><<<grid_for(e, 256), 256, 0, s>>>(
+            edge_list, nullptr, nullptr, 0, 0, 0, e, nullptr, nullptr, in_deg, out_deg);
+        GNNB_CUDA(cudaGetLastError());
+        if (launches) ++*launches;
+    }
+    return GNNB_OK;
+}
+
+int build_neighbor_tables(const int32_t *edge_list, const int32_t *in_deg, int n, int e,
+                          int32_t *offsets, int32_t *nbr, int32_t *edge_index, TableWorkspace &ws,
+                          cudaStream_t s, int *launches)
+{
+    if (n <= 0) return GNNB_OK;
+    GNNB_TRY(scan_offsets(in_deg, offsets, n, ws, s, launches));
+    if (e <= 0) return GNNB_OK;
+    GNNB_TRY(ws.keys_in.ensure(sizeof(uint32_t) * (size_t)e));
+    GNNB_TRY(ws.vals_in.ensure(sizeof(int32_t) * (size_t)e));
+    if (edge_index) {
+        edge_prepare_kernel<false, true><<<grid_for(e, 256), 256, 0, s>>>(
+            edge_list, nullptr, nullptr, 0, 0, 0, e, ws.keys_in.as<uint32_t>(), ws.vals_in.as<int32_t>(),
+            nullptr, nullptr);
+        GNNB_CUDA(cudaGetLastError());
+        GNNB_TRY(sort_pairs(ws, e, n, edge_index, s, launches));
+        gather_sources_kernel<<<grid_for(e, 256), 256, 0, s>>>(edge_list, edge_index, e, nbr);
+        GNNB_CUDA(cudaGetLastError());
+        if (launches) *launches += 2;
+    } else {
+        edge_prepare_kernel<false, false><<<grid_for(e, 256), 256, 0, s>>>(
+            edge_list, nullptr, nullptr, 0, 0, 0, e, ws.keys_in.as<uint32_t>(), ws.vals_in.as<int32_t>(),
+            nullptr, nullptr);
+        GNNB_CUDA(cudaGetLastError());
+        GNNB_TRY(sort_pairs(ws, e, n, nbr, s, launches));
+        if (launches) ++*launches;
+    }
+    return GNNB_OK;
+}
+
+int build_tables(const int32_t *edge_list, const int64_t *node_ptr, const int64_t *edge_ptr,
+                 int64_t node_base, int64_t edge_base, int n_graphs, int n, int e, int32_t *in_deg, int32_t *out_deg, int32_t *offsets,
+                 int32_t *nbr, int32_t *edge_index, TableWorkspace &ws, cudaStream_t s,
+                 int *launches)
+{
+    if (n <= 0) return GNNB_OK;
+    GNNB_CUDA(cudaMemsetAsync(in_deg, 0, sizeof(int32_t) * (size_t)n, s));
+    GNNB_CUDA(cudaMemsetAsync(out_deg, 0, sizeof(int32_t) * (size_t)n, s));
+    if (e > 0) {
+        GNNB_TRY(ws.keys_in.ensure(sizeof(uint32_t) * (size_t)e));
+        GNNB_TRY(ws.vals_in.ensure(sizeof(int32_t) * (size_t)e));
+        if (edge_index) {
+            GNNB_REQUIRE(node_ptr == nullptr, "edge-index tables are single-graph only");
+            edge_prepare_kernel<true, true><<<grid_for(e, 256), 256, 0, s>>>(
+                edge_list, nullptr, nullptr, 0, 0, 0, e, ws.keys_in.as<uint32_t>(),
+                ws.vals_in.as<int32_t>(), in_deg, out_deg);
+        } else {
+            edge_prepare_kernel<true, false><<<grid_for(e, 256), 256, 0, s>>>(
+                edge_list, node_ptr, edge_ptr, node_base, edge_base, n_graphs, e,
+                ws.keys_in.as<uint32_t>(),
+                ws.vals_in.as<int32_t>(), in_deg, out_deg);
+        }
+        GNNB_CUDA(cudaGetLastError());
+        if (launches) ++*launches;
+    }
+    GNNB_TRY(scan_offsets(in_deg, offsets, n, ws, s, launches));
+    if (e > 0) {
+        if (edge_index) {
+            GNNB_TRY(sort_pairs(ws, e, n, edge_index, s, launches));
+            gather_sources_kernel<<<grid_for(e, 256), 256, 0, s>>>(edge_list, edge_index, e, nbr);
+            GNNB_CUDA(cudaGetLastError());
+            if (launches) ++*launches;
+        } else {
+            GNNB_TRY(sort_pairs(ws, e, n, nbr, s, launches));
+        }
+    }
+    return GNNB_OK;
+}
+
+int find_heavy_rows(const int32_t *in_deg, int n, int threshold, TableWorkspace &ws,
+                    int *n_heavy_host, cudaStream_t s, int *launches)
+{
+    *n_heavy_host = 0;
+    if (n <= 0) return GNNB_OK;
+    GNNB_TRY(ws.heavy_rows.ensure(sizeof(int32_t) * (size_t)n));
+    GNNB_TRY(ws.counters.ensure(sizeof(int32_t) * 4));
+    GNNB_CUDA(cudaMemsetAsync(ws.counters.ptr, 0, sizeof(int32_t) * 4, s));
+    heavy_rows_kernel<<<grid_for(n, 256), 256, 0, s>>>(in_deg, n, threshold,
+                                                      ws.heavy_rows.as<int32_t>(),
+                                                      ws.counters.as<int32_t>());
+    GNNB_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+    GNNB_CUDA(cudaMemcpyAsync(n_heavy_host, ws.counters.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                              s));
+    GNNB_CUDA(cudaStreamSynchronize(s));
+    return GNNB_OK;
+}
+
+int compute_dinv(const int32_t *in_deg, float *dinv, int n, cudaStream_t s, int *launches)
+{
+    if (n <= 0) return GNNB_OK;
+    dinv_kernel<<<grid_for(n, 256), 256, 0, s>>>(in_deg, dinv, n);
+    GNNB_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+    return GNNB_OK;
+}
+
+}  // namespace gnnb

@@ -1,0 +1,186 @@
+"""GPU parity, whole model: gnnb_model_run_batch / run_graph (both kernels) against
+
+  * the committed outputs of the reference's own generated <name>_top (tests/golden/models),
+  * the CPU oracle on larger seeded batches,
+  * size-independent properties at BASELINE.json's full batch size.
+"""
+import numpy as np
+import pytest
+
+from conftest import MODEL_NAMES, load_model_golden, model_and_params, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # north star: <= 1e-4 relative in fp32
+
+
+@pytest.fixture(scope="module")
+def gnnb():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import gnn_builder_b200
+
+    return gnn_builder_b200
+
+
+def _paths(gnnb, eng, batch):
+    """run through every path the engine supports for this batch"""
+    outs = {}
+    eng.set_path(gnnb.PATH_LAYERWISE)
+    outs["layerwise"] = eng.run(batch)
+    assert eng.last_path == gnnb.PATH_LAYERWISE and eng.last_launches > 0
+    eng.set_path(gnnb.PATH_AUTO)
+    outs["auto"] = eng.run(batch)
+    if eng.last_path == gnnb.PATH_FUSED:
+        assert eng.last_launches > 0
+        outs["fused"] = outs["auto"]
+    return outs
+
+
+@pytest.mark.parametrize("name", [m + s for m in MODEL_NAMES for s in ("_small", "")])
+def test_golden_reference_top(gnnb, name):
+    batch, gold, _, _ = load_model_golden(name)
+    w, model, params = model_and_params(name)
+    with gnnb.Engine(model, max_nodes=w.max_nodes, max_edges=w.max_edges) as eng:
+        for path, out in _paths(gnnb, eng, batch).items():
+            assert rel_err(out, gold) < TOL, (name, path, rel_err(out, gold))
+        # one graph per call, the way <name>_top is called (model_tb.cpp.jinja:189-204)
+        for g in range(min(4, batch.n_graphs)):
+            assert rel_err(eng.run_graph(*batch.graph(g)), gold[g]) < TOL
+
+
+@pytest.mark.parametrize("name", ["c1_gcn_esol", "c2_gin_qm9", "c3_sage_hiv"])
+def test_strict_mode_bit_identical_to_reference(gnnb, name):
+    """STRICT math: same operation order, no FMA contraction => the reference's bits."""
+    for nm in (name + "_small", name):
+        batch, gold, _, _ = load_model_golden(nm)
+        w, model, _ = model_and_params(nm)
+        with gnnb.Engine(model, path=gnnb.PATH_LAYERWISE, math=gnnb.MATH_STRICT) as eng:
+            assert np.array_equal(eng.run(batch), gold), nm
+
+
+@pytest.mark.parametrize("name", MODEL_NAMES)
+def test_batch_vs_oracle(gnnb, orc, name):
+    w, model, params = model_and_params(name)
+    batch = gnnb.make_molecular_batch(600, w.mu_nodes, w.mu_edges, w.in_dim, seed=77 + w.seed)
+    ref = orc.model_forward_batch(model.describe(), list(params.values()), batch)
+    with gnnb.Engine(model) as eng:
+        for path, out in _paths(gnnb, eng, batch).items():
+            assert rel_err(out, ref) < TOL, (name, path, rel_err(out, ref))
+        if eng.last_path == gnnb.PATH_LAYERWISE:
+            pytest.skip("fused kernel not available for this model")
+
+
+def test_edge_cases(gnnb, orc):
+    """ragged batch: 1-node graphs without edges, an empty edge list, a graph at the capacity
+    limit, duplicate edges and self loops"""
+    w, model, params = model_and_params("c2_gin_qm9_small")
+    rng = np.random.default_rng(4)
+    graphs = []
+    graphs.append((rng.uniform(-1, 1, (1, w.in_dim)), np.zeros((0, 2), np.int32)))
+    graphs.append((rng.uniform(-1, 1, (5, w.in_dim)), np.zeros((0, 2), np.int32)))
+    graphs.append((rng.uniform(-1, 1, (2, w.in_dim)), np.array([[0, 1], [0, 1], [1, 1]], np.int32)))
+    n = 60
+    graphs.append((rng.uniform(-1, 1, (n, w.in_dim)),
+                   np.stack([rng.integers(0, n, 240), rng.integers(0, n, 240)], 1)))
+    graphs.append((rng.uniform(-1, 1, (3, w.in_dim)), np.array([[2, 0]], np.int32)))
+    batch = gnnb.GraphBatch.from_graphs(graphs)
+    ref = orc.model_forward_batch(model.describe(), list(params.values()), batch)
+    with gnnb.Engine(model, max_nodes=64, max_edges=256) as eng:
+        for path, out in _paths(gnnb, eng, batch).items():
+            assert rel_err(out, ref) < TOL, path
+        # capacity violations are errors, not undefined behaviour like the reference
+        big = gnnb.GraphBatch.from_graphs([(rng.uniform(-1, 1, (65, w.in_dim)),
+                                            np.zeros((0, 2), np.int32))])
+        with pytest.raises(gnnb._lib.GnnbError):
+            eng.run(big)
+        assert eng.run(gnnb.GraphBatch.from_graphs(graphs[:1])).shape == (1, w.out_dim)
+
+
+def test_pna_zero_in_degree_gives_nan_like_reference(gnnb, orc):
+    w, model, params = model_and_params("c4_pna_lipo_small")
+    x = np.random.default_rng(1).uniform(-1, 1, (4, w.in_dim)).astype(np.float32)
+    coo = np.array([[0, 1], [1, 2], [2, 1]], np.int32)   # nodes 0 and 3 have no in-edges
+    ref = orc.model_forward(model.describe(), list(params.values()), x, coo)
+    assert np.isnan(ref).all()
+    with gnnb.Engine(model, path=gnnb.PATH_LAYERWISE) as eng:
+        assert np.isnan(eng.run_graph(x, coo)).all()
+
+
+def test_medium_graphs_use_layerwise(gnnb, orc):
+    """graphs larger than a CTA tile (HIV has molecules of 222 atoms) fall back to kernel (2)"""
+    w, model, params = model_and_params("c3_sage_hiv")
+    batch = gnnb.make_molecular_batch(6, 300, 640, w.in_dim, seed=5, max_nodes=600)
+    ref = orc.model_forward_batch(model.describe(), list(params.values()), batch)
+    with gnnb.Engine(model) as eng:
+        out = eng.run(batch)
+        assert eng.last_path == gnnb.PATH_LAYERWISE
+        assert rel_err(out, ref) < TOL
+        emb = eng.node_embeddings(batch.total_nodes)
+        _, ref_emb = orc.model_forward(model.describe(), list(params.values()), *batch.graph(0),
+                                       return_node_emb=True)
+        assert rel_err(emb[: ref_emb.shape[0]], ref_emb) < TOL
+
+
+def test_device_pointer_api(gnnb, orc):
+    import torch
+
+    w, model, params = model_and_params("c2_gin_qm9")
+    batch = gnnb.make_molecular_batch(300, w.mu_nodes, w.mu_edges, w.in_dim, seed=12)
+    ref = orc.model_forward_batch(model.describe(), list(params.values()), batch)
+    dx, dcoo = torch.from_numpy(batch.x).cuda(), torch.from_numpy(batch.coo).cuda()
+    dn, de = torch.from_numpy(batch.node_ptr).cuda(), torch.from_numpy(batch.edge_ptr).cuda()
+    out = torch.empty((batch.n_graphs, w.out_dim), device="cuda")
+    with gnnb.Engine(model, max_nodes=64, max_edges=256) as eng:
+        eng.run_device_sync(dx, dcoo, dn, de, out, batch.n_graphs)
+        assert rel_err(out.cpu().numpy(), ref) < TOL
+        out.zero_()
+        eng.run_device(dx, dcoo, dn, de, out, batch.n_graphs, batch.total_nodes,
+                       batch.total_edges, sync=True)
+        assert rel_err(out.cpu().numpy(), ref) < TOL
+
+
+def test_full_size_properties_c2(gnnb, orc):
+    """BASELINE config 2 at full size (1M QM9-shaped graphs): outputs do not depend on batch
+    composition (a graph's result is bit-identical alone, in a slice, or in the full batch), and
+    a random sample agrees with the oracle."""
+    from gnn_builder_b200.configs import C2
+
+    w, model, params = model_and_params("c2_gin_qm9")
+    batch = gnnb.make_molecular_batch(C2.n_graphs, w.mu_nodes, w.mu_edges, w.in_dim, seed=w.seed)
+    with gnnb.Engine(model, max_nodes=w.max_nodes, max_edges=w.max_edges) as eng:
+        out = eng.run(batch)
+        assert out.shape == (C2.n_graphs, w.out_dim) and np.isfinite(out).all()
+        path = eng.last_path
+        rng = np.random.default_rng(0)
+        idx = np.sort(rng.choice(C2.n_graphs, 48, replace=False))
+        sample = gnnb.GraphBatch.from_graphs([batch.graph(int(g)) for g in idx])
+        ref = orc.model_forward_batch(model.describe(), list(params.values()), sample)
+        assert rel_err(out[idx], ref) < TOL
+        sl = batch.slice(500_000, 500_200)
+        out_sl = eng.run(sl)
+        assert eng.last_path == path
+        assert np.array_equal(out_sl, out[500_000:500_200])
+        # duplicated graphs give identical rows
+        dup = gnnb.GraphBatch.from_graphs([batch.graph(3)] * 5)
+        o = eng.run(dup)
+        assert all(np.array_equal(o[0], o[i]) for i in range(5))
+
+
+def test_project_flow(gnnb, tmp_path):
+    """the reference's user-facing call sequence (demos/demo.py:102-129)"""
+    w, model, params = model_and_params("c1_gcn_esol")
+    ds = gnnb.make_molecular_batch(20, w.mu_nodes, w.mu_edges, w.in_dim, seed=8)
+    proj = gnnb.Project("gcn_esol", model, "regression", None, tmp_path, dataset=ds, max_nodes=600,
+                        max_edges=600, float_or_fixed="float")
+    proj.gen_hw_model()
+    proj.gen_testbench()
+    proj.gen_makefile()
+    data = proj.build_and_run_testbench()
+    assert set(data) == {"model_output_mae", "model_runtime"}
+    assert data["model_output_mae"] < 1e-5 and data["model_runtime"] > 0
+    data_b = proj.build_and_run_testbench(batched=True)
+    assert data_b["model_output_mae"] < 1e-5
+    with pytest.raises(NotImplementedError):
+        proj.run_vitis_hls_synthesis()
