@@ -324,8 +324,8 @@ __global__ void __launch_bounds__(256) pna_agg_kernel(const PnaAggArgs a)
 #pragma unroll
                 for (int i = 0; i < VEC; i++) {
                     const float tv = __fadd_rn(t.v[i], b.v[i]);
-                    vmax.v[i] = (k == 0) ? tv : fmaxf(vmax.v[i], tv);
-                    vmin.v[i] = (k == 0) ? tv : fminf(vmin.v[i], tv);
+                    vmax.v[i] = (k == 0 || tv > vmax.v[i]) ? tv : vmax.v[i];  // lib:748-759
+                    vmin.v[i] = (k == 0 || tv < vmin.v[i]) ? tv : vmin.v[i];  // lib:784-795
                     vsum.v[i] = __fadd_rn(vsum.v[i], tv);
                     const float d = __fsub_rn(tv, wmean.v[i]);                    // lib:693
                     wmean.v[i] = __fadd_rn(wmean.v[i], __fdiv_rn(d, cnt));        // lib:694

@@ -369,7 +369,23 @@ extern "C" void *gnnb_model_stream(gnnb_model_t *m) { return m ? (void *)m->stre
 extern "C" int gnnb_model_synchronize(gnnb_model_t *m)
 {
     GNNB_REQUIRE(m != nullptr, "null model");
+    GNNB_CUDA(cudaSetDevice(m->device));
     GNNB_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->last_path == GNNB_PATH_FUSED) {
+        // the async entry point cannot fall back by itself: report capacity/index problems here
+        int status = 0;
+        GNNB_TRY(fused_status(m, &status));
+        if (status == 1) {
+            set_error("fused kernel: a tile exceeded its node/edge capacity (raise nothing: set "
+                      "accurate max_nodes/max_edges hints or use gnnb_model_run_batch, which "
+                      "falls back to the layerwise path)");
+            return GNNB_ERR_INVALID;
+        }
+        if (status == 2) {
+            set_error("edge_list holds a node index outside its graph");
+            return GNNB_ERR_INVALID;
+        }
+    }
     return GNNB_OK;
 }
 
@@ -584,7 +600,8 @@ extern "C" int gnnb_model_run_batch_async(gnnb_model_t *m, const float *x, const
     m->last_path = path;
     if (path == GNNB_PATH_FUSED) {
         ProfScope ps(m->prof, PROF_FUSED, s);
-        return fused_run(m, x, edge_list, node_ptr, edge_ptr, n_graphs, out, s, &m->last_launches);
+        return fused_run(m, x, edge_list, node_ptr, edge_ptr, n_graphs, total_nodes, hint_n, out, s,
+                         &m->last_launches);
     }
     return run_layerwise(m, x, edge_list, node_ptr, edge_ptr, 0, 0, n_graphs, total_nodes,
                          total_edges, out, s, &m->last_launches);
@@ -653,10 +670,7 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
     int path;
     GNNB_TRY(choose_path(m, (int)max_n, (int)max_e, &path));
     m->last_path = path;
-    if (path == GNNB_PATH_FUSED) {
-        ProfScope ps(m->prof, PROF_FUSED, s);
-        GNNB_TRY(fused_run(m, dx, dcoo, dnp, dep, n_graphs, dout, s, &m->last_launches));
-    } else {
+    auto layerwise_chunks = [&]() -> int {
         // chunk the union so that the per-layer activations stay within a fixed budget
         const int64_t kChunkNodes = 4ll << 20;
         int g0 = 0;
@@ -669,6 +683,31 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
                                    &m->last_launches));
             g0 = g1;
         }
+        return GNNB_OK;
+    };
+    if (path == GNNB_PATH_FUSED) {
+        {
+            ProfScope ps(m->prof, PROF_FUSED, s);
+            GNNB_TRY(fused_run(m, dx, dcoo, dnp, dep, n_graphs, T, (int)max_n, dout, s,
+                               &m->last_launches));
+        }
+        GNNB_CUDA(cudaStreamSynchronize(s));
+        int status = 0;
+        GNNB_TRY(fused_status(m, &status));
+        if (status == 2) {
+            set_error("edge_list holds a node index outside its graph");
+            return GNNB_ERR_INVALID;
+        }
+        if (status == 1) {  // a tile overflowed its edge capacity: redo the batch layerwise
+            if (m->path == GNNB_PATH_FUSED) {
+                set_error("fused path requested but a tile exceeded its edge capacity");
+                return GNNB_ERR_INVALID;
+            }
+            m->last_path = GNNB_PATH_LAYERWISE;
+            GNNB_TRY(layerwise_chunks());
+        }
+    } else {
+        GNNB_TRY(layerwise_chunks());
     }
     if (!dev)
         GNNB_CUDA(cudaMemcpyAsync(out, dout, sizeof(float) * (size_t)n_graphs * d.mlp_out,

@@ -119,8 +119,12 @@ int fused_prepare(gnnb_model *m);
 void fused_release(gnnb_model *m);
 // true when the fused kernel can run this batch (every graph fits a CTA tile)
 bool fused_supports(const gnnb_model *m, int max_nodes_in_batch, int max_edges_in_batch);
+// max_nodes: upper bound on the node count of any graph in the batch (sets the tile window)
 int fused_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_t *node_ptr,
-              const int64_t *edge_ptr, int n_graphs, float *out, cudaStream_t s, int *launches);
+              const int64_t *edge_ptr, int n_graphs, int64_t total_nodes, int max_nodes, float *out,
+              cudaStream_t s, int *launches);
+// after the stream is synchronised: 0 ok, 1 a tile overflowed (re-run layerwise), 2 bad edge index
+int fused_status(gnnb_model *m, int *status);
 int fused_tile_rows(const gnnb_model *m);
 
 }  // namespace gnnb

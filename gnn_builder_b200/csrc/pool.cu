@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128) pool_kernel(const PoolArgs a)
             for (int64_t r = r0; r < r1; r++) {
                 const float v = __ldg(a.x + (size_t)r * a.ldx + f);
                 sum = __fadd_rn(sum, v);
-                mx = first ? v : fmaxf(mx, v);
+                mx = (first || v > mx) ? v : mx;  // lib:748-759 (a NaN first sample sticks)
                 first = false;
             }
             if (a.splits == 1) {

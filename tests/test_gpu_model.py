@@ -98,14 +98,34 @@ def test_edge_cases(gnnb, orc):
         assert eng.run(gnnb.GraphBatch.from_graphs(graphs[:1])).shape == (1, w.out_dim)
 
 
-def test_pna_zero_in_degree_gives_nan_like_reference(gnnb, orc):
+def test_pna_zero_in_degree_nan_semantics(gnnb, orc):
+    """PNA's std is NaN for zero-in-degree nodes (0/0, lib:702).  Through the whole model the
+    reference's relu (`x > 0 ? x : 0`, lib:362-375) turns those rows into 0, with sigmoid they
+    stay NaN: the GPU must follow the reference in both cases."""
+    import dataclasses
+    from gnn_builder_b200.models import build_model
+
     w, model, params = model_and_params("c4_pna_lipo_small")
     x = np.random.default_rng(1).uniform(-1, 1, (4, w.in_dim)).astype(np.float32)
     coo = np.array([[0, 1], [1, 2], [2, 1]], np.int32)   # nodes 0 and 3 have no in-edges
     ref = orc.model_forward(model.describe(), list(params.values()), x, coo)
-    assert np.isnan(ref).all()
+    assert np.isfinite(ref).all()
     with gnnb.Engine(model, path=gnnb.PATH_LAYERWISE) as eng:
-        assert np.isnan(eng.run_graph(x, coo)).all()
+        assert rel_err(eng.run_graph(x, coo), ref) < TOL
+    w2 = dataclasses.replace(w, activation="sigmoid")
+    model2 = build_model(w2, pna_delta=w2.pna_delta, seed=0)
+    p2 = model2.named_parameter_arrays()
+    ref2, emb2 = orc.model_forward(model2.describe(), list(p2.values()), x, coo,
+                                   return_node_emb=True)
+    assert np.isnan(emb2[[0, 3]]).all() and np.isfinite(emb2[[1, 2]]).all()
+    with gnnb.Engine(model2, path=gnnb.PATH_LAYERWISE) as eng:
+        out2 = eng.run_graph(x, coo)
+        emb = eng.node_embeddings(4)
+        assert np.array_equal(np.isnan(emb), np.isnan(emb2))
+        assert rel_err(emb[[1, 2]], emb2[[1, 2]]) < TOL
+        # the head's relu maps the NaN pooled sums to 0 exactly like the reference
+        assert np.array_equal(np.isnan(out2), np.isnan(ref2))
+        assert rel_err(np.nan_to_num(out2), np.nan_to_num(ref2)) < TOL
 
 
 def test_medium_graphs_use_layerwise(gnnb, orc):
