@@ -98,6 +98,16 @@ __device__ __forceinline__ float act_apply(int act, float x)
     }
 }
 
+// Same function with a small instruction footprint for use inside unrolled epilogues: ReLU and
+// identity inline, everything else through one out-of-line call.
+static __device__ __noinline__ float act_apply_general(int act, float x) { return act_apply(act, x); }
+__device__ __forceinline__ float act_apply_compact(int act, float x)
+{
+    if (act == GNNB_ACT_RELU) return (x > 0.0f) ? x : 0.0f;
+    if (act == GNNB_ACT_IDENTITY) return x;
+    return act_apply_general(act, x);
+}
+
 // multiply-accumulate: fused in FAST mode, separately rounded (reference order) in STRICT mode
 template <bool STRICT>
 __device__ __forceinline__ float mac(float acc, float a, float b)

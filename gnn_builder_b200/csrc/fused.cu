@@ -29,7 +29,7 @@ namespace {
 constexpr int TM = 128;        // node rows per tile
 constexpr int LDX = 132;       // feature buffer row stride (floats)
 constexpr int ECAP = 2048;     // edges per tile
-constexpr int BK = 16;
+constexpr int BK = 32;        // k rows per staged weight tile (2 barriers per tile)
 constexpr int MAX_LAYERS = 8;
 constexpr int MAX_HEAD = 6;
 constexpr int HEAD_G = 16;     // graphs per pooling/head chunk
@@ -114,7 +114,7 @@ __global__ void tile_bounds_kernel(const int64_t *__restrict__ node_ptr, int n_g
 // starting from the bias (the reference's order, lib:852-903).  dst may alias A1/A2/skip: all
 // K-loop reads complete (barrier) before the first write.
 template <int BN>
-__device__ __forceinline__ void tile_gemm(Smem &sm, const float *A1, int K1, const float *W1t,
+__device__ __noinline__ void tile_gemm(Smem &sm, const float *A1, int K1, const float *W1t,
                                           int ldw1, const float *A2, int K2, const float *W2t,
                                           int ldw2, const float *bias, int N, const float *skip,
                                           int act, float *dst)
@@ -168,7 +168,7 @@ __device__ __forceinline__ void tile_gemm(Smem &sm, const float *A1, int K1, con
         const float *A = second ? A2 : A1;
         const int k0 = (second ? t - nt1 : t) * BK;
         const float *ws = sm.WS[t & 1];
-#pragma unroll
+#pragma unroll 2
         for (int k4 = 0; k4 < BK; k4 += 4) {
             float a[8][4];
 #pragma unroll
@@ -200,20 +200,23 @@ __device__ __forceinline__ void tile_gemm(Smem &sm, const float *A1, int K1, con
         __syncthreads();
     }
 
-    // epilogue: (+ skip) -> activation -> dst; columns [N, round_up(N,16)) are zeroed so that
+    // epilogue: (+ skip) -> activation -> dst; columns [N, round_up(N,32)) are zeroed so that
     // the next layer's K tiles read zeros, never stale data
-    const int npad = (N + 15) & ~15;
-#pragma unroll
+    const int npad = (N + BK - 1) / BK * BK;
+#pragma unroll 1
     for (int i = 0; i < 8; i++) {
         const int row = (i / 4) * 64 + ty * 4 + (i % 4);
 #pragma unroll
         for (int j = 0; j < TN; j++) {
             const int col = (j / CW) * (BN / NG) + tx * CW + (j % CW);
+            float v = 0.0f;
+#pragma unroll
+            for (int ii = 0; ii < 8; ii++)
+                if (ii == i) v = acc[ii][j];
             if (col < N) {
-                float v = acc[i][j];
                 if (skip != nullptr) v += skip[row * LDX + col];
-                dst[row * LDX + col] = act_apply(act, v);
-            } else if (col < npad) {
+                dst[row * LDX + col] = act_apply_compact(act, v);
+            } else if (col < npad && col < LDX) {
                 dst[row * LDX + col] = 0.0f;
             }
         }
@@ -302,9 +305,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_model_kernel(const FusedPar
             sm.grow[i] = (int)(__ldg(p.node_ptr + g0 + i) - row0);
             sm.gedge[i] = (int)(__ldg(p.edge_ptr + g0 + i) - e0);
         }
-        // node features, zero padded to a multiple of 16 columns (K tiles of the first GEMM)
+        // node features, zero padded to a multiple of BK columns (K tiles of the first GEMM)
         {
-            const int F = p.in_dim, Fp = (F + 15) & ~15;
+            const int F = p.in_dim, Fp = (F + BK - 1) / BK * BK;
             const float *src = p.x + (size_t)row0 * F;
             for (int idx = tid; idx < rows * Fp; idx += NTHREADS) {
                 const int r = idx / Fp, c = idx - r * Fp;
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_model_kernel(const FusedPar
         // ------------------------------------------------------------------ conv layers
         for (int l = 0; l < p.num_layers; l++) {
             const int fi = p.fi[l], fo = p.fo[l];
-            const int kp = (fi + 15) & ~15;
+            const int kp = (fi + BK - 1) / BK * BK;
             const bool do_skip = p.skip && l != 0 && l != p.num_layers - 1;  // cpp:269-279
             // aggregate: warp per row, lanes across features (float4)
             for (int r = warp; r < rows; r += NTHREADS / 32) {

@@ -96,6 +96,10 @@ __device__ __forceinline__ void store_tile(const Prefetch<BN> &p, float *As, flo
     }
 }
 
+// The instruction footprint matters: a first version that fully unrolled both operand loops and
+// inlined the 13-way activation switch 64 times was 85 KB of SASS and spent half its issue slots
+// stalled on instruction fetch (ncu: stalled_no_instructions, profiles/r1_gemm_v1.txt).  This one
+// keeps a single K-tile loop (operand pointers selected per tile) whose body is 16 k-steps.
 template <int BN>
 __global__ void __launch_bounds__(256, BN == 128 ? 1 : 2) gemm_fma_kernel(const GemmArgs g)
 {
@@ -119,47 +123,68 @@ __global__ void __launch_bounds__(256, BN == 128 ? 1 : 2) gemm_fma_kernel(const 
         for (int i = 0; i < 8; i++) acc[i][j] = b;
     }
 
-    TileSrc src[2] = {{g.A1, g.lda1, g.K1, g.W1t, g.ldw1}, {g.A2, g.lda2, g.K2, g.W2t, g.ldw2}};
-    const int n_src = (g.A2 != nullptr && g.K2 > 0) ? 2 : 1;
-    for (int si = 0; si < n_src; si++) {
-        const TileSrc t = src[si];
-        const bool a_vec = (t.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(t.A) & 15) == 0);
-        const int n_tiles = (t.K + BK - 1) / BK;
-        Prefetch<BN> pf;
-        load_tile<BN>(t, m0, n0, 0, g.M, a_vec, pf);
-        for (int kt = 0; kt < n_tiles; kt++) {
-            __syncthreads();  // previous tile fully consumed
-            store_tile<BN>(pf, As, Ws);
-            __syncthreads();
-            if (kt + 1 < n_tiles) load_tile<BN>(t, m0, n0, (kt + 1) * BK, g.M, a_vec, pf);
+    const int nt1 = (g.K1 + BK - 1) / BK;
+    const int nt2 = (g.A2 != nullptr && g.K2 > 0) ? (g.K2 + BK - 1) / BK : 0;
+    const int nt = nt1 + nt2;
+    const bool a1_vec = (g.lda1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A1) & 15) == 0);
+    const bool a2_vec = nt2 > 0 && (g.lda2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A2) & 15) == 0);
+    auto tile_src = [&](int t, TileSrc &src, int &k0, bool &vec) {
+        if (t < nt1) {
+            src = TileSrc{g.A1, g.lda1, g.K1, g.W1t, g.ldw1};
+            k0 = t * BK;
+            vec = a1_vec;
+        } else {
+            src = TileSrc{g.A2, g.lda2, g.K2, g.W2t, g.ldw2};
+            k0 = (t - nt1) * BK;
+            vec = a2_vec;
+        }
+    };
+
+    Prefetch<BN> pf;
+    {
+        TileSrc src; int k0; bool vec;
+        tile_src(0, src, k0, vec);
+        load_tile<BN>(src, m0, n0, k0, g.M, vec, pf);
+    }
+#pragma unroll 1
+    for (int t = 0; t < nt; t++) {
+        __syncthreads();  // previous tile fully consumed
+        store_tile<BN>(pf, As, Ws);
+        __syncthreads();
+        if (t + 1 < nt) {
+            TileSrc src; int k0; bool vec;
+            tile_src(t + 1, src, k0, vec);
+            load_tile<BN>(src, m0, n0, k0, g.M, vec, pf);
+        }
 #pragma unroll
-            for (int k = 0; k < BK; k++) {
-                float a[8], b[TN];
-                const float4 a0 = *reinterpret_cast<const float4 *>(As + k * LDAS + ty * 4);
-                const float4 a1 = *reinterpret_cast<const float4 *>(As + k * LDAS + 64 + ty * 4);
-                a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
-                a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        for (int k = 0; k < BK; k++) {
+            float a[8], b[TN];
+            const float4 a0 = *reinterpret_cast<const float4 *>(As + k * LDAS + ty * 4);
+            const float4 a1 = *reinterpret_cast<const float4 *>(As + k * LDAS + 64 + ty * 4);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+            a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
 #pragma unroll
-                for (int q = 0; q < NG; q++) {
-                    const float *wp = Ws + k * BN + q * (BN / NG) + tx * CW;
-                    if constexpr (CW == 4) {
-                        const float4 w = *reinterpret_cast<const float4 *>(wp);
-                        b[q * 4 + 0] = w.x; b[q * 4 + 1] = w.y; b[q * 4 + 2] = w.z; b[q * 4 + 3] = w.w;
-                    } else {
-                        const float2 w = *reinterpret_cast<const float2 *>(wp);
-                        b[0] = w.x; b[1] = w.y;
-                    }
+            for (int q = 0; q < NG; q++) {
+                const float *wp = Ws + k * BN + q * (BN / NG) + tx * CW;
+                if constexpr (CW == 4) {
+                    const float4 w = *reinterpret_cast<const float4 *>(wp);
+                    b[q * 4 + 0] = w.x; b[q * 4 + 1] = w.y; b[q * 4 + 2] = w.z; b[q * 4 + 3] = w.w;
+                } else {
+                    const float2 w = *reinterpret_cast<const float2 *>(wp);
+                    b[0] = w.x; b[1] = w.y;
                 }
-#pragma unroll
-                for (int i = 0; i < 8; i++)
-#pragma unroll
-                    for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
             }
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
     }
 
-    // epilogue: (+ skip) -> activation -> store
-#pragma unroll
+    // epilogue: (+ skip) -> activation -> store.  ReLU / identity inline, the transcendental
+    // activations through one out-of-line call so the code stays small.
+    const bool vec_ok = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+#pragma unroll 1
     for (int i = 0; i < 8; i++) {
         const int row = m0 + (i / 4) * 64 + ty * 4 + (i % 4);
         if (row >= g.M) continue;
@@ -169,16 +194,18 @@ __global__ void __launch_bounds__(256, BN == 128 ? 1 : 2) gemm_fma_kernel(const 
             float v[CW];
 #pragma unroll
             for (int j = 0; j < CW; j++) {
-                v[j] = acc[i][q * CW + j];
+                float t = 0.0f;
+#pragma unroll
+                for (int ii = 0; ii < 8; ii++)   // register select without dynamic indexing
+                    if (ii == i) t = acc[ii][q * CW + j];
                 if (g.skip != nullptr && col + j < g.N)
-                    v[j] += __ldg(g.skip + (size_t)row * g.ldskip + col + j);
-                v[j] = act_apply(g.act, v[j]);
+                    t += __ldg(g.skip + (size_t)row * g.ldskip + col + j);
+                v[j] = act_apply_compact(g.act, t);
             }
             float *dst = g.C + (size_t)row * g.ldc + col;
             bool vec_store = false;
             if constexpr (CW == 4) {
-                vec_store = col + 3 < g.N && (g.ldc % 4 == 0) &&
-                            ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+                vec_store = vec_ok && col + 3 < g.N;
                 if (vec_store)
                     *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
             }

@@ -117,12 +117,12 @@ def test_pna_zero_in_degree_nan_semantics(gnnb, orc):
     p2 = model2.named_parameter_arrays()
     ref2, emb2 = orc.model_forward(model2.describe(), list(p2.values()), x, coo,
                                    return_node_emb=True)
-    assert np.isnan(emb2[[0, 3]]).all() and np.isfinite(emb2[[1, 2]]).all()
+    assert np.isnan(emb2[[0, 3]]).all()   # (NaN then spreads along edges 0->1->2 layer by layer)
     with gnnb.Engine(model2, path=gnnb.PATH_LAYERWISE) as eng:
         out2 = eng.run_graph(x, coo)
         emb = eng.node_embeddings(4)
         assert np.array_equal(np.isnan(emb), np.isnan(emb2))
-        assert rel_err(emb[[1, 2]], emb2[[1, 2]]) < TOL
+        assert rel_err(np.nan_to_num(emb), np.nan_to_num(emb2)) < TOL
         # the head's relu maps the NaN pooled sums to 0 exactly like the reference
         assert np.array_equal(np.isnan(out2), np.isnan(ref2))
         assert rel_err(np.nan_to_num(out2), np.nan_to_num(ref2)) < TOL
