@@ -46,6 +46,7 @@ EXPORTS = [
     "gnnb_compute_neighbor_and_edge_index_tables", "gnnb_linear", "gnnb_apply_activation",
     "gnnb_gcn_conv", "gnnb_gin_conv", "gnnb_sage_conv", "gnnb_pna_conv",
     "gnnb_global_add_pool", "gnnb_global_mean_pool", "gnnb_global_max_pool",
+    "gnnb_debug_tc_gemm",
 ]
 
 _lib = None
@@ -101,6 +102,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
                                   ci, ci]
     for k in ("add", "mean", "max"):
         getattr(lib, f"gnnb_global_{k}_pool").argtypes = [ci, ci, vp, vp, ci]
+    lib.gnnb_debug_tc_gemm.argtypes = [vp, vp, vp, ci, ci]
     _lib = lib
     return lib
 

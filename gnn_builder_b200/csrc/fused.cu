@@ -21,6 +21,7 @@
 #include "model.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace gnnb {
 
@@ -58,6 +59,7 @@ struct FusedParams {
     const int32_t *tile_bounds;  // [n_tiles + 1]
     int n_tiles;
     int *error_flag;
+    unsigned long long *timing;  // optional per-phase cycle counters (GNNB_FUSED_TIMING=1)
 };
 
 struct Smem {
@@ -237,48 +239,78 @@ __device__ __forceinline__ void gemm_dispatch(Smem &sm, const float *A1, int K1,
         tile_gemm<32>(sm, A1, K1, W1t, ldw1, A2, K2, W2t, ldw2, bias, N, skip, act, dst);
 }
 
-// one MLP-head linear for up to HEAD_G graphs: thread = (graph tid/16, 4-column groups)
-__device__ __forceinline__ void head_linear(const float *A, int lda, int K, const FLinear &L,
-                                            int act, float *dst_smem, int ldo, float *dst_global,
-                                            int ldg, int n_rows)
+// one MLP-head linear for up to HEAD_G (=16) graphs: thread = (graph tid/16, column groups
+// cg*4 and 64+cg*4).  The weights are streamed through the same cp.async double buffer as the
+// conv GEMMs (a first version read them with __ldg from L2 inside the k loop and was bound by
+// that latency: ~300 cycles x K per linear).
+__device__ __noinline__ void head_linear(Smem &sm, const float *A, int lda, int K, const float *Wt,
+                                         int ldw, const float *bias, int N, int act,
+                                         float *dst_smem, int ldo, float *dst_global, int ldg,
+                                         int n_rows)
 {
+    constexpr int BN = MAX_DIM;
     const int tid = threadIdx.x;
     const int gi = tid >> 4, cg = tid & 15;
-    const int N = L.out;
     float acc[2][4];
 #pragma unroll
     for (int q = 0; q < 2; q++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int col = q * 64 + cg * 4 + j;
-            acc[q][j] = (L.bias != nullptr && col < N) ? __ldg(L.bias + col) : 0.0f;
+            acc[q][j] = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.0f;
         }
-    const float *a = A + gi * lda;
-    const bool q_on[2] = {cg * 4 < L.ldw, 64 + cg * 4 < L.ldw};
+    const int nt = (K + BK - 1) / BK;
+    auto issue = [&](int t, int buf) {
+        constexpr int GPR = BN / 4;
+        float *ws = sm.WS[buf];
+        const int k0 = t * BK;
+        for (int g = tid; g < BK * GPR; g += NTHREADS) {
+            const int kk = g / GPR, c4 = (g % GPR) * 4;
+            const bool valid = (k0 + kk < K) && (c4 < ldw);
+            const float *src = valid ? Wt + (size_t)(k0 + kk) * ldw + c4 : Wt;
+            cp_async16(ws + kk * BN + c4, src, valid);
+        }
+        cp_async_commit();
+    };
+    const float *a = A + (gi < n_rows ? gi : 0) * lda;
+    issue(0, 0);
+#pragma unroll 1
+    for (int t = 0; t < nt; t++) {
+        if (t + 1 < nt) {
+            issue(t + 1, (t + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float *ws = sm.WS[t & 1];
+        const int k0 = t * BK;
+        const int kn = min(BK, K - k0);
+#pragma unroll 4
+        for (int kk = 0; kk < kn; kk++) {
+            const float av = a[k0 + kk];
+            const float4 w0 = *reinterpret_cast<const float4 *>(ws + kk * BN + cg * 4);
+            const float4 w1 = *reinterpret_cast<const float4 *>(ws + kk * BN + 64 + cg * 4);
+            acc[0][0] = fmaf(av, w0.x, acc[0][0]); acc[0][1] = fmaf(av, w0.y, acc[0][1]);
+            acc[0][2] = fmaf(av, w0.z, acc[0][2]); acc[0][3] = fmaf(av, w0.w, acc[0][3]);
+            acc[1][0] = fmaf(av, w1.x, acc[1][0]); acc[1][1] = fmaf(av, w1.y, acc[1][1]);
+            acc[1][2] = fmaf(av, w1.z, acc[1][2]); acc[1][3] = fmaf(av, w1.w, acc[1][3]);
+        }
+        __syncthreads();
+    }
     if (gi < n_rows) {
-        for (int k = 0; k < K; k++) {
-            const float av = a[k];
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                if (!q_on[q]) continue;
-                const float4 w = ldg4(L.Wt + (size_t)k * L.ldw + q * 64 + cg * 4);
-                acc[q][0] = fmaf(av, w.x, acc[q][0]);
-                acc[q][1] = fmaf(av, w.y, acc[q][1]);
-                acc[q][2] = fmaf(av, w.z, acc[q][2]);
-                acc[q][3] = fmaf(av, w.w, acc[q][3]);
-            }
-        }
 #pragma unroll
         for (int q = 0; q < 2; q++)
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int col = q * 64 + cg * 4 + j;
                 if (col >= N) continue;
-                const float v = act_apply(act, acc[q][j]);
+                const float v = act_apply_compact(act, acc[q][j]);
                 if (dst_global != nullptr) dst_global[(size_t)gi * ldg + col] = v;
                 else dst_smem[gi * ldo + col] = v;
             }
     }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) fused_model_kernel(const FusedParams p)
@@ -286,6 +318,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_model_kernel(const FusedPar
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long t_prev = clock64();
+#define GNNB_PHASE(idx)                                                             \
+    if (p.timing != nullptr && tid == 0) {                                          \
+        const long long t_now = clock64();                                          \
+        atomicAdd(p.timing + (idx), (unsigned long long)(t_now - t_prev));          \
+        t_prev = t_now;                                                             \
+    }
 
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         // ------------------------------------------------------------------ tile geometry
@@ -337,6 +376,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_model_kernel(const FusedPar
             }
         }
         __syncthreads();
+        GNNB_PHASE(0)
         // ------------------------------------------------------------------ tables (lib:1051-1124)
         int my_deg = 0;
         if (tid < TM) {
@@ -373,6 +413,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_model_kernel(const FusedPar
             }
         }
         __syncthreads();
+        GNNB_PHASE(1)
 
         // ------------------------------------------------------------------ conv layers
         for (int l = 0; l < p.num_layers; l++) {
@@ -411,6 +452,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_model_kernel(const FusedPar
                 }
             }
             __syncthreads();
+            GNNB_PHASE(2)
             const float *skip = do_skip ? sm.X : nullptr;
             if (p.conv_type == GNNB_CONV_GCN) {
                 gemm_dispatch(sm, sm.WK, fi, p.l0[l].Wt, p.l0[l].ldw, nullptr, 0, nullptr, 4,
@@ -424,6 +466,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_model_kernel(const FusedPar
                 gemm_dispatch(sm, sm.WK, fi, p.l0[l].Wt, p.l0[l].ldw, sm.X, fi, p.l1[l].Wt,
                               p.l1[l].ldw, p.l0[l].bias, fo, skip, p.gnn_act, sm.X);
             }
+            GNNB_PHASE(3)
         }
 
         // ------------------------------------------------------------------ pooling + MLP head
@@ -453,25 +496,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_model_kernel(const FusedPar
                 }
             }
             __syncthreads();
+            GNNB_PHASE(4)
             const float *hin = pooled;
             int hld = ldp, hk = head_in;
             for (int j = 0; j < p.mlp_num_linear; j++) {
                 const bool last = j == p.mlp_num_linear - 1;
                 float *hout = (j & 1) ? hb1 : hb0;
-                head_linear(hin, hld, hk, p.head[j], last ? p.out_act : p.mlp_act, hout, LDX,
+                head_linear(sm, hin, hld, hk, p.head[j].Wt, p.head[j].ldw, p.head[j].bias,
+                            p.head[j].out, last ? p.out_act : p.mlp_act, hout, LDX,
                             last ? p.out + (size_t)(g0 + gc0) * p.mlp_out : nullptr, p.mlp_out, gcn);
-                __syncthreads();
                 hin = hout; hld = LDX; hk = p.head[j].out;
             }
+            GNNB_PHASE(5)
         }
     }
+#undef GNNB_PHASE
 }
 
 }  // namespace
 
 struct FusedPlan {
     FusedParams params{};
-    DeviceBuf bounds, flag;
+    DeviceBuf bounds, flag, timing;
     size_t smem_bytes = 0;
 };
 
@@ -514,6 +560,10 @@ int fused_prepare(gnnb_model *m)
         return cuda_fail(e, "cudaFuncSetAttribute(fused_model_kernel)", __FILE__, __LINE__);
     }
     int rc = plan->flag.ensure(sizeof(int));
+    if (rc == GNNB_OK && getenv("GNNB_FUSED_TIMING") != nullptr) {
+        rc = plan->timing.ensure(16 * sizeof(unsigned long long));
+        if (rc == GNNB_OK) cudaMemset(plan->timing.ptr, 0, 16 * sizeof(unsigned long long));
+    }
     if (rc != GNNB_OK) { delete plan; return rc; }
     m->fused = plan;
     return GNNB_OK;
@@ -524,6 +574,7 @@ void fused_release(gnnb_model *m)
     if (m->fused) {
         m->fused->bounds.release();
         m->fused->flag.release();
+        m->fused->timing.release();
         delete m->fused;
         m->fused = nullptr;
     }
@@ -558,6 +609,7 @@ int fused_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_t *
     p.x = x; p.coo = coo; p.node_ptr = node_ptr; p.edge_ptr = edge_ptr; p.n_graphs = n_graphs;
     p.out = out; p.tile_bounds = plan->bounds.as<int32_t>(); p.n_tiles = n_tiles;
     p.error_flag = plan->flag.as<int>();
+    p.timing = plan->timing.as<unsigned long long>();
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;  // persistent: one CTA per SM
     fused_model_kernel<<<grid, NTHREADS, plan->smem_bytes, s>>>(p);
     GNNB_CUDA(cudaGetLastError());
@@ -572,6 +624,18 @@ int fused_status(gnnb_model *m, int *status)
     *status = 0;
     if (m->fused == nullptr) return GNNB_OK;
     GNNB_CUDA(cudaMemcpy(status, m->fused->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (m->fused->timing.ptr != nullptr) {  // developer aid: per-phase cycles summed over CTAs
+        unsigned long long t[16];
+        GNNB_CUDA(cudaMemcpy(t, m->fused->timing.ptr, sizeof(t), cudaMemcpyDeviceToHost));
+        GNNB_CUDA(cudaMemset(m->fused->timing.ptr, 0, sizeof(t)));
+        const char *names[6] = {"stage", "tables", "aggregate", "gemm", "pool", "head"};
+        unsigned long long tot = 0;
+        for (int i = 0; i < 6; i++) tot += t[i];
+        fprintf(stderr, "[gnnb fused phases]");
+        for (int i = 0; i < 6; i++)
+            fprintf(stderr, " %s %.1f%%", names[i], tot ? 100.0 * (double)t[i] / (double)tot : 0.0);
+        fprintf(stderr, " (total %.3g cycles over all CTAs)\n", (double)tot);
+    }
     return GNNB_OK;
 }
 

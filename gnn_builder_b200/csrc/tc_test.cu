@@ -1,0 +1,165 @@
+// Stand-alone check of the tcgen05 building blocks (tc.cuh): one CTA computes
+//   C[128][N] = A[128][K] . W[N][K]^T      (3xTF32, fp32 accumulate in tensor memory)
+// with exactly the operand layouts, descriptors, bulk copies and barriers the fused kernel uses.
+// Exposed as gnnb_debug_tc_gemm so that a parity test can pin the primitives in isolation.
+#include <vector>
+
+#include "kernels.h"
+#include "tc.cuh"
+
+namespace gnnb {
+
+// Weight image for the tensor-core path: for every K atom (32 columns of K) the N x 128-byte
+// rows of W in the canonical swizzled layout, hi part followed by lo part.
+void build_weight_image(const float *W, int N, int K, int ld, int col0, std::vector<float> &img)
+{
+    const int KA = (K + tc::ATOM_K - 1) / tc::ATOM_K;
+    const size_t atom_floats = (size_t)2 * N * tc::ATOM_K;
+    const size_t base = img.size();
+    img.resize(base + (size_t)KA * atom_floats, 0.0f);
+    for (int ka = 0; ka < KA; ka++) {
+        float *hi = img.data() + base + (size_t)ka * atom_floats;
+        float *lo = hi + (size_t)N * tc::ATOM_K;
+        for (int n = 0; n < N; n++)
+            for (int kk = 0; kk < tc::ATOM_K; kk++) {
+                const int k = ka * tc::ATOM_K + kk;
+                const float v = (k < K) ? W[(size_t)n * ld + col0 + k] : 0.0f;
+                const float h = tc::tf32_hi(v);
+                const uint32_t off = tc::canon_offset(n, kk, N) / 4;  // atom-local (k < 32)
+                hi[off] = h;
+                lo[off] = v - h;
+            }
+    }
+}
+
+namespace {
+
+constexpr int TM = 128;
+
+__global__ void __launch_bounds__(256, 1) tc_gemm_test_kernel(const float *__restrict__ A,
+                                                              const float *__restrict__ Bimg,
+                                                              float *__restrict__ C, int K, int N)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_done;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KA = (K + tc::ATOM_K - 1) / tc::ATOM_K;
+    unsigned char *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *a_hi = base;
+    unsigned char *a_lo = a_hi + (size_t)KA * TM * tc::ROW_BYTES;
+    unsigned char *b_st = a_lo + (size_t)KA * TM * tc::ROW_BYTES;
+    const uint32_t stage_bytes = 2u * (uint32_t)N * tc::ROW_BYTES;
+
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 128);
+    if (tid == 0) {
+        tc::mbar_init(&bar_full[0], 1); tc::mbar_init(&bar_full[1], 1);
+        tc::mbar_init(&bar_empty[0], 1); tc::mbar_init(&bar_empty[1], 1);
+        tc::mbar_init(&bar_done, 1);
+        tc::mbar_fence_init();
+    }
+    // A -> hi / lo operand buffers (zero padded to whole K atoms)
+    for (int idx = tid; idx < TM * KA * 8; idx += blockDim.x) {
+        const int row = idx / (KA * 8), c4 = (idx % (KA * 8)) * 4;
+        float v[4], h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            v[j] = (c4 + j < K) ? A[(size_t)row * K + c4 + j] : 0.0f;
+            h[j] = tc::tf32_hi(v[j]);
+            l[j] = v[j] - h[j];
+        }
+        const uint32_t off = tc::canon_chunk_offset(row, c4, TM);
+        *reinterpret_cast<float4 *>(a_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4 *>(a_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_tf32(TM, N);
+        const unsigned char *bsrc = reinterpret_cast<const unsigned char *>(Bimg);
+        for (int s = 0; s < 2 && s < KA; s++) {
+            tc::mbar_expect_tx(&bar_full[s], stage_bytes);
+            tc::bulk_g2s(b_st + (size_t)s * stage_bytes, bsrc + (size_t)s * stage_bytes, stage_bytes,
+                         &bar_full[s]);
+        }
+        uint32_t full_par[2] = {0, 0}, empty_par[2] = {0, 0};
+        for (int ka = 0; ka < KA; ka++) {
+            const int s = ka & 1;
+            tc::mbar_wait(&bar_full[s], full_par[s]);
+            full_par[s] ^= 1;
+            tc::tc_fence_after();
+            const uint32_t ah = tc::smem_u32(a_hi) + (uint32_t)ka * TM * tc::ROW_BYTES;
+            const uint32_t al = tc::smem_u32(a_lo) + (uint32_t)ka * TM * tc::ROW_BYTES;
+            const uint32_t bh = tc::smem_u32(b_st) + (uint32_t)s * stage_bytes;
+            const uint32_t bl = bh + (uint32_t)N * tc::ROW_BYTES;
+#pragma unroll
+            for (int k8 = 0; k8 < tc::ATOM_K / tc::MMA_K; k8++) {
+                const uint32_t ko = (uint32_t)k8 * tc::MMA_K * 4;  // bytes along K inside the atom
+                const uint32_t first = (ka == 0 && k8 == 0) ? 0u : 1u;
+                tc::mma_tf32(tmem_d, tc::make_desc(ah + ko), tc::make_desc(bh + ko), idesc, first);
+                tc::mma_tf32(tmem_d, tc::make_desc(al + ko), tc::make_desc(bh + ko), idesc, 1u);
+                tc::mma_tf32(tmem_d, tc::make_desc(ah + ko), tc::make_desc(bl + ko), idesc, 1u);
+            }
+            tc::mma_commit(&bar_empty[s]);
+            if (ka >= 1 && ka + 1 < KA) {  // refill the stage atom ka-1 used with atom ka+1
+                const int sp = (ka - 1) & 1;
+                tc::mbar_wait(&bar_empty[sp], empty_par[sp]);
+                empty_par[sp] ^= 1;
+                tc::mbar_expect_tx(&bar_full[sp], stage_bytes);
+                tc::bulk_g2s(b_st + (size_t)sp * stage_bytes, bsrc + (size_t)(ka + 1) * stage_bytes,
+                             stage_bytes, &bar_full[sp]);
+            }
+        }
+        tc::mma_commit(&bar_done);
+    }
+    tc::mbar_wait(&bar_done, 0);
+    tc::tc_fence_after();
+    {
+        const int row = 32 * (warp & 3) + lane;
+        for (int c0 = (warp >> 2) * 32; c0 < N; c0 += 64) {
+            float v[32];
+            tc::tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (c0 + j < N) C[(size_t)row * N + c0 + j] = v[j];
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_d, 128);
+}
+
+}  // namespace
+}  // namespace gnnb
+
+using namespace gnnb;
+
+// Diagnostic entry point: C[128][N] = A[128][K] . W[N][K]^T on the tensor cores (host buffers).
+extern "C" int gnnb_debug_tc_gemm(const float *A, const float *W, float *C, int K, int N)
+{
+    GNNB_REQUIRE(A && W && C, "null argument");
+    GNNB_REQUIRE(K >= 1 && K <= 128 && N >= 16 && N <= 128 && N % 16 == 0,
+                 "tc gemm: 1 <= K <= 128, N a multiple of 16 up to 128");
+    const int KA = (K + tc::ATOM_K - 1) / tc::ATOM_K;
+    std::vector<float> img;
+    build_weight_image(W, N, K, K, 0, img);
+    float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    GNNB_CUDA(cudaMalloc(&dA, sizeof(float) * 128 * K));
+    GNNB_CUDA(cudaMalloc(&dB, sizeof(float) * img.size()));
+    GNNB_CUDA(cudaMalloc(&dC, sizeof(float) * 128 * N));
+    GNNB_CUDA(cudaMemcpy(dA, A, sizeof(float) * 128 * K, cudaMemcpyHostToDevice));
+    GNNB_CUDA(cudaMemcpy(dB, img.data(), sizeof(float) * img.size(), cudaMemcpyHostToDevice));
+    const size_t smem = 1024 + (size_t)2 * KA * TM * tc::ROW_BYTES + (size_t)2 * 2 * N * tc::ROW_BYTES;
+    GNNB_CUDA(cudaFuncSetAttribute(tc_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    tc_gemm_test_kernel<<<1, 256, smem>>>(dA, dB, dC, K, N);
+    GNNB_CUDA(cudaGetLastError());
+    GNNB_CUDA(cudaDeviceSynchronize());
+    GNNB_CUDA(cudaMemcpy(C, dC, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    return GNNB_OK;
+}

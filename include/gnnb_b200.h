@@ -183,6 +183,11 @@ int gnnb_global_add_pool(int num_nodes, int num_edges, const float *x, float *po
 int gnnb_global_mean_pool(int num_nodes, int num_edges, const float *x, float *pooled, int emb);
 int gnnb_global_max_pool(int num_nodes, int num_edges, const float *x, float *pooled, int emb);
 
+/* ---- diagnostics ------------------------------------------------------------------------- */
+/* One-CTA tensor-core GEMM C[128][N] = A[128][K] . W[N][K]^T (tcgen05, 3xTF32) built from the
+ * same primitives as the fused kernel's node transform; host buffers; K <= 128, N % 16 == 0. */
+int gnnb_debug_tc_gemm(const float *A, const float *W, float *C, int K, int N);
+
 #ifdef __cplusplus
 }
 #endif
