@@ -39,7 +39,7 @@ EXPORTS = [
     "gnnb_model_create", "gnnb_model_destroy", "gnnb_model_num_params", "gnnb_model_param_info",
     "gnnb_model_set_param", "gnnb_model_finalize", "gnnb_model_set_path", "gnnb_model_set_math",
     "gnnb_model_run_graph", "gnnb_model_run_batch", "gnnb_model_run_batch_async",
-    "gnnb_model_get_node_embeddings", "gnnb_model_last_launches", "gnnb_model_last_path",
+    "gnnb_model_get_node_embeddings", "gnnb_model_last_launches", "gnnb_model_last_path", "gnnb_model_last_kernel",
     "gnnb_model_stream", "gnnb_model_synchronize", "gnnb_model_set_profile",
     "gnnb_model_profile_read",
     "gnnb_compute_degree_tables", "gnnb_compute_neighbor_tables",
@@ -85,6 +85,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.gnnb_model_get_node_embeddings.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.gnnb_model_last_launches.argtypes = [C.c_void_p]
     lib.gnnb_model_last_path.argtypes = [C.c_void_p]
+    lib.gnnb_model_last_kernel.argtypes = [C.c_void_p]
     lib.gnnb_model_synchronize.argtypes = [C.c_void_p]
     lib.gnnb_model_set_profile.argtypes = [C.c_void_p, C.c_int]
     lib.gnnb_model_profile_read.argtypes = [C.c_void_p, f32p, C.POINTER(C.c_int)]

@@ -1,0 +1,704 @@
+// Kernel (1), tensor-core version: the persistent whole-model fused kernel of fused.cu with the
+// node-transform GEMMs on the 5th-generation tensor cores (tcgen05.mma.kind::tf32, accumulators in
+// tensor memory) using the error-compensated 3xTF32 split of tc.cuh, so results stay fp32-grade
+// (<= 1e-4 parity bound with two orders of magnitude of margin).
+//
+// Per CTA (one per SM, 256 threads, 128-row tile of packed graphs):
+//   shared memory   R_X  64 KB  layer input X, canonical K-major SWIZZLE_128B layout; while a GEMM
+//                               runs it is the 2-stage ring the weight atoms are bulk-copied into
+//                   R_HI 64 KB  A operand, hi parts   (aggregate, then the GIN hidden layer)
+//                   R_LO 64 KB  A operand, lo parts
+//   tensor memory   128 columns x 128 lanes fp32 accumulator
+//   weights         pre-split (hi/lo) and pre-swizzled on the host into the exact shared-memory
+//                   image of each 32-wide K atom, so one cp.async.bulk (TMA engine, no tensor map)
+//                   per atom lands them ready for the MMA; they stay L2 resident across CTAs.
+// One elected thread issues the bulk copies and the MMAs (12 per K atom: hi.hi, lo.hi, hi.lo for
+// four k-steps of 8) and signals completion through mbarriers; all 8 warps run the aggregation
+// before and the TMEM -> register -> shared epilogue (bias, skip, activation, hi/lo re-split) after.
+// The skip connection of interior layers needs X after R_X has been recycled for the weight ring:
+// X is parked in a per-CTA global scratch (64 KB, L2 resident) and re-read in the epilogue.
+//
+// Supported: GCN and GIN, every layer width a multiple of 16 up to 128 (BASELINE configs 1 and 2);
+// everything else uses fused.cu / the layerwise path.
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "model.h"
+#include "tc.cuh"
+
+namespace gnnb {
+
+void build_weight_image(const float *W, int N, int K, int ld, int col0, std::vector<float> &img);
+
+namespace {
+
+constexpr int TM = 128;
+constexpr int ECAP = 2048;
+constexpr int NTHREADS = 256;
+constexpr int MAX_LAYERS = 8;
+constexpr int MAX_HEAD = 6;
+constexpr int HEAD_G = 16;
+constexpr int HBK = 32;          // k rows per staged head-weight tile
+constexpr int MAX_DIM = 128;
+constexpr int HLD = 132;         // row stride of the head ping-pong buffers
+constexpr int REGION = TM * MAX_DIM * 4;  // 64 KB
+constexpr int MAX_NODES_PER_GRAPH = 64;
+
+struct TLinear {
+    const float *img;   // weight image, KA atoms of [hi N x 128 B | lo N x 128 B]
+    const float *bias;
+    int K, N, KA;
+};
+struct HLinear {
+    const float *Wt;
+    const float *bias;
+    int in, out, ldw;
+};
+
+struct TcParams {
+    int conv_type, num_layers, in_dim, skip, gnn_act, num_pools, pools[4];
+    int mlp_num_linear, mlp_act, out_act, emb, mlp_out;
+    float gin_eps;
+    int fi[MAX_LAYERS], fo[MAX_LAYERS];
+    TLinear l0[MAX_LAYERS], l1[MAX_LAYERS];
+    HLinear head[MAX_HEAD];
+    const float *x;
+    const int32_t *coo;
+    const int64_t *node_ptr, *edge_ptr;
+    int n_graphs;
+    float *out;
+    const int32_t *tile_bounds;
+    int n_tiles;
+    int *error_flag;
+    float *scratch;               // [gridDim.x][128][128] parked X for the skip connection
+    unsigned long long *timing;
+};
+
+struct Misc {
+    uint64_t bar_full[2], bar_empty[2], bar_done;
+    uint32_t tmem_slot;
+    float dinv[TM];
+    int deg[TM];
+    int off[TM + 1];
+    int rowg[TM];
+    int grow[TM + 2];
+    int gedge[TM + 2];
+    int scan_tmp[8];
+    unsigned short edges[ECAP];
+    unsigned char nbr[ECAP];
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool valid)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ int lower_bound64(const int64_t *__restrict__ ptr, int n, int64_t v)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(ptr + mid) < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void tc_tile_bounds_kernel(const int64_t *__restrict__ node_ptr, int n_graphs,
+                                      int window, int n_tiles, int32_t *__restrict__ bounds)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    bounds[t] = (t == n_tiles) ? n_graphs : lower_bound64(node_ptr, n_graphs, (int64_t)t * window);
+}
+
+struct PipeState {
+    uint32_t full_cnt[2];
+    uint32_t empty_cnt[2];
+};
+
+// Issued by ONE thread: D[128][N] (tensor memory) = A(hi,lo)[128][KA*32] . W^T, 3xTF32.
+// The weight atoms stream through the 2-stage ring at `ring` (R_X).
+__device__ __forceinline__ void gemm_issue(Misc &ms, PipeState &ps, uint32_t tmem_d,
+                                           uint32_t a_hi, uint32_t a_lo, unsigned char *ring,
+                                           const TLinear &L)
+{
+    const uint32_t stage_bytes = 2u * (uint32_t)L.N * tc::ROW_BYTES;
+    const uint32_t idesc = tc::make_idesc_tf32(TM, L.N);
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(L.img);
+    tc::tc_fence_after();
+    for (int s = 0; s < 2 && s < L.KA; s++) {
+        tc::mbar_expect_tx(&ms.bar_full[s], stage_bytes);
+        tc::bulk_g2s(ring + (size_t)s * stage_bytes, src + (size_t)s * stage_bytes, stage_bytes,
+                     &ms.bar_full[s]);
+    }
+    for (int ka = 0; ka < L.KA; ka++) {
+        const int s = ka & 1;
+        tc::mbar_wait(&ms.bar_full[s], ps.full_cnt[s] & 1);
+        ps.full_cnt[s]++;
+        tc::tc_fence_after();
+        const uint32_t ah = a_hi + (uint32_t)ka * TM * tc::ROW_BYTES;
+        const uint32_t al = a_lo + (uint32_t)ka * TM * tc::ROW_BYTES;
+        const uint32_t bh = tc::smem_u32(ring) + (uint32_t)s * stage_bytes;
+        const uint32_t bl = bh + (uint32_t)L.N * tc::ROW_BYTES;
+#pragma unroll
+        for (int k8 = 0; k8 < tc::ATOM_K / tc::MMA_K; k8++) {
+            const uint32_t ko = (uint32_t)k8 * tc::MMA_K * 4;
+            const uint32_t acc = (ka == 0 && k8 == 0) ? 0u : 1u;
+            tc::mma_tf32(tmem_d, tc::make_desc(ah + ko), tc::make_desc(bh + ko), idesc, acc);
+            tc::mma_tf32(tmem_d, tc::make_desc(al + ko), tc::make_desc(bh + ko), idesc, 1u);
+            tc::mma_tf32(tmem_d, tc::make_desc(ah + ko), tc::make_desc(bl + ko), idesc, 1u);
+        }
+        tc::mma_commit(&ms.bar_empty[s]);
+        ps.empty_cnt[s]++;
+        if (ka >= 1 && ka + 1 < L.KA) {  // refill the stage atom ka-1 used with atom ka+1
+            const int sp = (ka - 1) & 1;
+            tc::mbar_wait(&ms.bar_empty[sp], (ps.empty_cnt[sp] - 1) & 1);
+            tc::mbar_expect_tx(&ms.bar_full[sp], stage_bytes);
+            tc::bulk_g2s(ring + (size_t)sp * stage_bytes, src + (size_t)(ka + 1) * stage_bytes,
+                         stage_bytes, &ms.bar_full[sp]);
+        }
+    }
+    tc::mma_commit(&ms.bar_done);
+}
+
+// All threads: accumulator -> (+bias, +skip, activation) -> shared memory.
+//   split == true : write hi / lo parts into dst_hi / dst_lo (next GEMM's A operand)
+//   split == false: write the values into dst_hi (the X region), dst_lo unused
+// Columns [N, round_up(N, 32)) of the last K atom are zero filled.
+__device__ __forceinline__ void epilogue(uint32_t tmem_d, int N, const float *__restrict__ bias,
+                                         int act, const float *__restrict__ skip, bool split,
+                                         unsigned char *dst_hi, unsigned char *dst_lo)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = 32 * (warp & 3) + lane;
+    const int npad = (N + 31) & ~31;
+    for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += 64) {
+        float v[32];
+        tc::tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++) {
+            float o[4];
+            float4 sk = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (skip != nullptr && c0 + j4 * 4 < N)
+                sk = __ldg(reinterpret_cast<const float4 *>(skip + (size_t)row * MAX_DIM + c0 + j4 * 4));
+            const float sks[4] = {sk.x, sk.y, sk.z, sk.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int col = c0 + j4 * 4 + j;
+                float t = 0.0f;
+                if (col < N) t = act_apply_compact(act, v[j4 * 4 + j] + __ldg(bias + col) + sks[j]);
+                o[j] = t;
+            }
+            const uint32_t off = tc::canon_chunk_offset(row, c0 + j4 * 4, TM);
+            if (split) {
+                float h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { h[j] = tc::tf32_hi(o[j]); l[j] = o[j] - h[j]; }
+                *reinterpret_cast<float4 *>(dst_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4 *>(dst_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+            } else {
+                *reinterpret_cast<float4 *>(dst_hi + off) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
+// one MLP-head linear for up to 16 graphs (fp32 FMA; weights streamed through `ws`)
+__device__ __noinline__ void head_linear(float *ws, const float *A, int lda, int K, const float *Wt,
+                                         int ldw, const float *bias, int N, int act,
+                                         float *dst_smem, int ldo, float *dst_global, int ldg,
+                                         int n_rows)
+{
+    constexpr int BN = MAX_DIM;
+    const int tid = threadIdx.x;
+    const int gi = tid >> 4, cg = tid & 15;
+    float acc[2][4];
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int col = q * 64 + cg * 4 + j;
+            acc[q][j] = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.0f;
+        }
+    const int nt = (K + HBK - 1) / HBK;
+    auto issue = [&](int t, int buf) {
+        constexpr int GPR = BN / 4;
+        float *w = ws + buf * HBK * BN;
+        const int k0 = t * HBK;
+        for (int g = tid; g < HBK * GPR; g += NTHREADS) {
+            const int kk = g / GPR, c4 = (g % GPR) * 4;
+            const bool valid = (k0 + kk < K) && (c4 < ldw);
+            const float *src = valid ? Wt + (size_t)(k0 + kk) * ldw + c4 : Wt;
+            cp_async16(w + kk * BN + c4, src, valid);
+        }
+        cp_async_commit();
+    };
+    const float *a = A + (gi < n_rows ? gi : 0) * lda;
+    issue(0, 0);
+#pragma unroll 1
+    for (int t = 0; t < nt; t++) {
+        if (t + 1 < nt) {
+            issue(t + 1, (t + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float *w = ws + (t & 1) * HBK * BN;
+        const int k0 = t * HBK;
+        const int kn = min(HBK, K - k0);
+#pragma unroll 4
+        for (int kk = 0; kk < kn; kk++) {
+            const float av = a[k0 + kk];
+            const float4 w0 = *reinterpret_cast<const float4 *>(w + kk * BN + cg * 4);
+            const float4 w1 = *reinterpret_cast<const float4 *>(w + kk * BN + 64 + cg * 4);
+            acc[0][0] = fmaf(av, w0.x, acc[0][0]); acc[0][1] = fmaf(av, w0.y, acc[0][1]);
+            acc[0][2] = fmaf(av, w0.z, acc[0][2]); acc[0][3] = fmaf(av, w0.w, acc[0][3]);
+            acc[1][0] = fmaf(av, w1.x, acc[1][0]); acc[1][1] = fmaf(av, w1.y, acc[1][1]);
+            acc[1][2] = fmaf(av, w1.z, acc[1][2]); acc[1][3] = fmaf(av, w1.w, acc[1][3]);
+        }
+        __syncthreads();
+    }
+    if (gi < n_rows) {
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int col = q * 64 + cg * 4 + j;
+                if (col >= N) continue;
+                const float v = act_apply_compact(act, acc[q][j]);
+                if (dst_global != nullptr) dst_global[(size_t)gi * ldg + col] = v;
+                else dst_smem[gi * ldo + col] = v;
+            }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *RX = base, *RHI = base + REGION, *RLO = base + 2 * REGION;
+    Misc &ms = *reinterpret_cast<Misc *>(base + 3 * REGION);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long t_prev = clock64();
+#define GNNB_PHASE(idx)                                                             \
+    if (p.timing != nullptr && tid == 0) {                                          \
+        const long long t_now = clock64();                                          \
+        atomicAdd(p.timing + (idx), (unsigned long long)(t_now - t_prev));          \
+        t_prev = t_now;                                                             \
+    }
+
+    if (warp == 0) tc::tmem_alloc(&ms.tmem_slot, 128);
+    if (tid == 0) {
+        tc::mbar_init(&ms.bar_full[0], 1); tc::mbar_init(&ms.bar_full[1], 1);
+        tc::mbar_init(&ms.bar_empty[0], 1); tc::mbar_init(&ms.bar_empty[1], 1);
+        tc::mbar_init(&ms.bar_done, 1);
+        tc::mbar_fence_init();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = ms.tmem_slot;
+    PipeState ps{{0u, 0u}, {0u, 0u}};
+    uint32_t done_cnt = 0;
+    float *scratch = p.scratch + (size_t)blockIdx.x * TM * MAX_DIM;
+
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        // ------------------------------------------------------------------ tile geometry
+        const int g0 = __ldg(p.tile_bounds + tile), g1 = __ldg(p.tile_bounds + tile + 1);
+        const int ng = g1 - g0;
+        if (ng <= 0) continue;
+        const int64_t row0 = __ldg(p.node_ptr + g0);
+        const int64_t e0 = __ldg(p.edge_ptr + g0);
+        const int rows = (int)(__ldg(p.node_ptr + g1) - row0);
+        const int ne = (int)(__ldg(p.edge_ptr + g1) - e0);
+        if (rows > TM || ne > ECAP || ng > TM) {
+            if (tid == 0) atomicExch(p.error_flag, 1);
+            continue;
+        }
+        __syncthreads();
+        for (int i = tid; i <= ng; i += NTHREADS) {
+            ms.grow[i] = (int)(__ldg(p.node_ptr + g0 + i) - row0);
+            ms.gedge[i] = (int)(__ldg(p.edge_ptr + g0 + i) - e0);
+        }
+        {   // node features -> R_X (canonical layout), zero padded to whole K atoms; rows beyond
+            // the tile are zeroed too so that no stale NaN/Inf pattern ever enters an MMA
+            const int F = p.in_dim, Fp = (F + 31) & ~31;
+            const float *src = p.x + (size_t)row0 * F;
+            for (int idx = tid; idx < TM * Fp; idx += NTHREADS) {
+                const int r = idx / Fp, c = idx - r * Fp;
+                const float v = (r < rows && c < F) ? __ldg(src + (size_t)r * F + c) : 0.0f;
+                *reinterpret_cast<float *>(RX + tc::canon_offset(r, c, TM)) = v;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < ng; i += NTHREADS)
+            for (int r = ms.grow[i]; r < ms.grow[i + 1]; r++) ms.rowg[r] = i;
+        {
+            const int2 *coo = reinterpret_cast<const int2 *>(p.coo) + e0;
+            for (int j = tid; j < ne; j += NTHREADS) {
+                const int2 sd = __ldg(coo + j);
+                int lo = 0, hi = ng;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (ms.gedge[mid] <= j) lo = mid; else hi = mid;
+                }
+                const int b = ms.grow[lo], n_i = ms.grow[lo + 1] - b;
+                if ((unsigned)sd.x >= (unsigned)n_i || (unsigned)sd.y >= (unsigned)n_i) {
+                    atomicExch(p.error_flag, 2);
+                    ms.edges[j] = 0xffff;
+                } else {
+                    ms.edges[j] = (unsigned short)(((sd.y + b) << 8) | (sd.x + b));
+                }
+            }
+        }
+        __syncthreads();
+        GNNB_PHASE(0)
+        // ------------------------------------------------------------------ tables (lib:1051-1124)
+        int my_deg = 0;
+        if (tid < TM) {
+            if (tid < rows) {
+                const int gi = ms.rowg[tid];
+                for (int j = ms.gedge[gi]; j < ms.gedge[gi + 1]; j++)
+                    my_deg += ((ms.edges[j] >> 8) == tid) ? 1 : 0;
+            }
+            ms.deg[tid] = my_deg;
+            ms.dinv[tid] = 1.0f / sqrtf(1.0f + (float)my_deg);
+            int incl = my_deg;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (lane == 31) ms.scan_tmp[warp] = incl;
+            ms.off[tid] = incl - my_deg;
+        }
+        __syncthreads();
+        if (tid < TM) {
+            int b = 0;
+            for (int w = 0; w < warp; w++) b += ms.scan_tmp[w];
+            const int o = ms.off[tid] + b;
+            ms.off[tid] = o;
+            if (tid < rows) {
+                const int gi = ms.rowg[tid];
+                int pos = o;
+                for (int j = ms.gedge[gi]; j < ms.gedge[gi + 1]; j++) {
+                    const unsigned short ed = ms.edges[j];
+                    if ((ed >> 8) == tid) ms.nbr[pos++] = (unsigned char)(ed & 0xff);
+                }
+            }
+        }
+        __syncthreads();
+        GNNB_PHASE(1)
+
+        // ------------------------------------------------------------------ conv layers
+        for (int l = 0; l < p.num_layers; l++) {
+            const int fi = p.fi[l];
+            const int kp = (fi + 31) & ~31;
+            const bool do_skip = p.skip && l != 0 && l != p.num_layers - 1;  // cpp:269-279
+            // aggregate X -> (hi, lo) A operand; one warp per row, lanes across K (float4)
+            for (int r = warp; r < TM; r += NTHREADS / 32) {
+                const int c = lane * 4;
+                if (c >= kp) continue;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < rows) {
+                    const int d = ms.deg[r], o = ms.off[r];
+                    for (int k = 0; k < d; k++) {
+                        const int u = ms.nbr[o + k];
+                        const float4 v = *reinterpret_cast<const float4 *>(
+                            RX + tc::canon_chunk_offset(u, c, TM));
+                        if (p.conv_type == GNNB_CONV_GCN) {
+                            const float s = ms.dinv[u];
+                            acc.x = fmaf(v.x, s, acc.x); acc.y = fmaf(v.y, s, acc.y);
+                            acc.z = fmaf(v.z, s, acc.z); acc.w = fmaf(v.w, s, acc.w);
+                        } else {
+                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                        }
+                    }
+                    const float4 xs = *reinterpret_cast<const float4 *>(
+                        RX + tc::canon_chunk_offset(r, c, TM));
+                    if (p.conv_type == GNNB_CONV_GCN) {  // lib:1249-1278, factorised
+                        const float dv = ms.dinv[r], ss = dv * dv;
+                        acc.x = fmaf(xs.x, ss, acc.x * dv); acc.y = fmaf(xs.y, ss, acc.y * dv);
+                        acc.z = fmaf(xs.z, ss, acc.z * dv); acc.w = fmaf(xs.w, ss, acc.w * dv);
+                    } else {  // GIN, lib:1519-1529
+                        const float s = 1.0f + p.gin_eps;
+                        acc.x += xs.x * s; acc.y += xs.y * s; acc.z += xs.z * s; acc.w += xs.w * s;
+                    }
+                }
+                const float4 h = make_float4(tc::tf32_hi(acc.x), tc::tf32_hi(acc.y),
+                                             tc::tf32_hi(acc.z), tc::tf32_hi(acc.w));
+                const uint32_t off = tc::canon_chunk_offset(r, c, TM);
+                *reinterpret_cast<float4 *>(RHI + off) = h;
+                *reinterpret_cast<float4 *>(RLO + off) =
+                    make_float4(acc.x - h.x, acc.y - h.y, acc.z - h.z, acc.w - h.w);
+            }
+            if (do_skip) {  // park X: R_X is about to become the weight ring
+                for (int idx = tid; idx < TM * (kp / 4); idx += NTHREADS) {
+                    const int r = idx / (kp / 4), c = (idx % (kp / 4)) * 4;
+                    const float4 v = *reinterpret_cast<const float4 *>(
+                        RX + tc::canon_chunk_offset(r, c, TM));
+                    *reinterpret_cast<float4 *>(scratch + (size_t)r * MAX_DIM + c) = v;
+                }
+            }
+            tc::fence_async_smem();
+            tc::tc_fence_before();
+            __syncthreads();
+            GNNB_PHASE(2)
+            const float *skip = do_skip ? scratch : nullptr;
+            if (p.conv_type == GNNB_CONV_GCN) {
+                if (tid == 0)
+                    gemm_issue(ms, ps, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, p.l0[l]);
+                tc::mbar_wait(&ms.bar_done, done_cnt & 1);
+                done_cnt++;
+                tc::tc_fence_after();
+                epilogue(tmem_d, p.l0[l].N, p.l0[l].bias, p.gnn_act, skip, false, RX, nullptr);
+            } else {
+                if (tid == 0)
+                    gemm_issue(ms, ps, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, p.l0[l]);
+                tc::mbar_wait(&ms.bar_done, done_cnt & 1);
+                done_cnt++;
+                tc::tc_fence_after();
+                epilogue(tmem_d, p.l0[l].N, p.l0[l].bias, GNNB_ACT_RELU, nullptr, true, RHI, RLO);
+                tc::fence_async_smem();
+                tc::tc_fence_before();
+                __syncthreads();
+                if (tid == 0)
+                    gemm_issue(ms, ps, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, p.l1[l]);
+                tc::mbar_wait(&ms.bar_done, done_cnt & 1);
+                done_cnt++;
+                tc::tc_fence_after();
+                epilogue(tmem_d, p.l1[l].N, p.l1[l].bias, p.gnn_act, skip, false, RX, nullptr);
+            }
+            tc::tc_fence_before();
+            __syncthreads();
+            GNNB_PHASE(3)
+        }
+
+        // ------------------------------------------------------------------ pooling + MLP head
+        const int emb = p.emb, head_in = emb * p.num_pools;
+        const int ldp = ((head_in + 3) & ~3) + 4;
+        float *ws = reinterpret_cast<float *>(RHI);
+        float *pooled = reinterpret_cast<float *>(RLO);
+        float *hb0 = pooled + HEAD_G * ldp;
+        float *hb1 = hb0 + HEAD_G * HLD;
+        for (int gc0 = 0; gc0 < ng; gc0 += HEAD_G) {
+            const int gcn = min(HEAD_G, ng - gc0);
+            for (int gi = warp; gi < gcn; gi += NTHREADS / 32) {
+                const int r0 = ms.grow[gc0 + gi], r1 = ms.grow[gc0 + gi + 1];
+                for (int c = lane; c < emb; c += 32) {
+                    float sum = 0.0f, mx = 0.0f;
+                    for (int r = r0; r < r1; r++) {
+                        const float v = *reinterpret_cast<const float *>(RX + tc::canon_offset(r, c, TM));
+                        sum += v;
+                        mx = (r == r0 || v > mx) ? v : mx;  // lib:748-759
+                    }
+                    for (int q = 0; q < p.num_pools; q++) {
+                        float v;
+                        if (p.pools[q] == GNNB_POOL_ADD) v = sum;
+                        else if (p.pools[q] == GNNB_POOL_MEAN) v = (r1 > r0) ? sum / (float)(r1 - r0) : 0.0f;
+                        else v = mx;
+                        pooled[gi * ldp + q * emb + c] = v;
+                    }
+                }
+            }
+            __syncthreads();
+            GNNB_PHASE(4)
+            const float *hin = pooled;
+            int hld = ldp, hk = head_in;
+            for (int j = 0; j < p.mlp_num_linear; j++) {
+                const bool last = j == p.mlp_num_linear - 1;
+                float *hout = (j & 1) ? hb1 : hb0;
+                head_linear(ws, hin, hld, hk, p.head[j].Wt, p.head[j].ldw, p.head[j].bias,
+                            p.head[j].out, last ? p.out_act : p.mlp_act, hout, HLD,
+                            last ? p.out + (size_t)(g0 + gc0) * p.mlp_out : nullptr, p.mlp_out, gcn);
+                hin = hout; hld = HLD; hk = p.head[j].out;
+            }
+            GNNB_PHASE(5)
+        }
+    }
+#undef GNNB_PHASE
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_d, 128);
+}
+
+}  // namespace
+
+struct TcPlan {
+    TcParams params{};
+    DeviceBuf images, bounds, flag, scratch, timing;
+    size_t smem_bytes = 0;
+};
+
+static TcPlan *plan_of(gnnb_model *m) { return m->fused_tc; }
+
+int fused_tc_prepare(gnnb_model *m)
+{
+    m->fused_tc = nullptr;
+    const gnnb_model_desc &d = m->d;
+    if (getenv("GNNB_DISABLE_TC") != nullptr) return GNNB_OK;
+    const bool conv_ok = d.conv_type == GNNB_CONV_GCN || d.conv_type == GNNB_CONV_GIN;
+    const int head_in = m->emb_dim() * d.num_pools;
+    bool dims_ok = d.num_layers >= 1 && d.num_layers <= MAX_LAYERS && d.mlp_num_linear <= MAX_HEAD &&
+                   d.in_dim <= MAX_DIM && d.mlp_hidden <= MAX_DIM && d.mlp_out <= MAX_DIM &&
+                   head_in <= 512;
+    for (int k = 0; k < d.num_layers && dims_ok; k++) {
+        int fi, fo;
+        m->layer_dims(k, &fi, &fo);
+        dims_ok = fo % 16 == 0 && fo >= 16 && fo <= MAX_DIM && fi <= MAX_DIM;
+    }
+    if (!conv_ok || !dims_ok) return GNNB_OK;
+
+    TcPlan *plan = new TcPlan();
+    TcParams &p = plan->params;
+    p.conv_type = d.conv_type; p.num_layers = d.num_layers; p.in_dim = d.in_dim; p.skip = d.skip;
+    p.gnn_act = d.gnn_act; p.num_pools = d.num_pools;
+    for (int i = 0; i < 4; i++) p.pools[i] = d.pools[i];
+    p.mlp_num_linear = d.mlp_num_linear; p.mlp_act = d.mlp_act; p.out_act = d.out_act;
+    p.emb = m->emb_dim(); p.mlp_out = d.mlp_out; p.gin_eps = d.gin_eps;
+
+    // weight images from the host copies of the parameters (flat reference order: head first)
+    std::vector<float> img;
+    struct Pending { size_t off; int K, N; };
+    std::vector<Pending> pend;
+    size_t idx = 2 * (size_t)d.mlp_num_linear;
+    for (int k = 0; k < d.num_layers; k++) {
+        int fi, fo;
+        m->layer_dims(k, &fi, &fo);
+        if (d.conv_type == GNNB_CONV_GCN) {  // [bias, lin_weight]
+            pend.push_back({img.size(), fi, fo});
+            build_weight_image(m->params[idx + 1].host.data(), fo, fi, fi, 0, img);
+            idx += 2;
+        } else {                              // [w0, b0, w1, b1]
+            pend.push_back({img.size(), fi, fo});
+            build_weight_image(m->params[idx].host.data(), fo, fi, fi, 0, img);
+            pend.push_back({img.size(), fo, fo});
+            build_weight_image(m->params[idx + 2].host.data(), fo, fo, fo, 0, img);
+            idx += 4;
+        }
+    }
+    int rc = plan->images.ensure(img.size() * sizeof(float));
+    if (rc == GNNB_OK) {
+        cudaError_t e = cudaMemcpy(plan->images.ptr, img.data(), img.size() * sizeof(float),
+                                   cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = cuda_fail(e, "upload weight images", __FILE__, __LINE__);
+    }
+    if (rc == GNNB_OK) rc = plan->flag.ensure(sizeof(int));
+    if (rc == GNNB_OK) rc = plan->scratch.ensure((size_t)kNumSMs * TM * MAX_DIM * sizeof(float));
+    if (rc == GNNB_OK && getenv("GNNB_FUSED_TIMING") != nullptr) {
+        rc = plan->timing.ensure(16 * sizeof(unsigned long long));
+        if (rc == GNNB_OK) cudaMemset(plan->timing.ptr, 0, 16 * sizeof(unsigned long long));
+    }
+    if (rc != GNNB_OK) { delete plan; return rc; }
+    const float *base = plan->images.as<float>();
+    size_t pi = 0;
+    for (int k = 0; k < d.num_layers; k++) {
+        const LayerPack &L = m->layers[k];
+        p.fi[k] = L.fi; p.fo[k] = L.fo;
+        auto mk = [&](const Pending &q, const float *bias) {
+            TLinear t;
+            t.img = base + q.off; t.bias = bias; t.K = q.K; t.N = q.N;
+            t.KA = (q.K + tc::ATOM_K - 1) / tc::ATOM_K;
+            return t;
+        };
+        p.l0[k] = mk(pend[pi++], L.a.bias);
+        if (d.conv_type == GNNB_CONV_GIN) p.l1[k] = mk(pend[pi++], L.b.bias);
+    }
+    for (int j = 0; j < d.mlp_num_linear; j++) {
+        HLinear h;
+        h.Wt = m->head[j].Wt; h.bias = m->head[j].bias; h.in = m->head[j].in;
+        h.out = m->head[j].out; h.ldw = m->head[j].ldw;
+        p.head[j] = h;
+    }
+    plan->smem_bytes = 1024 + 3 * (size_t)REGION + sizeof(Misc);
+    cudaError_t e = cudaFuncSetAttribute(fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)plan->smem_bytes);
+    if (e != cudaSuccess) {
+        delete plan;
+        return cuda_fail(e, "cudaFuncSetAttribute(fused_tc_kernel)", __FILE__, __LINE__);
+    }
+    m->fused_tc = plan;
+    return GNNB_OK;
+}
+
+void fused_tc_release(gnnb_model *m)
+{
+    TcPlan *plan = plan_of(m);
+    if (plan) {
+        plan->images.release(); plan->bounds.release(); plan->flag.release();
+        plan->scratch.release(); plan->timing.release();
+        delete plan;
+        m->fused_tc = nullptr;
+    }
+}
+
+bool fused_tc_supports(const gnnb_model *m, int max_nodes_in_batch, int max_edges_in_batch)
+{
+    return m->fused_tc != nullptr && max_nodes_in_batch <= MAX_NODES_PER_GRAPH &&
+           max_edges_in_batch <= ECAP / 4;
+}
+
+int fused_tc_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_t *node_ptr,
+                 const int64_t *edge_ptr, int n_graphs, int64_t total_nodes, int max_nodes,
+                 float *out, cudaStream_t s, int *launches)
+{
+    TcPlan *plan = plan_of(m);
+    GNNB_REQUIRE(plan != nullptr, "tensor-core fused kernel not available for this model");
+    if (max_nodes < 1) max_nodes = 1;
+    GNNB_REQUIRE(max_nodes <= MAX_NODES_PER_GRAPH, "graph too large for the fused kernel");
+    const int window = TM - max_nodes + 1;
+    const int64_t n_tiles64 = total_nodes / window + 1;
+    GNNB_REQUIRE(n_tiles64 < (1ll << 30), "too many tiles");
+    const int n_tiles = (int)n_tiles64;
+    GNNB_TRY(plan->bounds.ensure(sizeof(int32_t) * ((size_t)n_tiles + 1)));
+    GNNB_CUDA(cudaMemsetAsync(plan->flag.ptr, 0, sizeof(int), s));
+    tc_tile_bounds_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, s>>>(node_ptr, n_graphs, window,
+                                                                    n_tiles,
+                                                                    plan->bounds.as<int32_t>());
+    GNNB_CUDA(cudaGetLastError());
+    TcParams p = plan->params;
+    p.x = x; p.coo = coo; p.node_ptr = node_ptr; p.edge_ptr = edge_ptr; p.n_graphs = n_graphs;
+    p.out = out; p.tile_bounds = plan->bounds.as<int32_t>(); p.n_tiles = n_tiles;
+    p.error_flag = plan->flag.as<int>();
+    p.scratch = plan->scratch.as<float>();
+    p.timing = plan->timing.as<unsigned long long>();
+    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+    fused_tc_kernel<<<grid, NTHREADS, plan->smem_bytes, s>>>(p);
+    GNNB_CUDA(cudaGetLastError());
+    if (launches) *launches += 2;
+    return GNNB_OK;
+}
+
+int fused_tc_status(gnnb_model *m, int *status)
+{
+    *status = 0;
+    TcPlan *plan = plan_of(m);
+    if (plan == nullptr) return GNNB_OK;
+    GNNB_CUDA(cudaMemcpy(status, plan->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (plan->timing.ptr != nullptr) {
+        unsigned long long t[16];
+        GNNB_CUDA(cudaMemcpy(t, plan->timing.ptr, sizeof(t), cudaMemcpyDeviceToHost));
+        GNNB_CUDA(cudaMemset(plan->timing.ptr, 0, sizeof(t)));
+        const char *names[6] = {"stage", "tables", "aggregate", "gemm", "pool", "head"};
+        unsigned long long tot = 0;
+        for (int i = 0; i < 6; i++) tot += t[i];
+        fprintf(stderr, "[gnnb fused-tc phases]");
+        for (int i = 0; i < 6; i++)
+            fprintf(stderr, " %s %.1f%%", names[i], tot ? 100.0 * (double)t[i] / (double)tot : 0.0);
+        fprintf(stderr, " (total %.3g cycles over all CTAs)\n", (double)tot);
+    }
+    return GNNB_OK;
+}
+
+}  // namespace gnnb

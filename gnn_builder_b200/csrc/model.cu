@@ -214,6 +214,7 @@ extern "C" int gnnb_model_destroy(gnnb_model_t *m)
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     fused_release(m);
+    fused_tc_release(m);
     m->prof.release();
     DeviceBuf *bufs[] = {&m->weights, &m->st_x, &m->st_coo, &m->st_nptr, &m->st_eptr, &m->st_out,
                          &m->in_deg, &m->out_deg, &m->offsets, &m->nbr, &m->dinv, &m->feat[0],
@@ -344,7 +345,9 @@ extern "C" int gnnb_model_finalize(gnnb_model_t *m)
         m->layers.push_back(lp);
     }
     fused_release(m);
+    fused_tc_release(m);
     GNNB_TRY(fused_prepare(m));
+    GNNB_TRY(fused_tc_prepare(m));
     m->finalized = true;
     return GNNB_OK;
 }
@@ -365,7 +368,9 @@ extern "C" int gnnb_model_set_math(gnnb_model_t *m, int math)
 
 extern "C" int gnnb_model_last_launches(const gnnb_model_t *m) { return m ? m->last_launches : 0; }
 extern "C" int gnnb_model_last_path(const gnnb_model_t *m) { return m ? m->last_path : 0; }
+extern "C" int gnnb_model_last_kernel(const gnnb_model_t *m) { return m ? m->last_kernel : 0; }
 extern "C" void *gnnb_model_stream(gnnb_model_t *m) { return m ? (void *)m->stream : nullptr; }
+static int fused_any_status(gnnb_model_t *m, int *status);
 extern "C" int gnnb_model_synchronize(gnnb_model_t *m)
 {
     GNNB_REQUIRE(m != nullptr, "null model");
@@ -374,7 +379,7 @@ extern "C" int gnnb_model_synchronize(gnnb_model_t *m)
     if (m->last_path == GNNB_PATH_FUSED) {
         // the async entry point cannot fall back by itself: report capacity/index problems here
         int status = 0;
-        GNNB_TRY(fused_status(m, &status));
+        GNNB_TRY(fused_any_status(m, &status));
         if (status == 1) {
             set_error("fused kernel: a tile exceeded its node/edge capacity (raise nothing: set "
                       "accurate max_nodes/max_edges hints or use gnnb_model_run_batch, which "
@@ -563,22 +568,47 @@ static int check_ready(gnnb_model_t *m)
     return GNNB_OK;
 }
 
-static int choose_path(gnnb_model_t *m, int max_n, int max_e, int *path)
+// kernel ids: 1 layerwise, 2 fused fp32-FMA (fused.cu), 3 fused tcgen05 (fused_tc.cu)
+static int choose_path(gnnb_model_t *m, int max_n, int max_e, int *path, int *kernel)
 {
-    const bool can_fuse = m->math == GNNB_MATH_FAST && fused_supports(m, max_n, max_e);
+    const bool fast = m->math == GNNB_MATH_FAST;
+    const bool can_tc = fast && fused_tc_supports(m, max_n, max_e);
+    const bool can_fma = fast && fused_supports(m, max_n, max_e);
     if (m->path == GNNB_PATH_FUSED) {
-        if (!can_fuse) {
+        if (!can_tc && !can_fma) {
             set_error("fused path requested but unsupported for this model/batch (graph larger than "
                       "a CTA tile, strict math, or unsupported dims)");
             return GNNB_ERR_INVALID;
         }
         *path = GNNB_PATH_FUSED;
+        *kernel = can_tc ? 3 : 2;
     } else if (m->path == GNNB_PATH_LAYERWISE) {
         *path = GNNB_PATH_LAYERWISE;
+        *kernel = 1;
     } else {
-        *path = can_fuse ? GNNB_PATH_FUSED : GNNB_PATH_LAYERWISE;
+        // AUTO: the tensor-core fused kernel when it applies, else the layerwise path (measured
+        // faster than the fp32-FMA fused kernel, profiles/)
+        *path = can_tc ? GNNB_PATH_FUSED : GNNB_PATH_LAYERWISE;
+        *kernel = can_tc ? 3 : 1;
     }
     return GNNB_OK;
+}
+
+static int run_fused(gnnb_model_t *m, int kernel, const float *x, const int32_t *coo,
+                     const int64_t *np, const int64_t *ep, int n_graphs, int64_t total_nodes,
+                     int max_nodes, float *out, cudaStream_t s)
+{
+    ProfScope ps(m->prof, PROF_FUSED, s);
+    if (kernel == 3)
+        return fused_tc_run(m, x, coo, np, ep, n_graphs, total_nodes, max_nodes, out, s,
+                            &m->last_launches);
+    return fused_run(m, x, coo, np, ep, n_graphs, total_nodes, max_nodes, out, s,
+                     &m->last_launches);
+}
+
+static int fused_any_status(gnnb_model_t *m, int *status)
+{
+    return m->last_kernel == 3 ? fused_tc_status(m, status) : fused_status(m, status);
 }
 
 extern "C" int gnnb_model_run_batch_async(gnnb_model_t *m, const float *x, const int32_t *edge_list,
@@ -592,17 +622,16 @@ extern "C" int gnnb_model_run_batch_async(gnnb_model_t *m, const float *x, const
     GNNB_REQUIRE(is_device_pointer(x) || total_nodes == 0, "run_batch_async needs device pointers");
     cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
     m->last_launches = 0;
-    int path;
+    int path, kernel;
     // without host copies of the offsets the capacity hints decide whether tiles fit
     const int hint_n = m->d.max_nodes > 0 ? m->d.max_nodes : (1 << 30);
     const int hint_e = m->d.max_edges > 0 ? m->d.max_edges : (1 << 30);
-    GNNB_TRY(choose_path(m, hint_n, hint_e, &path));
+    GNNB_TRY(choose_path(m, hint_n, hint_e, &path, &kernel));
     m->last_path = path;
-    if (path == GNNB_PATH_FUSED) {
-        ProfScope ps(m->prof, PROF_FUSED, s);
-        return fused_run(m, x, edge_list, node_ptr, edge_ptr, n_graphs, total_nodes, hint_n, out, s,
-                         &m->last_launches);
-    }
+    m->last_kernel = kernel;
+    if (path == GNNB_PATH_FUSED)
+        return run_fused(m, kernel, x, edge_list, node_ptr, edge_ptr, n_graphs, total_nodes, hint_n,
+                         out, s);
     return run_layerwise(m, x, edge_list, node_ptr, edge_ptr, 0, 0, n_graphs, total_nodes,
                          total_edges, out, s, &m->last_launches);
 }
@@ -667,9 +696,10 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
         dout = m->st_out.as<float>();
     }
     m->last_launches = 0;
-    int path;
-    GNNB_TRY(choose_path(m, (int)max_n, (int)max_e, &path));
+    int path, kernel;
+    GNNB_TRY(choose_path(m, (int)max_n, (int)max_e, &path, &kernel));
     m->last_path = path;
+    m->last_kernel = kernel;
     auto layerwise_chunks = [&]() -> int {
         // chunk the union so that the per-layer activations stay within a fixed budget
         const int64_t kChunkNodes = 4ll << 20;
@@ -686,14 +716,10 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
         return GNNB_OK;
     };
     if (path == GNNB_PATH_FUSED) {
-        {
-            ProfScope ps(m->prof, PROF_FUSED, s);
-            GNNB_TRY(fused_run(m, dx, dcoo, dnp, dep, n_graphs, T, (int)max_n, dout, s,
-                               &m->last_launches));
-        }
+        GNNB_TRY(run_fused(m, kernel, dx, dcoo, dnp, dep, n_graphs, T, (int)max_n, dout, s));
         GNNB_CUDA(cudaStreamSynchronize(s));
         int status = 0;
-        GNNB_TRY(fused_status(m, &status));
+        GNNB_TRY(fused_any_status(m, &status));
         if (status == 2) {
             set_error("edge_list holds a node index outside its graph");
             return GNNB_ERR_INVALID;
@@ -704,6 +730,7 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
                 return GNNB_ERR_INVALID;
             }
             m->last_path = GNNB_PATH_LAYERWISE;
+            m->last_kernel = 1;
             GNNB_TRY(layerwise_chunks());
         }
     } else {

@@ -28,8 +28,9 @@ struct LayerPack {
     PackedLinear a, b, c, d;  // meaning depends on the conv type (see model.cu pack_layer)
 };
 
-// fused-kernel weight image (fused.cu)
+// fused-kernel plans (fused.cu, fused_tc.cu)
 struct FusedPlan;
+struct TcPlan;
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py uses it
 // for the live roofline numbers).  Off by default: no events are recorded.
@@ -86,6 +87,7 @@ struct gnnb_model {
     std::vector<gnnb::LayerPack> layers;
     std::vector<gnnb::PackedLinear> head;
     gnnb::FusedPlan *fused = nullptr;
+    gnnb::TcPlan *fused_tc = nullptr;
 
     // staging for host-pointer calls
     gnnb::DeviceBuf st_x, st_coo, st_nptr, st_eptr, st_out;
@@ -97,6 +99,7 @@ struct gnnb_model {
     gnnb::Profiler prof;
     int last_launches = 0;
     int last_path = 0;
+    int last_kernel = 0;  // 1 layerwise, 2 fused fp32-FMA, 3 fused tcgen05
     const float *last_emb = nullptr;
     int last_emb_ld = 0;
     int64_t last_emb_rows = 0;
@@ -126,5 +129,14 @@ int fused_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_t *
 // after the stream is synchronised: 0 ok, 1 a tile overflowed (re-run layerwise), 2 bad edge index
 int fused_status(gnnb_model *m, int *status);
 int fused_tile_rows(const gnnb_model *m);
+
+// fused_tc.cu: same contract as the fused_* functions, tensor-core node transform
+int fused_tc_prepare(gnnb_model *m);
+void fused_tc_release(gnnb_model *m);
+bool fused_tc_supports(const gnnb_model *m, int max_nodes_in_batch, int max_edges_in_batch);
+int fused_tc_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_t *node_ptr,
+                 const int64_t *edge_ptr, int n_graphs, int64_t total_nodes, int max_nodes,
+                 float *out, cudaStream_t s, int *launches);
+int fused_tc_status(gnnb_model *m, int *status);
 
 }  // namespace gnnb

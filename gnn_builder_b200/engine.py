@@ -84,6 +84,12 @@ class Engine:
     def last_path(self) -> int:
         return int(self.lib.gnnb_model_last_path(self._h))
 
+    KERNEL_NAMES = {0: "none", 1: "layerwise", 2: "fused-fma", 3: "fused-tcgen05"}
+
+    @property
+    def last_kernel(self) -> str:
+        return self.KERNEL_NAMES[int(self.lib.gnnb_model_last_kernel(self._h))]
+
     @property
     def stream(self) -> int:
         return int(self.lib.gnnb_model_stream(self._h) or 0)

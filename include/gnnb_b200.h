@@ -123,6 +123,8 @@ int gnnb_model_get_node_embeddings(gnnb_model_t *m, float *dst, int64_t total_no
 /* statistics of the most recent run: kernels launched by this library, and which path ran */
 int gnnb_model_last_launches(const gnnb_model_t *m);
 int gnnb_model_last_path(const gnnb_model_t *m);
+/* which kernel family ran: 1 layerwise, 2 fused (fp32 FMA node transform), 3 fused (tcgen05) */
+int gnnb_model_last_kernel(const gnnb_model_t *m);
 /* optional per-kernel-class timing with CUDA events on the launching stream: ms[8]/counts[8]
  * indexed 0 tables, 1 aggregation, 2 GEMM, 3 pooling, 4 fused kernel; reading resets */
 int gnnb_model_set_profile(gnnb_model_t *m, int on);

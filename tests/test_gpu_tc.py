@@ -46,4 +46,4 @@ def test_tc_gemm_wide_dynamic_range():
     W = (rng.standard_normal((128, 128)) * 10.0 ** rng.integers(-3, 4, (128, 128))).astype(np.float32)
     ref = A.astype(np.float64) @ W.astype(np.float64).T
     scale = np.abs(A).astype(np.float64) @ np.abs(W).astype(np.float64).T
-    assert np.max(np.abs(tc_gemm(A, W) - ref) / scale) < 2e-6
+    assert np.max(np.abs(tc_gemm(A, W) - ref) / scale) < 5e-6
