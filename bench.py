@@ -248,6 +248,130 @@ def workload_config(w, args, per_gpu_graphs):
     }
 
 
+# ------------------------------------------------------------------------------ large graph (C5)
+def run_large(args, w):
+    """BASELINE configs[4]: GCN 2-layer hidden=128 on one power-law graph (2M nodes, avg in-degree
+    16).  N = 1: the layerwise kernels through the model handle, aggregation timed live for the
+    HBM roofline.  N > 1: 1D row partition + NCCL all-gather of the feature shards per layer."""
+    import torch
+
+    import gnn_builder_b200 as gnnb
+    from gnn_builder_b200.distributed import LargeGraphGCN, RowPartition
+
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    local_rank = env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.nodes or w.large_nodes
+    n -= n % world
+    model = gnnb.build_model(w, seed=0)
+    x, coo = gnnb.make_powerlaw_graph(n, w.large_avg_degree, w.in_dim, seed=w.seed)
+    E, F, L = int(coo.shape[0]), w.in_dim, w.num_layers
+    agg_bytes_layer = E * (4 * F + 8) + n * (4 * F + 4 * F + 8)
+    peaks_fp = ROOT / "MEASURED_PEAKS.json"
+    peaks = json.loads(peaks_fp.read_text()) if peaks_fp.exists() else {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    sampler = ClockSampler(local_rank)
+    roofline, launches, cpu_baseline = None, 0, None
+    if world == 1:
+        eng = gnnb.Engine(model, device=local_rank, path=gnnb.PATH_LAYERWISE)
+        dx, dcoo = torch.from_numpy(x).cuda(), torch.from_numpy(coo).cuda()
+        dn = torch.tensor([0, n], dtype=torch.int64, device="cuda")
+        de = torch.tensor([0, E], dtype=torch.int64, device="cuda")
+        dout = torch.empty((1, w.out_dim), device="cuda")
+        step = lambda: eng.run_device(dx, dcoo, dn, de, dout, 1, n, E)  # noqa: E731
+        stream = torch.cuda.ExternalStream(eng.stream)
+        sync = eng.synchronize
+    else:
+        part = RowPartition(n, world)
+        r0, r1 = part.rows(rank)
+        runner = LargeGraphGCN(model, n, rank, world, dist=dist).setup(part.local_edges(coo, rank))
+        x_local = torch.from_numpy(x[r0:r1]).cuda()
+        step = lambda: runner.forward(x_local)  # noqa: E731
+        stream = torch.cuda.current_stream()
+        sync = torch.cuda.synchronize
+    for _ in range(args.warmup):
+        step()
+    sync()
+    if world == 1:
+        launches = eng.last_launches
+    sampler.start()
+    time.sleep(0.3)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0w = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+    sync()
+    torch.cuda.synchronize()
+    t1w = time.time()
+    clocks = sampler.stop(t0w, t1w)
+    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item())
+    value = E * L / (ms_per_step * 1e-3)
+    e2e = None
+    if world == 1:
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.steps // 2)):
+            eng.run_graph(x, coo)
+        e2e_s = (time.perf_counter() - t0) / max(1, args.steps // 2)
+        e2e = {"value": E * L / e2e_s, "unit": "edges/s",
+               "h2d_bytes_per_step": int(x.nbytes + coo.nbytes + 32),
+               "d2h_bytes_per_step": int(w.out_dim * 4), "ms_per_step": e2e_s * 1e3}
+        eng.set_profile(True)
+        for _ in range(2):
+            step()
+        prof = eng.read_profile()
+        eng.set_profile(False)
+        agg_ms = prof["aggregate"]["ms"] / 2 / L
+        achieved = agg_bytes_layer / (agg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "aggregate (agg_rows_kernel + agg_heavy_kernel)",
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None,
+                    "kernel_ms": agg_ms, "algorithmic_bytes_per_layer": agg_bytes_layer,
+                    "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                    "class_ms_per_step": {k: v["ms"] / 2 for k, v in prof.items()}}
+        if rank == 0 and not args.no_cpu_baseline:
+            sys.path.insert(0, str(ROOT / "oracle"))
+            from oracle import ref_available, ref_big_gcn_rate
+
+            if ref_available():
+                rows = min(n, 40000)
+                Wm = model.named_parameter_arrays()["gnn_convs_0_conv_lin_weight"]
+                bm = model.named_parameter_arrays()["gnn_convs_0_conv_bias"]
+                rate, secs, edges_done, t_tab, _ = ref_big_gcn_rate(x, coo, n, Wm, bm, rows)
+                cpu_baseline = {"value": rate, "unit": "edges/s", "cores": 1, "kind": "reference",
+                                "sample": f"reference gcn_conv<2000000,40000000,128,128> over the "
+                                          f"first {rows} destination rows ({edges_done} edges, "
+                                          f"{secs:.1f} s) of the same graph; tables {t_tab:.1f} s"}
+    if rank == 0:
+        line = {"metric": "edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{w.name}: GCN {L}-layer hidden={w.hidden_dim}, power-law "
+                                       f"graph N={n} E={E} F={F}; value = E x layers / step time",
+                           "partition": "single GPU" if world == 1 else
+                           f"1D row partition over {world} GPUs, NCCL all-gather of feature shards",
+                           "l2_policy": "feature matrix (1 GB) larger than L2; no flush"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * args.steps),
+                "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -262,6 +386,7 @@ def main():
                     help="graphs per process per step of the reference arm")
     ap.add_argument("--cpu-baseline-graphs", type=int, default=8000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nodes", type=int, default=0, help="large-graph workloads: node count")
     args = ap.parse_args()
 
     from gnn_builder_b200.configs import WORKLOADS
@@ -269,6 +394,9 @@ def main():
     w = WORKLOADS[args.workload]
     if args.graphs <= 0:
         args.graphs = w.n_graphs
+    if w.large_nodes and args.impl != "reference":
+        run_large(args, w)
+        return
     if args.impl == "reference":
         run_reference_arm(args, w)
         return
@@ -343,7 +471,7 @@ def main():
         step_device()
     eng.synchronize()
     launches_per_step = eng.last_launches
-    path_used = {gnnb.PATH_FUSED: "fused", gnnb.PATH_LAYERWISE: "layerwise"}[eng.last_path]
+    path_used = eng.last_kernel
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)

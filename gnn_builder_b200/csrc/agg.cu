@@ -104,7 +104,7 @@ __device__ __forceinline__ void finish_row(const AggArgs &a, int v, int deg_v, f
 {
     if (MODE == AGG_GCN) {
         Vec<VEC> xs;
-        xs.load(a.x + (size_t)v * a.ldx + c);
+        xs.load(a.x + (size_t)(v + a.row_base) * a.ldx + c);
         if (STRICT) {
             const float di = __fadd_rn(1.0f, (float)deg_v);
             const float ss = __fdiv_rn(1.0f, __fsqrt_rn(__fmul_rn(di, di)));  // lib:1266-1267
@@ -118,7 +118,7 @@ __device__ __forceinline__ void finish_row(const AggArgs &a, int v, int deg_v, f
         }
     } else if (MODE == AGG_GIN) {
         Vec<VEC> xs;
-        xs.load(a.x + (size_t)v * a.ldx + c);
+        xs.load(a.x + (size_t)(v + a.row_base) * a.ldx + c);
         const float s = __fadd_rn(1.0f, a.eps);  // lib:1522
 #pragma unroll
         for (int i = 0; i < VEC; i++) acc.v[i] = __fadd_rn(acc.v[i], __fmul_rn(xs.v[i], s));
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) agg_rows_kernel(const AggArgs a)
         const int deg_v = __ldg(a.in_deg + v);
         if (a.n_heavy > 0 && deg_v > a.heavy_threshold) continue;  // CTA-per-row kernel does these
         const int off = __ldg(a.offsets + v);
-        const float dinv_v = (MODE == AGG_GCN && !STRICT) ? __ldg(a.dinv + v) : 0.0f;
+        const float dinv_v = (MODE == AGG_GCN && !STRICT) ? __ldg(a.dinv + v + a.row_base) : 0.0f;
         for (int c = lg * VEC; c < a.F; c += LPR * VEC) {
             Vec<VEC> acc;
 #pragma unroll
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) agg_heavy_kernel(const AggArgs a)
         const int v = __ldg(a.heavy_rows + h);
         const int deg_v = __ldg(a.in_deg + v);
         const int off = __ldg(a.offsets + v);
-        const float dinv_v = (MODE == AGG_GCN) ? __ldg(a.dinv + v) : 0.0f;
+        const float dinv_v = (MODE == AGG_GCN) ? __ldg(a.dinv + v + a.row_base) : 0.0f;
         const int per = (deg_v + 7) / 8;
         const int k0 = min(deg_v, warp * per), k1 = min(deg_v, (warp + 1) * per);
         for (int c = lane * VEC; c < a.F; c += 32 * VEC) {

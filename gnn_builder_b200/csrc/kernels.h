@@ -26,6 +26,11 @@ int build_degree_tables(const int32_t *edge_list, int n, int e, int32_t *in_deg,
 int build_neighbor_tables(const int32_t *edge_list, const int32_t *in_deg, int n, int e,
                           int32_t *offsets, int32_t *nbr, int32_t *edge_index, TableWorkspace &ws,
                           cudaStream_t s, int *launches);
+// CSR slice of a 1D row partition: edge_list holds the in-edges of the owned destination rows
+// [row_begin, row_begin + n_local) with GLOBAL node ids; neighbors keep their global ids
+int build_partition_tables(const int32_t *edge_list, int row_begin, int n_local, int e,
+                           int32_t *in_deg_local, int32_t *offsets_local, int32_t *nbr_global,
+                           TableWorkspace &ws, cudaStream_t s, int *launches);
 // rows with in-degree > threshold, compacted into ws.heavy_rows; count returned through host ptr
 int find_heavy_rows(const int32_t *in_deg, int n, int threshold, TableWorkspace &ws,
                     int *n_heavy_host, cudaStream_t s, int *launches);
@@ -49,6 +54,8 @@ struct AggArgs {
     const int32_t *heavy_rows;  // optional list of rows handled by the CTA-per-row kernel
     int n_heavy;
     int heavy_threshold;
+    int row_base;          // row-partitioned graphs: global id of local row 0 (x / dinv are global,
+                           // offsets / in_deg / out are local); 0 otherwise
 };
 int launch_agg(const AggArgs &a, bool strict, cudaStream_t s, int *launches);
 

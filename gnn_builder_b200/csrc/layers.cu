@@ -404,3 +404,78 @@ extern "C" int gnnb_global_max_pool(int num_nodes, int num_edges, const float *x
     (void)num_edges;
     return pool_common(GNNB_POOL_MAX, num_nodes, x, pooled, emb);
 }
+
+// ============================================================================ row partition
+// One large graph split by destination rows across GPUs (the reference has no
+// counterpart: it holds one graph in static MAX_NODES arrays).  All pointers are DEVICE pointers
+// and the work is enqueued on `stream` (e.g. torch's current stream) so that it orders with the
+// NCCL all-gather of the feature shards issued on the same stream.
+namespace {
+struct PartitionCache {
+    TableWorkspace ws;
+    DeviceBuf wt, agg;
+    const int32_t *heavy_key = nullptr;
+    int heavy_n = 0, n_heavy = 0;
+};
+thread_local PartitionCache g_part;
+}  // namespace
+
+extern "C" int gnnb_partition_tables(const int32_t *edge_list_local, int row_begin, int n_local,
+                                     int num_edges_local, int32_t *in_degree_local,
+                                     int32_t *offsets_local, int32_t *neighbor_table_global,
+                                     void *stream)
+{
+    GNNB_REQUIRE(n_local >= 0 && num_edges_local >= 0 && row_begin >= 0, "negative size");
+    GNNB_REQUIRE(num_edges_local == 0 || is_device_pointer(edge_list_local),
+                 "gnnb_partition_tables takes device pointers");
+    g_part.heavy_key = nullptr;
+    return build_partition_tables(edge_list_local, row_begin, n_local, num_edges_local,
+                                  in_degree_local, offsets_local, neighbor_table_global, g_part.ws,
+                                  (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int gnnb_degree_inv_sqrt(const int32_t *in_degree, float *dinv, int n, void *stream)
+{
+    GNNB_REQUIRE(n >= 0, "negative size");
+    return compute_dinv(in_degree, dinv, n, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int gnnb_gcn_conv_partition(int n_local, int row_begin, int n_total, int num_edges_local,
+                                       const float *x_full, float *y_local,
+                                       const int32_t *offsets_local,
+                                       const int32_t *neighbor_table_global,
+                                       const int32_t *in_degree_local, const float *dinv_full,
+                                       const float *weight, const float *bias,
+                                       const float *skip_local, int emb_in, int emb_out, int act,
+                                       void *stream)
+{
+    (void)num_edges_local;
+    GNNB_REQUIRE(n_local >= 0 && row_begin >= 0 && row_begin + n_local <= n_total, "bad row range");
+    GNNB_REQUIRE(emb_in > 0 && emb_out > 0 && act >= 0 && act <= GNNB_ACT_COS, "bad dims");
+    if (n_local == 0) return GNNB_OK;
+    GNNB_REQUIRE(is_device_pointer(x_full) && is_device_pointer(y_local),
+                 "gnnb_gcn_conv_partition takes device pointers");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int ldw = round_up(emb_out, 4), lda = round_up(emb_in, 4);
+    GNNB_TRY(g_part.wt.ensure(sizeof(float) * (size_t)emb_in * ldw));
+    GNNB_TRY(g_part.agg.ensure(sizeof(float) * (size_t)n_local * lda));
+    GNNB_TRY(launch_transpose_weight(weight, g_part.wt.as<float>(), emb_out, emb_in, ldw, s, nullptr));
+    if (g_part.heavy_key != in_degree_local || g_part.heavy_n != n_local) {
+        GNNB_TRY(find_heavy_rows(in_degree_local, n_local, 1024, g_part.ws, &g_part.n_heavy, s,
+                                 nullptr));
+        g_part.heavy_key = in_degree_local;
+        g_part.heavy_n = n_local;
+    }
+    AggArgs a{};
+    a.mode = AGG_GCN; a.x = x_full; a.ldx = emb_in; a.F = emb_in; a.out = g_part.agg.as<float>();
+    a.ldo = lda; a.offsets = offsets_local; a.nbr = neighbor_table_global; a.in_deg = in_degree_local;
+    a.dinv = dinv_full; a.n = n_local; a.row_base = row_begin;
+    a.heavy_rows = g_part.ws.heavy_rows.as<int32_t>(); a.n_heavy = g_part.n_heavy;
+    a.heavy_threshold = 1024;
+    GNNB_TRY(launch_agg(a, false, s, nullptr));
+    GemmArgs g = simple_gemm(a.out, lda, emb_in, g_part.wt.as<float>(), ldw, bias, y_local, emb_out,
+                             n_local, emb_out, act);
+    g.skip = skip_local; g.ldskip = emb_out;
+    GNNB_TRY(launch_gemm(g, false, s, nullptr));
+    return GNNB_OK;
+}

@@ -64,6 +64,28 @@ __global__ void gather_sources_kernel(const int32_t *__restrict__ edge_list,
         nbr[i] = __ldg(edge_list + 2 * (size_t)__ldg(edge_index + i));
 }
 
+// row-partitioned graph: this rank owns destination rows [row_begin, row_begin + n_local); sources
+// keep their global ids
+__global__ void edge_prepare_partition_kernel(const int32_t *__restrict__ edge_list, int e,
+                                              int row_begin, int n_local,
+                                              uint32_t *__restrict__ keys, int32_t *__restrict__ vals,
+                                              int32_t *__restrict__ in_deg, int *__restrict__ bad)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
+        const int2 sd = __ldg(reinterpret_cast<const int2 *>(edge_list) + i);
+        const int dst = sd.y - row_begin;
+        if ((unsigned)dst >= (unsigned)n_local) {
+            atomicExch(bad, 1);
+            keys[i] = 0;
+            vals[i] = 0;
+            continue;
+        }
+        keys[i] = (uint32_t)dst;
+        vals[i] = sd.x;
+        atomicAdd(in_deg + dst, 1);
+    }
+}
+
 __global__ void heavy_rows_kernel(const int32_t *__restrict__ in_deg, int n, int threshold,
                                   int32_t *__restrict__ rows, int32_t *__restrict__ counter)
 {
@@ -202,6 +224,34 @@ int build_tables(const int32_t *edge_list, const int64_t *node_ptr, const int64_
         } else {
             GNNB_TRY(sort_pairs(ws, e, n, nbr, s, launches));
         }
+    }
+    return GNNB_OK;
+}
+
+int build_partition_tables(const int32_t *edge_list, int row_begin, int n_local, int e,
+                           int32_t *in_deg_local, int32_t *offsets_local, int32_t *nbr_global,
+                           TableWorkspace &ws, cudaStream_t s, int *launches)
+{
+    if (n_local <= 0) return GNNB_OK;
+    GNNB_CUDA(cudaMemsetAsync(in_deg_local, 0, sizeof(int32_t) * (size_t)n_local, s));
+    int bad_host = 0;
+    if (e > 0) {
+        GNNB_TRY(ws.keys_in.ensure(sizeof(uint32_t) * (size_t)e));
+        GNNB_TRY(ws.vals_in.ensure(sizeof(int32_t) * (size_t)e));
+        GNNB_TRY(ws.counters.ensure(sizeof(int32_t) * 4));
+        GNNB_CUDA(cudaMemsetAsync(ws.counters.ptr, 0, sizeof(int32_t) * 4, s));
+        edge_prepare_partition_kernel<<<grid_for(e, 256), 256, 0, s>>>(
+            edge_list, e, row_begin, n_local, ws.keys_in.as<uint32_t>(), ws.vals_in.as<int32_t>(),
+            in_deg_local, ws.counters.as<int32_t>());
+        GNNB_CUDA(cudaGetLastError());
+        if (launches) ++*launches;
+    }
+    GNNB_TRY(scan_offsets(in_deg_local, offsets_local, n_local, ws, s, launches));
+    if (e > 0) {
+        GNNB_TRY(sort_pairs(ws, e, n_local, nbr_global, s, launches));
+        GNNB_CUDA(cudaMemcpyAsync(&bad_host, ws.counters.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+        GNNB_CUDA(cudaStreamSynchronize(s));
+        GNNB_REQUIRE(bad_host == 0, "partition tables: an edge's destination is outside the owned rows");
     }
     return GNNB_OK;
 }

@@ -185,6 +185,24 @@ int gnnb_global_add_pool(int num_nodes, int num_edges, const float *x, float *po
 int gnnb_global_mean_pool(int num_nodes, int num_edges, const float *x, float *pooled, int emb);
 int gnnb_global_max_pool(int num_nodes, int num_edges, const float *x, float *pooled, int emb);
 
+/* ---- one large graph, 1D row partition across GPUs (no reference counterpart) ---- */
+/* DEVICE pointers only; work is enqueued on `stream` (a cudaStream_t, NULL = default stream).
+ * This rank owns destination rows [row_begin, row_begin + n_local); edge_list_local holds their
+ * in-edges with GLOBAL node ids.  Tables: in-degree and offsets of the owned rows, neighbor table
+ * with global source ids, stable in COO order like lib:1086-1124. */
+int gnnb_partition_tables(const int32_t *edge_list_local, int row_begin, int n_local,
+                          int num_edges_local, int32_t *in_degree_local, int32_t *offsets_local,
+                          int32_t *neighbor_table_global, void *stream);
+/* dinv[i] = 1 / sqrt(1 + in_degree[i]) (the factorised GCN normalisation, lib:1249-1252) */
+int gnnb_degree_inv_sqrt(const int32_t *in_degree, float *dinv, int n, void *stream);
+/* y_local[n_local][emb_out] = act(gcn_conv(x_full)[owned rows] (+ skip_local)); x_full holds the
+ * features of ALL n_total nodes (after the halo all-gather), dinv_full their 1/sqrt(1+deg). */
+int gnnb_gcn_conv_partition(int n_local, int row_begin, int n_total, int num_edges_local,
+                            const float *x_full, float *y_local, const int32_t *offsets_local,
+                            const int32_t *neighbor_table_global, const int32_t *in_degree_local,
+                            const float *dinv_full, const float *weight, const float *bias,
+                            const float *skip_local, int emb_in, int emb_out, int act, void *stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------- */
 /* One-CTA tensor-core GEMM C[128][N] = A[128][K] . W[N][K]^T (tcgen05, 3xTF32) built from the
  * same primitives as the fused kernel's node transform; host buffers; K <= 128, N % 16 == 0. */

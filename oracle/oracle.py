@@ -374,3 +374,38 @@ class RefModel:
             x, coo = batch.graph(g)
             out[g] = self(x, coo)
         return out
+
+
+def ref_big_gcn_rate(x, coo, n, W, b, num_rows: int):
+    """Reference CPU baseline for the large-graph config: the reference's own
+    compute_degree_tables / compute_neighbor_tables / gcn_conv<2000000, 40000000, 128, 128>
+    driven on heap buffers.  Times one gcn_conv layer over the first ``num_rows`` destination rows
+    of the graph.  Returns (edges_per_second, seconds, edges_done, table_seconds).  The reference
+    keeps `int neighbors[MAX_NODES]` (8 MB) on the stack, hence the big-stack thread."""
+    import threading
+    import time
+
+    lib = C.CDLL(str(OUT / "libgnnb_ref_layers.so"))
+    x, W, b = _c32(x), _c32(W), _c32(b)
+    coo = _ci(coo).reshape(-1, 2)
+    e = coo.shape[0]
+    ind, outd = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    off, nbr = np.zeros(n, np.int32), np.zeros(e, np.int32)
+    y = np.zeros((max(num_rows, 1), 128), np.float32)
+    res = {}
+
+    def work():
+        t0 = time.perf_counter()
+        lib.ref_big_tables(_i(coo), _i(ind), _i(outd), _i(off), _i(nbr), C.c_int(n), C.c_int(e))
+        t1 = time.perf_counter()
+        lib.ref_big_gcn_conv_128_128(C.c_int(num_rows), C.c_int(e), _f(x), _f(y), _i(coo), _i(off),
+                                     _i(nbr), _i(ind), _i(outd), _f(W), _f(b))
+        res["t_tables"], res["t_conv"] = t1 - t0, time.perf_counter() - t1
+
+    threading.stack_size(512 * 1024 * 1024)
+    th = threading.Thread(target=work)
+    th.start()
+    th.join()
+    threading.stack_size(0)
+    edges_done = int(ind[:num_rows].sum())
+    return edges_done / res["t_conv"], res["t_conv"], edges_done, res["t_tables"], y

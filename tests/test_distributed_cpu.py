@@ -1,0 +1,163 @@
+"""Host-side logic of the N > 1 paths on CPU: world_size-2 `gloo` process groups.
+
+The product has no CPU compute path, so these tests inject a *checker* backend (numpy + the
+oracle) into the orchestration code and verify what the orchestration is responsible for: shard
+ranges, the row partition, the all-gather / all-reduce plumbing and the assembly of results."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+class NumpyBackend:
+    """Checker backend for LargeGraphGCN: numpy restatement of the partitioned GCN layer."""
+
+    def to_device(self, a):
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(a))
+
+    def partition_tables(self, coo_local, row_begin, n_local):
+        import torch
+        coo = coo_local.numpy()
+        dst = coo[:, 1] - row_begin
+        order = np.argsort(dst, kind="stable")
+        ind = np.bincount(dst, minlength=n_local).astype(np.int32)
+        off = np.concatenate([[0], np.cumsum(ind)[:-1]]).astype(np.int32)
+        return torch.from_numpy(ind), torch.from_numpy(off), torch.from_numpy(coo[order, 0].copy())
+
+    def dinv(self, in_deg_full):
+        return 1.0 / (1.0 + in_deg_full.float()).sqrt()
+
+    def gcn_layer(self, x_full, tables, dinv_full, row_begin, W, b, skip, act):
+        import torch
+        ind, off, nbr = tables
+        n_local = ind.shape[0]
+        rows = torch.repeat_interleave(torch.arange(n_local), ind.long())
+        msg = x_full[nbr.long()] * dinv_full[nbr.long()].view(-1, 1)
+        agg = torch.zeros(n_local, x_full.shape[1]).index_add_(0, rows, msg)
+        dv = dinv_full[row_begin:row_begin + n_local].view(-1, 1)
+        agg = agg * dv + x_full[row_begin:row_begin + n_local] * dv * dv
+        y = agg @ W.T + b
+        if skip is not None:
+            y = y + skip
+        return torch.relu(y) if act == 1 else y
+
+    def pool_partial(self, x_local):
+        return x_local.sum(0), x_local.max(0).values
+
+    def head(self, pooled, linears, mlp_act, out_act):
+        import torch
+        h = pooled
+        for j, (W, b) in enumerate(linears):
+            h = W @ h + b
+            if j < len(linears) - 1 and mlp_act == 1:
+                h = torch.relu(h)
+        return h
+
+    def all_gather_rows(self, dist, x_local, n_total):
+        import torch
+        full = torch.empty((n_total, x_local.shape[1]), dtype=x_local.dtype)
+        dist.all_gather_into_tensor(full, x_local.contiguous())
+        return full
+
+    def all_reduce(self, dist, t, op):
+        dist.all_reduce(t, op=op)
+        return t
+
+
+class OracleEngine:
+    """Checker stand-in for Engine (tests only): runs a shard through the CPU oracle."""
+
+    def __init__(self, model):
+        sys.path.insert(0, str(ROOT / "oracle"))
+        from oracle import Oracle
+        self.orc, self.model = Oracle(), model
+        self.params = list(model.named_parameter_arrays().values())
+        self.out_dim = model.output_features_dim
+
+    def run(self, batch):
+        return self.orc.model_forward_batch(self.model.describe(), self.params, batch)
+
+
+def _worker(rank, world, port, result_dir):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "oracle"))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import dataclasses
+        import gnn_builder_b200 as gnnb
+        from gnn_builder_b200 import distributed as D
+        from gnn_builder_b200.configs import C1, C5
+        from gnn_builder_b200.data import make_powerlaw_graph
+        from oracle import Oracle
+
+        # ---- independent graphs: shard, run, gather
+        w = dataclasses.replace(C1, hidden_dim=12, in_dim=5, mlp_hidden_dim=8)
+        model = gnnb.build_model(w, seed=0)
+        batch = gnnb.make_molecular_batch(37, w.mu_nodes, w.mu_edges, w.in_dim, seed=3)
+        eng = OracleEngine(model)
+        out = D.run_sharded(eng, batch, rank, world, gather=True, dist=dist)
+        ref = eng.run(batch)
+        assert np.array_equal(out, ref), "sharded + gathered outputs differ from the single run"
+
+        # ---- one large graph: row partition + all-gather per layer
+        n = 600
+        wl = dataclasses.replace(C5, in_dim=16, hidden_dim=16, out_dim=4, mlp_hidden_dim=8)
+        big = gnnb.build_model(wl, seed=1)
+        x, coo = make_powerlaw_graph(n, 6, wl.in_dim, seed=9, max_degree=80)
+        part = D.RowPartition(n, world)
+        r0, r1 = part.rows(rank)
+        runner = D.LargeGraphGCN(big, n, rank, world, dist=dist, backend=NumpyBackend())
+        runner.setup(part.local_edges(coo, rank))
+        out, emb_local = runner.forward(x[r0:r1], return_embeddings=True)
+        orc = Oracle()
+        ref_out, ref_emb = orc.model_forward(big.describe(),
+                                             list(big.named_parameter_arrays().values()), x, coo,
+                                             return_node_emb=True)
+        assert np.abs(emb_local.numpy() - ref_emb[r0:r1]).max() < 1e-5
+        assert np.abs(out.numpy() - ref_out).max() < 1e-4 * max(1.0, np.abs(ref_out).max())
+        Path(result_dir, f"ok_{rank}").write_text("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
+
+
+def test_shard_ranges_balance_and_cover():
+    sys.path.insert(0, str(ROOT))
+    import gnn_builder_b200 as gnnb
+    from gnn_builder_b200.distributed import RowPartition, shard_ranges
+
+    b = gnnb.make_molecular_batch(1000, 18, 38, 11, seed=2)
+    for world in (1, 2, 4, 8):
+        r = shard_ranges(b.node_ptr, world)
+        assert r[0][0] == 0 and r[-1][1] == b.n_graphs
+        assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+        nodes = [int(b.node_ptr[g1] - b.node_ptr[g0]) for g0, g1 in r]
+        assert max(nodes) - min(nodes) <= 2 * int(np.diff(b.node_ptr).max())
+    # row partition: every edge belongs to exactly one rank, order preserved
+    rng = np.random.default_rng(0)
+    coo = rng.integers(0, 64, (500, 2)).astype(np.int32)
+    part = RowPartition(64, 4)
+    pieces = [part.local_edges(coo, r) for r in range(4)]
+    assert sum(p.shape[0] for p in pieces) == 500
+    for r, p in enumerate(pieces):
+        lo, hi = part.rows(r)
+        assert ((p[:, 1] >= lo) & (p[:, 1] < hi)).all()
+    with pytest.raises(ValueError):
+        RowPartition(65, 4)
