@@ -92,7 +92,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.dev)],
+                 "-lms", "50", "-i", str(self.dev)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -114,7 +114,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         for ts, line in self.lines:
-            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+            if t0 is not None and not (t0 - 0.12 <= ts <= t1 + 0.12):
                 continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
@@ -300,7 +300,7 @@ def run_large(args, w):
     if world == 1:
         launches = eng.last_launches
     sampler.start()
-    time.sleep(0.3)
+    time.sleep(1.2)  # nvidia-smi needs about a second before its first sample
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -474,7 +474,7 @@ def main():
     path_used = eng.last_kernel
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.3)
+    time.sleep(1.2)  # nvidia-smi needs about a second before its first sample
     barrier()
     t_wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
