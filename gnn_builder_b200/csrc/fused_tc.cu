@@ -5,18 +5,25 @@
 //
 // Per CTA (one per SM, 256 threads, 128-row tile of packed graphs):
 //   shared memory   R_X  64 KB  layer input X, canonical K-major SWIZZLE_128B layout; while a GEMM
-//                               runs it is the 2-stage ring the weight atoms are bulk-copied into
+//                               runs it is the ring of weight slots the bulk copies land in
 //                   R_HI 64 KB  A operand, hi parts   (aggregate, then the GIN hidden layer)
 //                   R_LO 64 KB  A operand, lo parts
 //   tensor memory   128 columns x 128 lanes fp32 accumulator
 //   weights         pre-split (hi/lo) and pre-swizzled on the host into the exact shared-memory
 //                   image of each 32-wide K atom, so one cp.async.bulk (TMA engine, no tensor map)
 //                   per atom lands them ready for the MMA; they stay L2 resident across CTAs.
-// One elected thread issues the bulk copies and the MMAs (12 per K atom: hi.hi, lo.hi, hi.lo for
-// four k-steps of 8) and signals completion through mbarriers; all 8 warps run the aggregation
+// One elected thread issues the bulk copies and the MMAs and signals completion through mbarriers.
+// A GEMM is a sequence of "units": first the hi weight atoms (each: A_hi.B_hi and A_lo.B_hi, four
+// k-steps of 8), then the lo atoms (A_hi.B_lo).  With N = 128 the ring holds 4 slots of 16 KB, so
+// ALL hi atoms of a K = 128 GEMM are in flight at once (one L2 latency), and each lo atom is
+// fetched into the slot of a finished hi unit while later units run.  GIN's second GEMM has its
+// first slots prefetched while the first GEMM's epilogue runs.  All 8 warps run the aggregation
 // before and the TMEM -> register -> shared epilogue (bias, skip, activation, hi/lo re-split) after.
 // The skip connection of interior layers needs X after R_X has been recycled for the weight ring:
 // X is parked in a per-CTA global scratch (64 KB, L2 resident) and re-read in the epilogue.
+// The MLP head (fp32 FMA, 16 graphs per call) is deferred: pooled vectors queue in a per-CTA
+// pending buffer and the head runs once 16 graphs are waiting, so its weight streaming is
+// amortised over ~3 tiles.
 //
 // Supported: GCN and GIN, every layer width a multiple of 16 up to 128 (BASELINE configs 1 and 2);
 // everything else uses fused.cu / the layerwise path.
@@ -36,17 +43,22 @@ namespace {
 constexpr int TM = 128;
 constexpr int ECAP = 2048;
 constexpr int NTHREADS = 256;
+constexpr int NWARPS = NTHREADS / 32;
 constexpr int MAX_LAYERS = 8;
 constexpr int MAX_HEAD = 6;
-constexpr int HEAD_G = 16;
+constexpr int HEAD_G = 16;       // graphs per head call
 constexpr int HBK = 32;          // k rows per staged head-weight tile
+constexpr int HSTAGES = 4;       // head weight ring depth (4 x 16 KB = R_HI)
 constexpr int MAX_DIM = 128;
 constexpr int HLD = 132;         // row stride of the head ping-pong buffers
+constexpr int PLD = 520;         // row stride of the pending pooled vectors (>= 512 + 4)
 constexpr int REGION = TM * MAX_DIM * 4;  // 64 KB
+constexpr int MAX_SLOTS = 8;
 constexpr int MAX_NODES_PER_GRAPH = 64;
+constexpr int AGG_R = 4;         // destination rows aggregated concurrently per warp
 
 struct TLinear {
-    const float *img;   // weight image, KA atoms of [hi N x 128 B | lo N x 128 B]
+    const float *img;   // weight image: per K atom [hi N x 128 B | lo N x 128 B]
     const float *bias;
     int K, N, KA;
 };
@@ -71,13 +83,17 @@ struct TcParams {
     const int32_t *tile_bounds;
     int n_tiles;
     int *error_flag;
-    float *scratch;               // [gridDim.x][128][128] parked X for the skip connection
+    float *scratch;               // [grid][128][128] parked X for the skip connection
+    float *pending;               // [grid][HEAD_G][PLD] pooled vectors waiting for the head
     unsigned long long *timing;
 };
 
 struct Misc {
-    uint64_t bar_full[2], bar_empty[2], bar_done;
+    uint64_t bar_full[MAX_SLOTS], bar_empty[MAX_SLOTS], bar_done;
+    uint32_t full_cnt[MAX_SLOTS], empty_cnt[MAX_SLOTS];
     uint32_t tmem_slot;
+    int pend_n;
+    int pend_gid[HEAD_G];
     float dinv[TM];
     int deg[TM];
     int off[TM + 1];
@@ -120,51 +136,67 @@ __global__ void tc_tile_bounds_kernel(const int64_t *__restrict__ node_ptr, int 
     bounds[t] = (t == n_tiles) ? n_graphs : lower_bound64(node_ptr, n_graphs, (int64_t)t * window);
 }
 
-struct PipeState {
-    uint32_t full_cnt[2];
-    uint32_t empty_cnt[2];
-};
-
-// Issued by ONE thread: D[128][N] (tensor memory) = A(hi,lo)[128][KA*32] . W^T, 3xTF32.
-// The weight atoms stream through the 2-stage ring at `ring` (R_X).
-__device__ __forceinline__ void gemm_issue(Misc &ms, PipeState &ps, uint32_t tmem_d,
-                                           uint32_t a_hi, uint32_t a_lo, unsigned char *ring,
-                                           const TLinear &L)
+// ---------------------------------------------------------------------------------------
+// GEMM issue (ONE thread).  D[128][N] (tensor memory) = A(hi,lo)[128][KA*32] . W^T, 3xTF32.
+__device__ __forceinline__ int gemm_slots(const TLinear &L)
 {
-    const uint32_t stage_bytes = 2u * (uint32_t)L.N * tc::ROW_BYTES;
-    const uint32_t idesc = tc::make_idesc_tf32(TM, L.N);
-    const unsigned char *src = reinterpret_cast<const unsigned char *>(L.img);
-    tc::tc_fence_after();
-    for (int s = 0; s < 2 && s < L.KA; s++) {
-        tc::mbar_expect_tx(&ms.bar_full[s], stage_bytes);
-        tc::bulk_g2s(ring + (size_t)s * stage_bytes, src + (size_t)s * stage_bytes, stage_bytes,
-                     &ms.bar_full[s]);
+    const int s = REGION / (L.N * tc::ROW_BYTES);
+    return s < MAX_SLOTS ? s : MAX_SLOTS;
+}
+__device__ __forceinline__ const unsigned char *unit_src(const TLinear &L, int u)
+{
+    const int part = u >= L.KA ? 1 : 0, ka = part ? u - L.KA : u;
+    return reinterpret_cast<const unsigned char *>(L.img) +
+           ((size_t)ka * 2 + part) * (size_t)L.N * tc::ROW_BYTES;
+}
+// start the bulk copies of the first min(slots, units) weight slots
+__device__ __forceinline__ void gemm_prefetch(Misc &ms, unsigned char *ring, const TLinear &L)
+{
+    const uint32_t slot_bytes = (uint32_t)L.N * tc::ROW_BYTES;
+    const int U = 2 * L.KA, ns = gemm_slots(L);
+    for (int u = 0; u < ns && u < U; u++) {
+        tc::mbar_expect_tx(&ms.bar_full[u], slot_bytes);
+        tc::bulk_g2s(ring + (size_t)u * slot_bytes, unit_src(L, u), slot_bytes, &ms.bar_full[u]);
     }
-    for (int ka = 0; ka < L.KA; ka++) {
-        const int s = ka & 1;
-        tc::mbar_wait(&ms.bar_full[s], ps.full_cnt[s] & 1);
-        ps.full_cnt[s]++;
+}
+__device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo,
+                                           unsigned char *ring, const TLinear &L, bool prefetched)
+{
+    const uint32_t slot_bytes = (uint32_t)L.N * tc::ROW_BYTES;
+    const uint32_t idesc = tc::make_idesc_tf32(TM, L.N);
+    const int U = 2 * L.KA, ns = gemm_slots(L);
+    if (!prefetched) gemm_prefetch(ms, ring, L);
+    tc::tc_fence_after();
+    for (int u = 0; u < U; u++) {
+        const int s = u % ns;
+        tc::mbar_wait(&ms.bar_full[s], ms.full_cnt[s] & 1);
+        ms.full_cnt[s]++;
         tc::tc_fence_after();
+        const int part = u >= L.KA ? 1 : 0, ka = part ? u - L.KA : u;
         const uint32_t ah = a_hi + (uint32_t)ka * TM * tc::ROW_BYTES;
         const uint32_t al = a_lo + (uint32_t)ka * TM * tc::ROW_BYTES;
-        const uint32_t bh = tc::smem_u32(ring) + (uint32_t)s * stage_bytes;
-        const uint32_t bl = bh + (uint32_t)L.N * tc::ROW_BYTES;
+        const uint32_t b = tc::smem_u32(ring) + (uint32_t)s * slot_bytes;
 #pragma unroll
         for (int k8 = 0; k8 < tc::ATOM_K / tc::MMA_K; k8++) {
             const uint32_t ko = (uint32_t)k8 * tc::MMA_K * 4;
-            const uint32_t acc = (ka == 0 && k8 == 0) ? 0u : 1u;
-            tc::mma_tf32(tmem_d, tc::make_desc(ah + ko), tc::make_desc(bh + ko), idesc, acc);
-            tc::mma_tf32(tmem_d, tc::make_desc(al + ko), tc::make_desc(bh + ko), idesc, 1u);
-            tc::mma_tf32(tmem_d, tc::make_desc(ah + ko), tc::make_desc(bl + ko), idesc, 1u);
+            if (part == 0) {
+                tc::mma_tf32(tmem_d, tc::make_desc(ah + ko), tc::make_desc(b + ko), idesc,
+                             (u == 0 && k8 == 0) ? 0u : 1u);
+                tc::mma_tf32(tmem_d, tc::make_desc(al + ko), tc::make_desc(b + ko), idesc, 1u);
+            } else {
+                tc::mma_tf32(tmem_d, tc::make_desc(ah + ko), tc::make_desc(b + ko), idesc, 1u);
+            }
         }
         tc::mma_commit(&ms.bar_empty[s]);
-        ps.empty_cnt[s]++;
-        if (ka >= 1 && ka + 1 < L.KA) {  // refill the stage atom ka-1 used with atom ka+1
-            const int sp = (ka - 1) & 1;
-            tc::mbar_wait(&ms.bar_empty[sp], (ps.empty_cnt[sp] - 1) & 1);
-            tc::mbar_expect_tx(&ms.bar_full[sp], stage_bytes);
-            tc::bulk_g2s(ring + (size_t)sp * stage_bytes, src + (size_t)(ka + 1) * stage_bytes,
-                         stage_bytes, &ms.bar_full[sp]);
+        ms.empty_cnt[s]++;
+        // refill the slot of the PREVIOUS unit (its MMAs were issued before this unit's, so the
+        // wait is short and this unit's MMAs keep the tensor core busy meanwhile)
+        if (u >= 1 && u - 1 + ns < U) {
+            const int sp = (u - 1) % ns;
+            tc::mbar_wait(&ms.bar_empty[sp], (ms.empty_cnt[sp] - 1) & 1);
+            tc::mbar_expect_tx(&ms.bar_full[sp], slot_bytes);
+            tc::bulk_g2s(ring + (size_t)sp * slot_bytes, unit_src(L, u - 1 + ns), slot_bytes,
+                         &ms.bar_full[sp]);
         }
     }
     tc::mma_commit(&ms.bar_done);
@@ -188,16 +220,18 @@ __device__ __forceinline__ void epilogue(uint32_t tmem_d, int N, const float *__
         for (int j4 = 0; j4 < 8; j4++) {
             float o[4];
             float4 sk = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (skip != nullptr && c0 + j4 * 4 < N)
-                sk = __ldg(reinterpret_cast<const float4 *>(skip + (size_t)row * MAX_DIM + c0 + j4 * 4));
-            const float sks[4] = {sk.x, sk.y, sk.z, sk.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int col = c0 + j4 * 4 + j;
-                float t = 0.0f;
-                if (col < N) t = act_apply_compact(act, v[j4 * 4 + j] + __ldg(bias + col) + sks[j]);
-                o[j] = t;
+            float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool in_range = c0 + j4 * 4 < N;  // N % 4 == 0
+            if (in_range) {
+                bs = __ldg(reinterpret_cast<const float4 *>(bias + c0 + j4 * 4));
+                if (skip != nullptr)
+                    sk = __ldg(reinterpret_cast<const float4 *>(skip + (size_t)row * MAX_DIM + c0 + j4 * 4));
             }
+            const float sks[4] = {sk.x, sk.y, sk.z, sk.w};
+            const float bss[4] = {bs.x, bs.y, bs.z, bs.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                o[j] = in_range ? act_apply_compact(act, v[j4 * 4 + j] + bss[j] + sks[j]) : 0.0f;
             const uint32_t off = tc::canon_chunk_offset(row, c0 + j4 * 4, TM);
             if (split) {
                 float h[4], l[4];
@@ -212,11 +246,13 @@ __device__ __forceinline__ void epilogue(uint32_t tmem_d, int N, const float *__
     }
 }
 
-// one MLP-head linear for up to 16 graphs (fp32 FMA; weights streamed through `ws`)
+// one MLP-head linear for up to 16 graphs (fp32 FMA).  Thread = (graph tid/16, columns cg*4 and
+// 64+cg*4); the weights stream through a 4-stage cp.async ring (`ws`, 4 x [32][128] floats) so
+// three K tiles are in flight while one is consumed.  A may live in global or shared memory.
 __device__ __noinline__ void head_linear(float *ws, const float *A, int lda, int K, const float *Wt,
                                          int ldw, const float *bias, int N, int act,
                                          float *dst_smem, int ldo, float *dst_global, int ldg,
-                                         int n_rows)
+                                         const int *gids, int n_rows)
 {
     constexpr int BN = MAX_DIM;
     const int tid = threadIdx.x;
@@ -230,9 +266,9 @@ __device__ __noinline__ void head_linear(float *ws, const float *A, int lda, int
             acc[q][j] = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.0f;
         }
     const int nt = (K + HBK - 1) / HBK;
-    auto issue = [&](int t, int buf) {
+    auto issue = [&](int t) {
         constexpr int GPR = BN / 4;
-        float *w = ws + buf * HBK * BN;
+        float *w = ws + (t % HSTAGES) * HBK * BN;
         const int k0 = t * HBK;
         for (int g = tid; g < HBK * GPR; g += NTHREADS) {
             const int kk = g / GPR, c4 = (g % GPR) * 4;
@@ -242,18 +278,18 @@ __device__ __noinline__ void head_linear(float *ws, const float *A, int lda, int
         }
         cp_async_commit();
     };
-    const float *a = A + (gi < n_rows ? gi : 0) * lda;
-    issue(0, 0);
+    const float *a = A + (size_t)(gi < n_rows ? gi : 0) * lda;
+    for (int t = 0; t < HSTAGES - 1 && t < nt; t++) issue(t);
 #pragma unroll 1
     for (int t = 0; t < nt; t++) {
-        if (t + 1 < nt) {
-            issue(t + 1, (t + 1) & 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+        if (t + HSTAGES - 1 < nt) issue(t + HSTAGES - 1);
+        const int newer = min(HSTAGES - 1, nt - 1 - t);  // groups allowed to stay in flight
+        if (newer >= 3) cp_async_wait<3>();
+        else if (newer == 2) cp_async_wait<2>();
+        else if (newer == 1) cp_async_wait<1>();
+        else cp_async_wait<0>();
         __syncthreads();
-        const float *w = ws + (t & 1) * HBK * BN;
+        const float *w = ws + (t % HSTAGES) * HBK * BN;
         const int k0 = t * HBK;
         const int kn = min(HBK, K - k0);
 #pragma unroll 4
@@ -269,6 +305,7 @@ __device__ __noinline__ void head_linear(float *ws, const float *A, int lda, int
         __syncthreads();
     }
     if (gi < n_rows) {
+        float *drow = dst_global != nullptr ? dst_global + (size_t)gids[gi] * ldg : nullptr;
 #pragma unroll
         for (int q = 0; q < 2; q++)
 #pragma unroll
@@ -276,11 +313,30 @@ __device__ __noinline__ void head_linear(float *ws, const float *A, int lda, int
                 const int col = q * 64 + cg * 4 + j;
                 if (col >= N) continue;
                 const float v = act_apply_compact(act, acc[q][j]);
-                if (dst_global != nullptr) dst_global[(size_t)gi * ldg + col] = v;
+                if (drow != nullptr) drow[col] = v;
                 else dst_smem[gi * ldo + col] = v;
             }
     }
     __syncthreads();
+}
+
+// run the MLP head over the pending pooled vectors (all threads)
+__device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, unsigned char *RHI,
+                                           unsigned char *RLO, const float *pending, int n_rows)
+{
+    float *ws = reinterpret_cast<float *>(RHI);
+    float *hb0 = reinterpret_cast<float *>(RLO);
+    float *hb1 = hb0 + HEAD_G * HLD;
+    const float *hin = pending;
+    int hld = PLD, hk = p.emb * p.num_pools;
+    for (int j = 0; j < p.mlp_num_linear; j++) {
+        const bool last = j == p.mlp_num_linear - 1;
+        float *hout = (j & 1) ? hb1 : hb0;
+        head_linear(ws, hin, hld, hk, p.head[j].Wt, p.head[j].ldw, p.head[j].bias, p.head[j].out,
+                    last ? p.out_act : p.mlp_act, hout, HLD, last ? p.out : nullptr, p.mlp_out,
+                    ms.pend_gid, n_rows);
+        hin = hout; hld = HLD; hk = p.head[j].out;
+    }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
@@ -300,155 +356,214 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
 
     if (warp == 0) tc::tmem_alloc(&ms.tmem_slot, 128);
     if (tid == 0) {
-        tc::mbar_init(&ms.bar_full[0], 1); tc::mbar_init(&ms.bar_full[1], 1);
-        tc::mbar_init(&ms.bar_empty[0], 1); tc::mbar_init(&ms.bar_empty[1], 1);
+        for (int i = 0; i < MAX_SLOTS; i++) {
+            tc::mbar_init(&ms.bar_full[i], 1);
+            tc::mbar_init(&ms.bar_empty[i], 1);
+            ms.full_cnt[i] = 0;
+            ms.empty_cnt[i] = 0;
+        }
         tc::mbar_init(&ms.bar_done, 1);
         tc::mbar_fence_init();
+        ms.pend_n = 0;
     }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_d = ms.tmem_slot;
-    PipeState ps{{0u, 0u}, {0u, 0u}};
     uint32_t done_cnt = 0;
     float *scratch = p.scratch + (size_t)blockIdx.x * TM * MAX_DIM;
+    float *pending = p.pending + (size_t)blockIdx.x * HEAD_G * PLD;
+    const int emb = p.emb;
+
+    // geometry of the first tile; later tiles are prefetched one iteration ahead
+    int g0 = 0, g1 = 0;
+    int64_t row0 = 0, e0 = 0, row1 = 0, e1 = 0;
+    if ((int)blockIdx.x < p.n_tiles) {
+        g0 = __ldg(p.tile_bounds + blockIdx.x);
+        g1 = __ldg(p.tile_bounds + blockIdx.x + 1);
+        row0 = __ldg(p.node_ptr + g0); row1 = __ldg(p.node_ptr + g1);
+        e0 = __ldg(p.edge_ptr + g0); e1 = __ldg(p.edge_ptr + g1);
+    }
 
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        // ------------------------------------------------------------------ tile geometry
-        const int g0 = __ldg(p.tile_bounds + tile), g1 = __ldg(p.tile_bounds + tile + 1);
         const int ng = g1 - g0;
-        if (ng <= 0) continue;
-        const int64_t row0 = __ldg(p.node_ptr + g0);
-        const int64_t e0 = __ldg(p.edge_ptr + g0);
-        const int rows = (int)(__ldg(p.node_ptr + g1) - row0);
-        const int ne = (int)(__ldg(p.edge_ptr + g1) - e0);
-        if (rows > TM || ne > ECAP || ng > TM) {
-            if (tid == 0) atomicExch(p.error_flag, 1);
-            continue;
+        const int rows = (int)(row1 - row0);
+        const int ne = (int)(e1 - e0);
+        const int cur_g0 = g0;
+        const int64_t cur_row0 = row0, cur_e0 = e0;
+        // next tile's graph range: issue the loads now, consume them after the table build
+        const int nxt = tile + gridDim.x;
+        int ng0 = 0, ng1 = 0;
+        if (nxt < p.n_tiles) {
+            ng0 = __ldg(p.tile_bounds + nxt);
+            ng1 = __ldg(p.tile_bounds + nxt + 1);
         }
-        __syncthreads();
-        for (int i = tid; i <= ng; i += NTHREADS) {
-            ms.grow[i] = (int)(__ldg(p.node_ptr + g0 + i) - row0);
-            ms.gedge[i] = (int)(__ldg(p.edge_ptr + g0 + i) - e0);
-        }
-        {   // node features -> R_X (canonical layout), zero padded to whole K atoms; rows beyond
-            // the tile are zeroed too so that no stale NaN/Inf pattern ever enters an MMA
-            const int F = p.in_dim, Fp = (F + 31) & ~31;
-            const float *src = p.x + (size_t)row0 * F;
-            for (int idx = tid; idx < TM * Fp; idx += NTHREADS) {
-                const int r = idx / Fp, c = idx - r * Fp;
-                const float v = (r < rows && c < F) ? __ldg(src + (size_t)r * F + c) : 0.0f;
-                *reinterpret_cast<float *>(RX + tc::canon_offset(r, c, TM)) = v;
+        const bool bad = rows > TM || ne > ECAP || ng > TM;
+        if (bad && tid == 0) atomicExch(p.error_flag, 1);
+        if (ng > 0 && !bad) {
+            __syncthreads();
+            // ---------------------------------------------------------------- stage inputs
+            for (int i = tid; i <= ng; i += NTHREADS) {
+                ms.grow[i] = (int)(__ldg(p.node_ptr + cur_g0 + i) - cur_row0);
+                ms.gedge[i] = (int)(__ldg(p.edge_ptr + cur_g0 + i) - cur_e0);
             }
-        }
-        __syncthreads();
-        for (int i = tid; i < ng; i += NTHREADS)
-            for (int r = ms.grow[i]; r < ms.grow[i + 1]; r++) ms.rowg[r] = i;
-        {
-            const int2 *coo = reinterpret_cast<const int2 *>(p.coo) + e0;
-            for (int j = tid; j < ne; j += NTHREADS) {
-                const int2 sd = __ldg(coo + j);
-                int lo = 0, hi = ng;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (ms.gedge[mid] <= j) lo = mid; else hi = mid;
-                }
-                const int b = ms.grow[lo], n_i = ms.grow[lo + 1] - b;
-                if ((unsigned)sd.x >= (unsigned)n_i || (unsigned)sd.y >= (unsigned)n_i) {
-                    atomicExch(p.error_flag, 2);
-                    ms.edges[j] = 0xffff;
-                } else {
-                    ms.edges[j] = (unsigned short)(((sd.y + b) << 8) | (sd.x + b));
+            {   // node features -> R_X (canonical layout), zero padded to whole K atoms; rows
+                // beyond the tile are zeroed too so no stale NaN/Inf ever enters an MMA
+                const int F = p.in_dim, Fp = (F + 31) & ~31;
+                const float *src = p.x + (size_t)cur_row0 * F;
+                for (int idx = tid; idx < TM * Fp; idx += NTHREADS) {
+                    const int r = idx / Fp, c = idx - r * Fp;
+                    const float v = (r < rows && c < F) ? __ldg(src + (size_t)r * F + c) : 0.0f;
+                    *reinterpret_cast<float *>(RX + tc::canon_offset(r, c, TM)) = v;
                 }
             }
-        }
-        __syncthreads();
-        GNNB_PHASE(0)
-        // ------------------------------------------------------------------ tables (lib:1051-1124)
-        int my_deg = 0;
-        if (tid < TM) {
-            if (tid < rows) {
-                const int gi = ms.rowg[tid];
-                for (int j = ms.gedge[gi]; j < ms.gedge[gi + 1]; j++)
-                    my_deg += ((ms.edges[j] >> 8) == tid) ? 1 : 0;
-            }
-            ms.deg[tid] = my_deg;
-            ms.dinv[tid] = 1.0f / sqrtf(1.0f + (float)my_deg);
-            int incl = my_deg;
+            int2 my_edge[ECAP / NTHREADS];
+            {   // edge list: issue the global loads before the barrier, localise after it
+                const int2 *coo = reinterpret_cast<const int2 *>(p.coo) + cur_e0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += v;
-            }
-            if (lane == 31) ms.scan_tmp[warp] = incl;
-            ms.off[tid] = incl - my_deg;
-        }
-        __syncthreads();
-        if (tid < TM) {
-            int b = 0;
-            for (int w = 0; w < warp; w++) b += ms.scan_tmp[w];
-            const int o = ms.off[tid] + b;
-            ms.off[tid] = o;
-            if (tid < rows) {
-                const int gi = ms.rowg[tid];
-                int pos = o;
-                for (int j = ms.gedge[gi]; j < ms.gedge[gi + 1]; j++) {
-                    const unsigned short ed = ms.edges[j];
-                    if ((ed >> 8) == tid) ms.nbr[pos++] = (unsigned char)(ed & 0xff);
+                for (int q = 0; q < ECAP / NTHREADS; q++) {
+                    const int j = tid + q * NTHREADS;
+                    my_edge[q] = (j < ne) ? __ldg(coo + j) : make_int2(0, 0);
                 }
             }
+            __syncthreads();
+            for (int i = tid; i < ng; i += NTHREADS)
+                for (int r = ms.grow[i]; r < ms.grow[i + 1]; r++) ms.rowg[r] = i;
+#pragma unroll
+            for (int q = 0; q < ECAP / NTHREADS; q++) {
+                const int j = tid + q * NTHREADS;
+                if (j < ne) {
+                    const int2 sd = my_edge[q];
+                    int lo = 0, hi = ng;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (ms.gedge[mid] <= j) lo = mid; else hi = mid;
+                    }
+                    const int b = ms.grow[lo], n_i = ms.grow[lo + 1] - b;
+                    if ((unsigned)sd.x >= (unsigned)n_i || (unsigned)sd.y >= (unsigned)n_i) {
+                        atomicExch(p.error_flag, 2);
+                        ms.edges[j] = 0xffff;
+                    } else {
+                        ms.edges[j] = (unsigned short)(((sd.y + b) << 8) | (sd.x + b));
+                    }
+                }
+            }
+            __syncthreads();
+            GNNB_PHASE(0)
+            // ---------------------------------------------------------------- tables (lib:1051-1124)
+            int my_deg = 0;
+            if (tid < TM) {
+                if (tid < rows) {
+                    const int gi = ms.rowg[tid];
+                    for (int j = ms.gedge[gi]; j < ms.gedge[gi + 1]; j++)
+                        my_deg += ((ms.edges[j] >> 8) == tid) ? 1 : 0;
+                }
+                ms.deg[tid] = my_deg;
+                ms.dinv[tid] = 1.0f / sqrtf(1.0f + (float)my_deg);
+                int incl = my_deg;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                if (lane == 31) ms.scan_tmp[warp] = incl;
+                ms.off[tid] = incl - my_deg;
+            }
+            __syncthreads();
+            if (tid < TM) {
+                int b = 0;
+                for (int w = 0; w < warp; w++) b += ms.scan_tmp[w];
+                const int o = ms.off[tid] + b;
+                ms.off[tid] = o;
+                if (tid < rows) {
+                    const int gi = ms.rowg[tid];
+                    int pos = o;
+                    for (int j = ms.gedge[gi]; j < ms.gedge[gi + 1]; j++) {
+                        const unsigned short ed = ms.edges[j];
+                        if ((ed >> 8) == tid) ms.nbr[pos++] = (unsigned char)(ed & 0xff);
+                    }
+                }
+            }
+            __syncthreads();
+            GNNB_PHASE(1)
         }
-        __syncthreads();
-        GNNB_PHASE(1)
+        // second half of the next tile's geometry (the bounds have arrived by now)
+        if (nxt < p.n_tiles) {
+            g0 = ng0; g1 = ng1;
+            row0 = __ldg(p.node_ptr + ng0); row1 = __ldg(p.node_ptr + ng1);
+            e0 = __ldg(p.edge_ptr + ng0); e1 = __ldg(p.edge_ptr + ng1);
+        }
+        if (ng <= 0 || bad) continue;
 
-        // ------------------------------------------------------------------ conv layers
+        // -------------------------------------------------------------------- conv layers
         for (int l = 0; l < p.num_layers; l++) {
             const int fi = p.fi[l];
             const int kp = (fi + 31) & ~31;
             const bool do_skip = p.skip && l != 0 && l != p.num_layers - 1;  // cpp:269-279
-            // aggregate X -> (hi, lo) A operand; one warp per row, lanes across K (float4)
-            for (int r = warp; r < TM; r += NTHREADS / 32) {
-                const int c = lane * 4;
-                if (c >= kp) continue;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < rows) {
-                    const int d = ms.deg[r], o = ms.off[r];
-                    for (int k = 0; k < d; k++) {
-                        const int u = ms.nbr[o + k];
-                        const float4 v = *reinterpret_cast<const float4 *>(
-                            RX + tc::canon_chunk_offset(u, c, TM));
-                        if (p.conv_type == GNNB_CONV_GCN) {
-                            const float s = ms.dinv[u];
-                            acc.x = fmaf(v.x, s, acc.x); acc.y = fmaf(v.y, s, acc.y);
-                            acc.z = fmaf(v.z, s, acc.z); acc.w = fmaf(v.w, s, acc.w);
-                        } else {
-                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            // aggregate X -> (hi, lo) A operand: a warp works on AGG_R rows at a time (independent
+            // gather chains), lanes across K (float4 each)
+            const int c = lane * 4;
+            if (c < kp) {
+                for (int rb = warp * AGG_R; rb < TM; rb += NWARPS * AGG_R) {
+                    int d[AGG_R], o[AGG_R];
+                    float4 acc[AGG_R];
+                    int kmax = 0;
+#pragma unroll
+                    for (int j = 0; j < AGG_R; j++) {
+                        const int r = rb + j;
+                        d[j] = r < rows ? ms.deg[r] : 0;
+                        o[j] = ms.off[r];
+                        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        kmax = max(kmax, d[j]);
+                    }
+                    for (int k = 0; k < kmax; k++) {
+#pragma unroll
+                        for (int j = 0; j < AGG_R; j++) {
+                            if (k < d[j]) {
+                                const int u = ms.nbr[o[j] + k];
+                                const float4 v = *reinterpret_cast<const float4 *>(
+                                    RX + tc::canon_chunk_offset(u, c, TM));
+                                if (p.conv_type == GNNB_CONV_GCN) {
+                                    const float s = ms.dinv[u];
+                                    acc[j].x = fmaf(v.x, s, acc[j].x); acc[j].y = fmaf(v.y, s, acc[j].y);
+                                    acc[j].z = fmaf(v.z, s, acc[j].z); acc[j].w = fmaf(v.w, s, acc[j].w);
+                                } else {
+                                    acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
+                                }
+                            }
                         }
                     }
-                    const float4 xs = *reinterpret_cast<const float4 *>(
-                        RX + tc::canon_chunk_offset(r, c, TM));
-                    if (p.conv_type == GNNB_CONV_GCN) {  // lib:1249-1278, factorised
-                        const float dv = ms.dinv[r], ss = dv * dv;
-                        acc.x = fmaf(xs.x, ss, acc.x * dv); acc.y = fmaf(xs.y, ss, acc.y * dv);
-                        acc.z = fmaf(xs.z, ss, acc.z * dv); acc.w = fmaf(xs.w, ss, acc.w * dv);
-                    } else {  // GIN, lib:1519-1529
-                        const float s = 1.0f + p.gin_eps;
-                        acc.x += xs.x * s; acc.y += xs.y * s; acc.z += xs.z * s; acc.w += xs.w * s;
+#pragma unroll
+                    for (int j = 0; j < AGG_R; j++) {
+                        const int r = rb + j;
+                        float4 a = acc[j];
+                        if (r < rows) {
+                            const float4 xs = *reinterpret_cast<const float4 *>(
+                                RX + tc::canon_chunk_offset(r, c, TM));
+                            if (p.conv_type == GNNB_CONV_GCN) {  // lib:1249-1278, factorised
+                                const float dv = ms.dinv[r], ss = dv * dv;
+                                a.x = fmaf(xs.x, ss, a.x * dv); a.y = fmaf(xs.y, ss, a.y * dv);
+                                a.z = fmaf(xs.z, ss, a.z * dv); a.w = fmaf(xs.w, ss, a.w * dv);
+                            } else {  // GIN, lib:1519-1529
+                                const float s = 1.0f + p.gin_eps;
+                                a.x += xs.x * s; a.y += xs.y * s; a.z += xs.z * s; a.w += xs.w * s;
+                            }
+                        }
+                        const float4 h = make_float4(tc::tf32_hi(a.x), tc::tf32_hi(a.y),
+                                                     tc::tf32_hi(a.z), tc::tf32_hi(a.w));
+                        const uint32_t off = tc::canon_chunk_offset(r, c, TM);
+                        *reinterpret_cast<float4 *>(RHI + off) = h;
+                        *reinterpret_cast<float4 *>(RLO + off) =
+                            make_float4(a.x - h.x, a.y - h.y, a.z - h.z, a.w - h.w);
                     }
                 }
-                const float4 h = make_float4(tc::tf32_hi(acc.x), tc::tf32_hi(acc.y),
-                                             tc::tf32_hi(acc.z), tc::tf32_hi(acc.w));
-                const uint32_t off = tc::canon_chunk_offset(r, c, TM);
-                *reinterpret_cast<float4 *>(RHI + off) = h;
-                *reinterpret_cast<float4 *>(RLO + off) =
-                    make_float4(acc.x - h.x, acc.y - h.y, acc.z - h.z, acc.w - h.w);
             }
             if (do_skip) {  // park X: R_X is about to become the weight ring
                 for (int idx = tid; idx < TM * (kp / 4); idx += NTHREADS) {
-                    const int r = idx / (kp / 4), c = (idx % (kp / 4)) * 4;
+                    const int r = idx / (kp / 4), cc = (idx % (kp / 4)) * 4;
                     const float4 v = *reinterpret_cast<const float4 *>(
-                        RX + tc::canon_chunk_offset(r, c, TM));
-                    *reinterpret_cast<float4 *>(scratch + (size_t)r * MAX_DIM + c) = v;
+                        RX + tc::canon_chunk_offset(r, cc, TM));
+                    *reinterpret_cast<float4 *>(scratch + (size_t)r * MAX_DIM + cc) = v;
                 }
             }
             tc::fence_async_smem();
@@ -456,25 +571,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
             __syncthreads();
             GNNB_PHASE(2)
             const float *skip = do_skip ? scratch : nullptr;
+            if (tid == 0)
+                gemm_issue(ms, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, p.l0[l], false);
+            tc::mbar_wait(&ms.bar_done, done_cnt & 1);
+            done_cnt++;
+            tc::tc_fence_after();
             if (p.conv_type == GNNB_CONV_GCN) {
-                if (tid == 0)
-                    gemm_issue(ms, ps, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, p.l0[l]);
-                tc::mbar_wait(&ms.bar_done, done_cnt & 1);
-                done_cnt++;
-                tc::tc_fence_after();
                 epilogue(tmem_d, p.l0[l].N, p.l0[l].bias, p.gnn_act, skip, false, RX, nullptr);
             } else {
-                if (tid == 0)
-                    gemm_issue(ms, ps, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, p.l0[l]);
-                tc::mbar_wait(&ms.bar_done, done_cnt & 1);
-                done_cnt++;
-                tc::tc_fence_after();
+                // the ring is idle while the epilogue runs: start fetching the second GEMM's weights
+                if (tid == 0) gemm_prefetch(ms, RX, p.l1[l]);
                 epilogue(tmem_d, p.l0[l].N, p.l0[l].bias, GNNB_ACT_RELU, nullptr, true, RHI, RLO);
                 tc::fence_async_smem();
                 tc::tc_fence_before();
                 __syncthreads();
                 if (tid == 0)
-                    gemm_issue(ms, ps, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, p.l1[l]);
+                    gemm_issue(ms, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, p.l1[l], true);
                 tc::mbar_wait(&ms.bar_done, done_cnt & 1);
                 done_cnt++;
                 tc::tc_fence_after();
@@ -485,21 +597,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
             GNNB_PHASE(3)
         }
 
-        // ------------------------------------------------------------------ pooling + MLP head
-        const int emb = p.emb, head_in = emb * p.num_pools;
-        const int ldp = ((head_in + 3) & ~3) + 4;
-        float *ws = reinterpret_cast<float *>(RHI);
-        float *pooled = reinterpret_cast<float *>(RLO);
-        float *hb0 = pooled + HEAD_G * ldp;
-        float *hb1 = hb0 + HEAD_G * HLD;
-        for (int gc0 = 0; gc0 < ng; gc0 += HEAD_G) {
-            const int gcn = min(HEAD_G, ng - gc0);
-            for (int gi = warp; gi < gcn; gi += NTHREADS / 32) {
-                const int r0 = ms.grow[gc0 + gi], r1 = ms.grow[gc0 + gi + 1];
-                for (int c = lane; c < emb; c += 32) {
+        // -------------------------------------------------------------------- pooling -> pending
+        for (int gdone = 0; gdone < ng;) {
+            const int base_n = ms.pend_n;  // uniform: written below only after a barrier
+            const int cnt = min(HEAD_G - base_n, ng - gdone);
+            for (int gi = warp; gi < cnt; gi += NWARPS) {
+                const int r0 = ms.grow[gdone + gi], r1 = ms.grow[gdone + gi + 1];
+                float *dst = pending + (size_t)(base_n + gi) * PLD;
+                for (int cc = lane; cc < emb; cc += 32) {
                     float sum = 0.0f, mx = 0.0f;
                     for (int r = r0; r < r1; r++) {
-                        const float v = *reinterpret_cast<const float *>(RX + tc::canon_offset(r, c, TM));
+                        const float v = *reinterpret_cast<const float *>(RX + tc::canon_offset(r, cc, TM));
                         sum += v;
                         mx = (r == r0 || v > mx) ? v : mx;  // lib:748-759
                     }
@@ -508,25 +616,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
                         if (p.pools[q] == GNNB_POOL_ADD) v = sum;
                         else if (p.pools[q] == GNNB_POOL_MEAN) v = (r1 > r0) ? sum / (float)(r1 - r0) : 0.0f;
                         else v = mx;
-                        pooled[gi * ldp + q * emb + c] = v;
+                        dst[q * emb + cc] = v;
                     }
                 }
+                if (lane == 0) ms.pend_gid[base_n + gi] = cur_g0 + gdone + gi;
             }
             __syncthreads();
+            if (tid == 0) ms.pend_n = base_n + cnt;
+            gdone += cnt;
             GNNB_PHASE(4)
-            const float *hin = pooled;
-            int hld = ldp, hk = head_in;
-            for (int j = 0; j < p.mlp_num_linear; j++) {
-                const bool last = j == p.mlp_num_linear - 1;
-                float *hout = (j & 1) ? hb1 : hb0;
-                head_linear(ws, hin, hld, hk, p.head[j].Wt, p.head[j].ldw, p.head[j].bias,
-                            p.head[j].out, last ? p.out_act : p.mlp_act, hout, HLD,
-                            last ? p.out + (size_t)(g0 + gc0) * p.mlp_out : nullptr, p.mlp_out, gcn);
-                hin = hout; hld = HLD; hk = p.head[j].out;
+            if (base_n + cnt == HEAD_G) {
+                head_flush(p, ms, RHI, RLO, pending, HEAD_G);
+                if (tid == 0) ms.pend_n = 0;
+                GNNB_PHASE(5)
             }
-            GNNB_PHASE(5)
+            __syncthreads();
         }
     }
+    // graphs still waiting for the head
+    __syncthreads();
+    {
+        const int left = ms.pend_n;
+        if (left > 0) head_flush(p, ms, RHI, RLO, pending, left);
+    }
+    GNNB_PHASE(5)
 #undef GNNB_PHASE
     tc::tc_fence_before();
     __syncthreads();
@@ -537,11 +650,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
 
 struct TcPlan {
     TcParams params{};
-    DeviceBuf images, bounds, flag, scratch, timing;
+    DeviceBuf images, bounds, flag, scratch, pending, timing;
     size_t smem_bytes = 0;
 };
-
-static TcPlan *plan_of(gnnb_model *m) { return m->fused_tc; }
 
 int fused_tc_prepare(gnnb_model *m)
 {
@@ -596,6 +707,7 @@ int fused_tc_prepare(gnnb_model *m)
     }
     if (rc == GNNB_OK) rc = plan->flag.ensure(sizeof(int));
     if (rc == GNNB_OK) rc = plan->scratch.ensure((size_t)kNumSMs * TM * MAX_DIM * sizeof(float));
+    if (rc == GNNB_OK) rc = plan->pending.ensure((size_t)kNumSMs * HEAD_G * PLD * sizeof(float));
     if (rc == GNNB_OK && getenv("GNNB_FUSED_TIMING") != nullptr) {
         rc = plan->timing.ensure(16 * sizeof(unsigned long long));
         if (rc == GNNB_OK) cudaMemset(plan->timing.ptr, 0, 16 * sizeof(unsigned long long));
@@ -634,10 +746,10 @@ int fused_tc_prepare(gnnb_model *m)
 
 void fused_tc_release(gnnb_model *m)
 {
-    TcPlan *plan = plan_of(m);
+    TcPlan *plan = m->fused_tc;
     if (plan) {
         plan->images.release(); plan->bounds.release(); plan->flag.release();
-        plan->scratch.release(); plan->timing.release();
+        plan->scratch.release(); plan->pending.release(); plan->timing.release();
         delete plan;
         m->fused_tc = nullptr;
     }
@@ -653,7 +765,7 @@ int fused_tc_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_
                  const int64_t *edge_ptr, int n_graphs, int64_t total_nodes, int max_nodes,
                  float *out, cudaStream_t s, int *launches)
 {
-    TcPlan *plan = plan_of(m);
+    TcPlan *plan = m->fused_tc;
     GNNB_REQUIRE(plan != nullptr, "tensor-core fused kernel not available for this model");
     if (max_nodes < 1) max_nodes = 1;
     GNNB_REQUIRE(max_nodes <= MAX_NODES_PER_GRAPH, "graph too large for the fused kernel");
@@ -672,6 +784,7 @@ int fused_tc_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_
     p.out = out; p.tile_bounds = plan->bounds.as<int32_t>(); p.n_tiles = n_tiles;
     p.error_flag = plan->flag.as<int>();
     p.scratch = plan->scratch.as<float>();
+    p.pending = plan->pending.as<float>();
     p.timing = plan->timing.as<unsigned long long>();
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
     fused_tc_kernel<<<grid, NTHREADS, plan->smem_bytes, s>>>(p);
@@ -683,7 +796,7 @@ int fused_tc_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_
 int fused_tc_status(gnnb_model *m, int *status)
 {
     *status = 0;
-    TcPlan *plan = plan_of(m);
+    TcPlan *plan = m->fused_tc;
     if (plan == nullptr) return GNNB_OK;
     GNNB_CUDA(cudaMemcpy(status, plan->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost));
     if (plan->timing.ptr != nullptr) {
