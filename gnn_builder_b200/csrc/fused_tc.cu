@@ -206,8 +206,10 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t tmem_d, uint32_t a
 //   split == true : write hi / lo parts into dst_hi / dst_lo (next GEMM's A operand)
 //   split == false: write the values into dst_hi (the X region), dst_lo unused
 // Columns [N, round_up(N, 32)) of the last K atom are zero filled.
+// `skip` is written by this CTA earlier in the same kernel: read it with ld.global.cg (L2), never
+// through the non-coherent read-only path.
 __device__ __forceinline__ void epilogue(uint32_t tmem_d, int N, const float *__restrict__ bias,
-                                         int act, const float *__restrict__ skip, bool split,
+                                         int act, const float *skip, bool split,
                                          unsigned char *dst_hi, unsigned char *dst_lo)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -216,17 +218,23 @@ __device__ __forceinline__ void epilogue(uint32_t tmem_d, int N, const float *__
     for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += 64) {
         float v[32];
         tc::tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
+        // bias (warp-uniform addresses) and the parked skip rows: issue all loads of this block
+        // up front so that their latencies overlap
+        float4 bsv[8], skv[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++) {
+            const bool in_range = c0 + j4 * 4 < N;  // N % 4 == 0
+            bsv[j4] = in_range ? __ldg(reinterpret_cast<const float4 *>(bias + c0 + j4 * 4))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            skv[j4] = (in_range && skip != nullptr)
+                          ? __ldcg(reinterpret_cast<const float4 *>(skip + (size_t)row * MAX_DIM + c0 + j4 * 4))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int j4 = 0; j4 < 8; j4++) {
             float o[4];
-            float4 sk = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
-            const bool in_range = c0 + j4 * 4 < N;  // N % 4 == 0
-            if (in_range) {
-                bs = __ldg(reinterpret_cast<const float4 *>(bias + c0 + j4 * 4));
-                if (skip != nullptr)
-                    sk = __ldg(reinterpret_cast<const float4 *>(skip + (size_t)row * MAX_DIM + c0 + j4 * 4));
-            }
+            const float4 sk = skv[j4], bs = bsv[j4];
+            const bool in_range = c0 + j4 * 4 < N;
             const float sks[4] = {sk.x, sk.y, sk.z, sk.w};
             const float bss[4] = {bs.x, bs.y, bs.z, bs.w};
 #pragma unroll
@@ -327,8 +335,12 @@ __device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, unsigned
     float *ws = reinterpret_cast<float *>(RHI);
     float *hb0 = reinterpret_cast<float *>(RLO);
     float *hb1 = hb0 + HEAD_G * HLD;
-    const float *hin = pending;
+    float *pin = hb1 + HEAD_G * HLD;  // [HEAD_G][PLD] copy of the pending pooled vectors
     int hld = PLD, hk = p.emb * p.num_pools;
+    for (int idx = threadIdx.x; idx < n_rows * (PLD / 4); idx += NTHREADS)
+        reinterpret_cast<float4 *>(pin)[idx] = __ldcg(reinterpret_cast<const float4 *>(pending) + idx);
+    __syncthreads();
+    const float *hin = pin;
     for (int j = 0; j < p.mlp_num_linear; j++) {
         const bool last = j == p.mlp_num_linear - 1;
         float *hout = (j & 1) ? hb1 : hb0;
@@ -516,20 +528,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
                         acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                         kmax = max(kmax, d[j]);
                     }
+                    // branch-free body: all AGG_R gather chains (index -> row -> add) issue back to
+                    // back; rows that have run out of neighbors read slot 0 and select 0
+                    const bool gcn = p.conv_type == GNNB_CONV_GCN;
                     for (int k = 0; k < kmax; k++) {
+                        int u[AGG_R];
+                        float4 v[AGG_R];
+                        float s[AGG_R];
+#pragma unroll
+                        for (int j = 0; j < AGG_R; j++) u[j] = ms.nbr[(k < d[j]) ? o[j] + k : 0];
 #pragma unroll
                         for (int j = 0; j < AGG_R; j++) {
-                            if (k < d[j]) {
-                                const int u = ms.nbr[o[j] + k];
-                                const float4 v = *reinterpret_cast<const float4 *>(
-                                    RX + tc::canon_chunk_offset(u, c, TM));
-                                if (p.conv_type == GNNB_CONV_GCN) {
-                                    const float s = ms.dinv[u];
-                                    acc[j].x = fmaf(v.x, s, acc[j].x); acc[j].y = fmaf(v.y, s, acc[j].y);
-                                    acc[j].z = fmaf(v.z, s, acc[j].z); acc[j].w = fmaf(v.w, s, acc[j].w);
-                                } else {
-                                    acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
-                                }
+                            v[j] = *reinterpret_cast<const float4 *>(
+                                RX + tc::canon_chunk_offset(u[j], c, TM));
+                            s[j] = gcn ? ms.dinv[u[j]] : 1.0f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < AGG_R; j++) {
+                            const bool on = k < d[j];
+                            const float4 t = make_float4(on ? v[j].x : 0.0f, on ? v[j].y : 0.0f,
+                                                         on ? v[j].z : 0.0f, on ? v[j].w : 0.0f);
+                            if (gcn) {
+                                acc[j].x = fmaf(t.x, s[j], acc[j].x); acc[j].y = fmaf(t.y, s[j], acc[j].y);
+                                acc[j].z = fmaf(t.z, s[j], acc[j].z); acc[j].w = fmaf(t.w, s[j], acc[j].w);
+                            } else {
+                                acc[j].x += t.x; acc[j].y += t.y; acc[j].z += t.z; acc[j].w += t.w;
                             }
                         }
                     }
@@ -558,6 +581,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
                     }
                 }
             }
+            GNNB_PHASE(2)   // this warp's own aggregation time (no barrier yet)
             if (do_skip) {  // park X: R_X is about to become the weight ring
                 for (int idx = tid; idx < TM * (kp / 4); idx += NTHREADS) {
                     const int r = idx / (kp / 4), cc = (idx % (kp / 4)) * 4;
@@ -569,13 +593,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
             tc::fence_async_smem();
             tc::tc_fence_before();
             __syncthreads();
-            GNNB_PHASE(2)
+            GNNB_PHASE(6)   // skip spill + proxy fence + barrier (waiting for the slowest warp)
             const float *skip = do_skip ? scratch : nullptr;
-            if (tid == 0)
+            if (tid == 0) {
                 gemm_issue(ms, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, p.l0[l], false);
-            tc::mbar_wait(&ms.bar_done, done_cnt & 1);
+                tc::mbar_wait(&ms.bar_done, done_cnt & 1);  // one poller; the rest park on bar.sync
+            }
             done_cnt++;
+            __syncthreads();
             tc::tc_fence_after();
+            GNNB_PHASE(7)   // weight copies + MMAs until the accumulator is ready
             if (p.conv_type == GNNB_CONV_GCN) {
                 epilogue(tmem_d, p.l0[l].N, p.l0[l].bias, p.gnn_act, skip, false, RX, nullptr);
             } else {
@@ -585,11 +612,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
                 tc::fence_async_smem();
                 tc::tc_fence_before();
                 __syncthreads();
-                if (tid == 0)
+                GNNB_PHASE(3)
+                if (tid == 0) {
                     gemm_issue(ms, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, p.l1[l], true);
-                tc::mbar_wait(&ms.bar_done, done_cnt & 1);
+                    tc::mbar_wait(&ms.bar_done, done_cnt & 1);
+                }
                 done_cnt++;
+                __syncthreads();
                 tc::tc_fence_after();
+                GNNB_PHASE(7)
                 epilogue(tmem_d, p.l1[l].N, p.l1[l].bias, p.gnn_act, skip, false, RX, nullptr);
             }
             tc::tc_fence_before();
@@ -604,19 +635,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
             for (int gi = warp; gi < cnt; gi += NWARPS) {
                 const int r0 = ms.grow[gdone + gi], r1 = ms.grow[gdone + gi + 1];
                 float *dst = pending + (size_t)(base_n + gi) * PLD;
-                for (int cc = lane; cc < emb; cc += 32) {
-                    float sum = 0.0f, mx = 0.0f;
+                for (int cc = lane * 4; cc < emb; cc += 128) {   // emb % 16 == 0
+                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), mx = sum;
                     for (int r = r0; r < r1; r++) {
-                        const float v = *reinterpret_cast<const float *>(RX + tc::canon_offset(r, cc, TM));
-                        sum += v;
-                        mx = (r == r0 || v > mx) ? v : mx;  // lib:748-759
+                        const float4 v = *reinterpret_cast<const float4 *>(
+                            RX + tc::canon_chunk_offset(r, cc, TM));
+                        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                        const bool first = r == r0;                       // lib:748-759
+                        mx.x = (first || v.x > mx.x) ? v.x : mx.x; mx.y = (first || v.y > mx.y) ? v.y : mx.y;
+                        mx.z = (first || v.z > mx.z) ? v.z : mx.z; mx.w = (first || v.w > mx.w) ? v.w : mx.w;
                     }
+                    const float inv_on = (r1 > r0) ? 1.0f : 0.0f, cntf = (float)max(r1 - r0, 1);
                     for (int q = 0; q < p.num_pools; q++) {
-                        float v;
+                        float4 v;
                         if (p.pools[q] == GNNB_POOL_ADD) v = sum;
-                        else if (p.pools[q] == GNNB_POOL_MEAN) v = (r1 > r0) ? sum / (float)(r1 - r0) : 0.0f;
+                        else if (p.pools[q] == GNNB_POOL_MEAN)
+                            v = make_float4(inv_on * (sum.x / cntf), inv_on * (sum.y / cntf),
+                                            inv_on * (sum.z / cntf), inv_on * (sum.w / cntf));
                         else v = mx;
-                        dst[q * emb + cc] = v;
+                        *reinterpret_cast<float4 *>(dst + q * emb + cc) = v;
                     }
                 }
                 if (lane == 0) ms.pend_gid[base_n + gi] = cur_g0 + gdone + gi;
@@ -803,11 +840,12 @@ int fused_tc_status(gnnb_model *m, int *status)
         unsigned long long t[16];
         GNNB_CUDA(cudaMemcpy(t, plan->timing.ptr, sizeof(t), cudaMemcpyDeviceToHost));
         GNNB_CUDA(cudaMemset(plan->timing.ptr, 0, sizeof(t)));
-        const char *names[6] = {"stage", "tables", "aggregate", "gemm", "pool", "head"};
+        const char *names[8] = {"stage", "tables", "aggregate", "epilogue", "pool", "head",
+                                "agg-barrier", "mma"};
         unsigned long long tot = 0;
-        for (int i = 0; i < 6; i++) tot += t[i];
+        for (int i = 0; i < 8; i++) tot += t[i];
         fprintf(stderr, "[gnnb fused-tc phases]");
-        for (int i = 0; i < 6; i++)
+        for (int i = 0; i < 8; i++)
             fprintf(stderr, " %s %.1f%%", names[i], tot ? 100.0 * (double)t[i] / (double)tot : 0.0);
         fprintf(stderr, " (total %.3g cycles over all CTAs)\n", (double)tot);
     }
