@@ -160,19 +160,26 @@ __global__ void __launch_bounds__(256) agg_rows_kernel(const AggArgs a)
     }
 }
 
-// One CTA (8 warps) per heavy row: the neighbor list is split into 8 contiguous ranges.
+// Heavy rows (in-degree above the threshold): the neighbor list of row h is cut into
+// `heavy_slices` slices, one CTA per (row, slice); its 8 warps split the slice, reduce their
+// partial sums in shared memory in warp order and write partial[h][slice][F].  A second kernel
+// adds the slices in order and applies the self term / normalisation, so the result does not
+// depend on scheduling.  (A first version gave each heavy row to ONE CTA: a 100k-neighbor hub
+// then ran for ~5 ms on 8 warps while 147 SMs idled.)
 template <int VEC, int MODE>
 __global__ void __launch_bounds__(256) agg_heavy_kernel(const AggArgs a)
 {
     extern __shared__ float partial[];  // [8][F]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int S = a.heavy_slices, sl = blockIdx.y;
     for (int h = blockIdx.x; h < a.n_heavy; h += gridDim.x) {
         const int v = __ldg(a.heavy_rows + h);
         const int deg_v = __ldg(a.in_deg + v);
         const int off = __ldg(a.offsets + v);
         const float dinv_v = (MODE == AGG_GCN) ? __ldg(a.dinv + v + a.row_base) : 0.0f;
-        const int per = (deg_v + 7) / 8;
-        const int k0 = min(deg_v, warp * per), k1 = min(deg_v, (warp + 1) * per);
+        const int s0 = (int)((int64_t)deg_v * sl / S), s1 = (int)((int64_t)deg_v * (sl + 1) / S);
+        const int per = (s1 - s0 + 7) / 8;
+        const int k0 = min(s1, s0 + warp * per), k1 = min(s1, s0 + (warp + 1) * per);
         for (int c = lane * VEC; c < a.F; c += 32 * VEC) {
             Vec<VEC> acc;
 #pragma unroll
@@ -183,19 +190,43 @@ __global__ void __launch_bounds__(256) agg_heavy_kernel(const AggArgs a)
         }
         __syncthreads();
         if (warp == 0) {
+            float *dst = a.heavy_partial + ((size_t)h * S + sl) * a.F;
             for (int c = lane * VEC; c < a.F; c += 32 * VEC) {
                 Vec<VEC> acc;
 #pragma unroll
                 for (int i = 0; i < VEC; i++) {
-                    float s = 0.0f;
+                    float t = 0.0f;
 #pragma unroll
-                    for (int w = 0; w < 8; w++) s += partial[w * a.F + c + i];
-                    acc.v[i] = s;
+                    for (int w = 0; w < 8; w++) t += partial[w * a.F + c + i];
+                    acc.v[i] = t;
                 }
-                finish_row<VEC, MODE, false>(a, v, deg_v, dinv_v, c, acc);
+                acc.store(dst + c);
             }
         }
         __syncthreads();
+    }
+}
+
+template <int VEC, int MODE>
+__global__ void __launch_bounds__(128) agg_heavy_combine_kernel(const AggArgs a)
+{
+    const int S = a.heavy_slices;
+    for (int h = blockIdx.x; h < a.n_heavy; h += gridDim.x) {
+        const int v = __ldg(a.heavy_rows + h);
+        const int deg_v = __ldg(a.in_deg + v);
+        const float dinv_v = (MODE == AGG_GCN) ? __ldg(a.dinv + v + a.row_base) : 0.0f;
+        for (int c = threadIdx.x * VEC; c < a.F; c += blockDim.x * VEC) {
+            Vec<VEC> acc;
+#pragma unroll
+            for (int i = 0; i < VEC; i++) acc.v[i] = 0.0f;
+            for (int sl = 0; sl < S; sl++) {
+                Vec<VEC> t;
+                t.load(a.heavy_partial + ((size_t)h * S + sl) * a.F + c);
+#pragma unroll
+                for (int i = 0; i < VEC; i++) acc.v[i] += t.v[i];
+            }
+            finish_row<VEC, MODE, false>(a, v, deg_v, dinv_v, c, acc);
+        }
     }
 }
 
@@ -226,16 +257,23 @@ int launch_lpr(const AggArgs &a, int lpr, int grid, cudaStream_t s)
     }
 }
 
+template <int VEC, int MODE>
+void launch_heavy_mode(const AggArgs &a, cudaStream_t s)
+{
+    const int gx = a.n_heavy < kNumSMs * 8 ? a.n_heavy : kNumSMs * 8;
+    const size_t smem = sizeof(float) * 8 * (size_t)a.F;
+    agg_heavy_kernel<VEC, MODE><<<dim3(gx, a.heavy_slices), 256, smem, s>>>(a);
+    agg_heavy_combine_kernel<VEC, MODE><<<gx, 128, 0, s>>>(a);
+}
+
 template <int VEC>
 int launch_heavy(const AggArgs &a, cudaStream_t s)
 {
-    const int grid = a.n_heavy < kNumSMs * 4 ? a.n_heavy : kNumSMs * 4;
-    const size_t smem = sizeof(float) * 8 * (size_t)a.F;
     switch (a.mode) {
-    case AGG_GCN: agg_heavy_kernel<VEC, AGG_GCN><<<grid, 256, smem, s>>>(a); break;
-    case AGG_GIN: agg_heavy_kernel<VEC, AGG_GIN><<<grid, 256, smem, s>>>(a); break;
-    case AGG_MEAN: agg_heavy_kernel<VEC, AGG_MEAN><<<grid, 256, smem, s>>>(a); break;
-    case AGG_SUM: agg_heavy_kernel<VEC, AGG_SUM><<<grid, 256, smem, s>>>(a); break;
+    case AGG_GCN: launch_heavy_mode<VEC, AGG_GCN>(a, s); break;
+    case AGG_GIN: launch_heavy_mode<VEC, AGG_GIN>(a, s); break;
+    case AGG_MEAN: launch_heavy_mode<VEC, AGG_MEAN>(a, s); break;
+    case AGG_SUM: launch_heavy_mode<VEC, AGG_SUM>(a, s); break;
     default: set_error("heavy-row path: unsupported mode"); return GNNB_ERR_INVALID;
     }
     return GNNB_OK;
@@ -271,10 +309,11 @@ int launch_agg(const AggArgs &a_in, bool strict, cudaStream_t s, int *launches)
     GNNB_CUDA(cudaGetLastError());
     if (launches) ++*launches;
     if (a.n_heavy > 0) {
-        GNNB_REQUIRE(a.heavy_rows != nullptr, "heavy row list missing");
+        GNNB_REQUIRE(a.heavy_rows != nullptr && a.heavy_partial != nullptr && a.heavy_slices > 0,
+                     "heavy row list / partial buffer missing");
         GNNB_TRY(vec == 4 ? launch_heavy<4>(a, s) : launch_heavy<1>(a, s));
         GNNB_CUDA(cudaGetLastError());
-        if (launches) ++*launches;
+        if (launches) *launches += 2;
     }
     return GNNB_OK;
 }

@@ -7,7 +7,7 @@ namespace gnnb {
 
 // ---------------------------------------------------------------- graph tables (tables.cu)
 struct TableWorkspace {
-    DeviceBuf keys_in, keys_out, vals_in, vals_out, cub_tmp, heavy_rows, counters;
+    DeviceBuf keys_in, keys_out, vals_in, vals_out, cub_tmp, heavy_rows, heavy_partial, counters;
 };
 
 // edge_list [E][2] local ids; node_ptr/edge_ptr (device int64, G+1 entries) translate them to
@@ -34,6 +34,9 @@ int build_partition_tables(const int32_t *edge_list, int row_begin, int n_local,
 // rows with in-degree > threshold, compacted into ws.heavy_rows; count returned through host ptr
 int find_heavy_rows(const int32_t *in_deg, int n, int threshold, TableWorkspace &ws,
                     int *n_heavy_host, cudaStream_t s, int *launches);
+// degree bucketing parameters + partial-sum scratch for the heavy-row kernels
+constexpr int kHeavyThreshold = 256;
+int heavy_setup(TableWorkspace &ws, int n_heavy, int F, int *slices);
 // dinv[i] = 1 / sqrt(1 + in_deg[i])
 int compute_dinv(const int32_t *in_deg, float *dinv, int n, cudaStream_t s, int *launches);
 
@@ -54,6 +57,8 @@ struct AggArgs {
     const int32_t *heavy_rows;  // optional list of rows handled by the CTA-per-row kernel
     int n_heavy;
     int heavy_threshold;
+    float *heavy_partial;  // [n_heavy][heavy_slices][F] slice sums of the heavy rows
+    int heavy_slices;
     int row_base;          // row-partitioned graphs: global id of local row 0 (x / dinv are global,
                            // offsets / in_deg / out are local); 0 otherwise
 };

@@ -73,7 +73,7 @@ struct TempWs {
     ~TempWs()
     {
         DeviceBuf *b[] = {&ws.keys_in, &ws.keys_out, &ws.vals_in, &ws.vals_out, &ws.cub_tmp,
-                          &ws.heavy_rows, &ws.counters};
+                          &ws.heavy_rows, &ws.heavy_partial, &ws.counters};
         for (DeviceBuf *x : b) x->release();
     }
 };
@@ -415,7 +415,7 @@ struct PartitionCache {
     TableWorkspace ws;
     DeviceBuf wt, agg;
     const int32_t *heavy_key = nullptr;
-    int heavy_n = 0, n_heavy = 0;
+    int heavy_n = 0, n_heavy = 0, slices = 0;
 };
 thread_local PartitionCache g_part;
 }  // namespace
@@ -461,8 +461,9 @@ extern "C" int gnnb_gcn_conv_partition(int n_local, int row_begin, int n_total, 
     GNNB_TRY(g_part.agg.ensure(sizeof(float) * (size_t)n_local * lda));
     GNNB_TRY(launch_transpose_weight(weight, g_part.wt.as<float>(), emb_out, emb_in, ldw, s, nullptr));
     if (g_part.heavy_key != in_degree_local || g_part.heavy_n != n_local) {
-        GNNB_TRY(find_heavy_rows(in_degree_local, n_local, 1024, g_part.ws, &g_part.n_heavy, s,
-                                 nullptr));
+        GNNB_TRY(find_heavy_rows(in_degree_local, n_local, kHeavyThreshold, g_part.ws,
+                                 &g_part.n_heavy, s, nullptr));
+        GNNB_TRY(heavy_setup(g_part.ws, g_part.n_heavy, emb_in, &g_part.slices));
         g_part.heavy_key = in_degree_local;
         g_part.heavy_n = n_local;
     }
@@ -471,7 +472,8 @@ extern "C" int gnnb_gcn_conv_partition(int n_local, int row_begin, int n_total, 
     a.ldo = lda; a.offsets = offsets_local; a.nbr = neighbor_table_global; a.in_deg = in_degree_local;
     a.dinv = dinv_full; a.n = n_local; a.row_base = row_begin;
     a.heavy_rows = g_part.ws.heavy_rows.as<int32_t>(); a.n_heavy = g_part.n_heavy;
-    a.heavy_threshold = 1024;
+    a.heavy_threshold = kHeavyThreshold;
+    a.heavy_partial = g_part.ws.heavy_partial.as<float>(); a.heavy_slices = g_part.slices;
     GNNB_TRY(launch_agg(a, false, s, nullptr));
     GemmArgs g = simple_gemm(a.out, lda, emb_in, g_part.wt.as<float>(), ldw, bias, y_local, emb_out,
                              n_local, emb_out, act);

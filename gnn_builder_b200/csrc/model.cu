@@ -221,6 +221,7 @@ extern "C" int gnnb_model_destroy(gnnb_model_t *m)
                          &m->feat[1], &m->agg, &m->hid, &m->wide, &m->pooled, &m->hbuf[0],
                          &m->hbuf[1], &m->pool_tmp, &m->ptr_tmp, &m->tws.keys_in, &m->tws.keys_out,
                          &m->tws.vals_in, &m->tws.vals_out, &m->tws.cub_tmp, &m->tws.heavy_rows,
+                         &m->tws.heavy_partial,
                          &m->tws.counters};
     for (DeviceBuf *b : bufs) b->release();
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -443,11 +444,13 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
         dinv = m->dinv.as<float>();
     }
     // degree bucketing only matters for big graphs (molecular graphs have in-degree <= ~8)
-    int n_heavy = 0;
-    const int heavy_threshold = 1024;
+    int n_heavy = 0, heavy_slices = 0;
+    const int heavy_threshold = kHeavyThreshold;
     if (!strict && d.num_layers > 0 && d.conv_type != GNNB_CONV_PNA && n_graphs > 0 &&
-        T64 / n_graphs > 50000)
+        T64 / n_graphs > 50000) {
         GNNB_TRY(find_heavy_rows(in_deg, T, heavy_threshold, m->tws, &n_heavy, s, launches));
+        GNNB_TRY(heavy_setup(m->tws, n_heavy, maxf, &heavy_slices));
+    }
 
     GNNB_TRY(m->feat[0].ensure(sizeof(float) * (size_t)Tn * ldf));
     GNNB_TRY(m->feat[1].ensure(sizeof(float) * (size_t)Tn * ldf));
@@ -471,6 +474,7 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
         a.offsets = offsets; a.nbr = nbr; a.in_deg = in_deg; a.dinv = dinv; a.n = T;
         a.eps = d.gin_eps; a.heavy_rows = m->tws.heavy_rows.as<int32_t>(); a.n_heavy = n_heavy;
         a.heavy_threshold = heavy_threshold;
+        a.heavy_partial = m->tws.heavy_partial.as<float>(); a.heavy_slices = heavy_slices;
         switch (d.conv_type) {
         case GNNB_CONV_GCN: {
             a.mode = AGG_GCN;

@@ -275,6 +275,14 @@ int find_heavy_rows(const int32_t *in_deg, int n, int threshold, TableWorkspace 
     return GNNB_OK;
 }
 
+int heavy_setup(TableWorkspace &ws, int n_heavy, int F, int *slices)
+{
+    *slices = n_heavy <= 4096 ? 32 : (n_heavy <= 65536 ? 8 : 2);
+    if (n_heavy > 0)
+        GNNB_TRY(ws.heavy_partial.ensure(sizeof(float) * (size_t)n_heavy * *slices * (size_t)F));
+    return GNNB_OK;
+}
+
 int compute_dinv(const int32_t *in_deg, float *dinv, int n, cudaStream_t s, int *launches)
 {
     if (n <= 0) return GNNB_OK;
