@@ -36,7 +36,8 @@
 
 namespace gnnb {
 
-void build_weight_image(const float *W, int N, int K, int ld, int col0, std::vector<float> &img);
+void build_weight_image(const float *W, int N, int n_valid, int K, int ld, int col0,
+                        std::vector<float> &img);
 
 namespace {
 
@@ -46,11 +47,9 @@ constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int MAX_LAYERS = 8;
 constexpr int MAX_HEAD = 6;
-constexpr int HEAD_G = 16;       // graphs per head call
-constexpr int HBK = 32;          // k rows per staged head-weight tile
-constexpr int HSTAGES = 4;       // head weight ring depth (4 x 16 KB = R_HI)
+constexpr int HEAD_G = 128;      // pooled graphs per head call (one 128-row MMA tile)
+constexpr int MAX_HCHUNK = 4;    // 128-wide K chunks of the first head layer (head_in <= 512)
 constexpr int MAX_DIM = 128;
-constexpr int HLD = 132;         // row stride of the head ping-pong buffers
 constexpr int PLD = 520;         // row stride of the pending pooled vectors (>= 512 + 4)
 constexpr int REGION = TM * MAX_DIM * 4;  // 64 KB
 constexpr int MAX_SLOTS = 8;
@@ -62,11 +61,6 @@ struct TLinear {
     const float *bias;
     int K, N, KA;
 };
-struct HLinear {
-    const float *Wt;
-    const float *bias;
-    int in, out, ldw;
-};
 
 struct TcParams {
     int conv_type, num_layers, in_dim, skip, gnn_act, num_pools, pools[4];
@@ -74,7 +68,9 @@ struct TcParams {
     float gin_eps;
     int fi[MAX_LAYERS], fo[MAX_LAYERS];
     TLinear l0[MAX_LAYERS], l1[MAX_LAYERS];
-    HLinear head[MAX_HEAD];
+    TLinear hl[MAX_HEAD][MAX_HCHUNK];   // MLP head linears, K cut into 128-wide chunks
+    int hchunks[MAX_HEAD];
+    int head_n[MAX_HEAD];               // true output widths (N of the images is padded to 16)
     const float *x;
     const int32_t *coo;
     const int64_t *node_ptr, *edge_ptr;
@@ -160,7 +156,8 @@ __device__ __forceinline__ void gemm_prefetch(Misc &ms, unsigned char *ring, con
     }
 }
 __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo,
-                                           unsigned char *ring, const TLinear &L, bool prefetched)
+                                           unsigned char *ring, const TLinear &L, bool prefetched,
+                                           bool accumulate = false)
 {
     const uint32_t slot_bytes = (uint32_t)L.N * tc::ROW_BYTES;
     const uint32_t idesc = tc::make_idesc_tf32(TM, L.N);
@@ -181,7 +178,7 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t tmem_d, uint32_t a
             const uint32_t ko = (uint32_t)k8 * tc::MMA_K * 4;
             if (part == 0) {
                 tc::mma_tf32(tmem_d, tc::make_desc(ah + ko), tc::make_desc(b + ko), idesc,
-                             (u == 0 && k8 == 0) ? 0u : 1u);
+                             (u == 0 && k8 == 0 && !accumulate) ? 0u : 1u);
                 tc::mma_tf32(tmem_d, tc::make_desc(al + ko), tc::make_desc(b + ko), idesc, 1u);
             } else {
                 tc::mma_tf32(tmem_d, tc::make_desc(ah + ko), tc::make_desc(b + ko), idesc, 1u);
@@ -202,19 +199,25 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t tmem_d, uint32_t a
     tc::mma_commit(&ms.bar_done);
 }
 
-// All threads: accumulator -> (+bias, +skip, activation) -> shared memory.
-//   split == true : write hi / lo parts into dst_hi / dst_lo (next GEMM's A operand)
-//   split == false: write the values into dst_hi (the X region), dst_lo unused
-// Columns [N, round_up(N, 32)) of the last K atom are zero filled.
+// All threads: accumulator -> (+bias, +skip, activation) -> destination.
+//   EPI_X      : write the values into dst_hi (the X region, canonical layout)
+//   EPI_SPLIT  : write hi / lo parts into dst_hi / dst_lo (the next GEMM's A operand)
+//   EPI_GLOBAL : write columns [0, n_true) of rows [0, n_rows) to gout[gids[row]][col] (model output)
+// Columns [N, round_up(N, 32)) of the last K atom are zero filled (shared-memory modes).
 // `skip` is written by this CTA earlier in the same kernel: read it with ld.global.cg (L2), never
 // through the non-coherent read-only path.
+enum { EPI_X = 0, EPI_SPLIT = 1, EPI_GLOBAL = 2 };
 __device__ __forceinline__ void epilogue(uint32_t tmem_d, int N, const float *__restrict__ bias,
-                                         int act, const float *skip, bool split,
-                                         unsigned char *dst_hi, unsigned char *dst_lo)
+                                         int act, const float *skip, int mode,
+                                         unsigned char *dst_hi, unsigned char *dst_lo,
+                                         float *gout = nullptr, const int *gids = nullptr,
+                                         int n_rows = 0, int ldg = 0, int n_true = 0)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = 32 * (warp & 3) + lane;
     const int npad = (N + 31) & ~31;
+    float *grow = nullptr;
+    if (mode == EPI_GLOBAL && row < n_rows) grow = gout + (size_t)gids[row] * ldg;
     for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += 64) {
         float v[32];
         tc::tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
@@ -240,8 +243,16 @@ __device__ __forceinline__ void epilogue(uint32_t tmem_d, int N, const float *__
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 o[j] = in_range ? act_apply_compact(act, v[j4 * 4 + j] + bss[j] + sks[j]) : 0.0f;
+            if (mode == EPI_GLOBAL) {
+                if (grow != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (c0 + j4 * 4 + j < n_true) grow[c0 + j4 * 4 + j] = o[j];
+                }
+                continue;
+            }
             const uint32_t off = tc::canon_chunk_offset(row, c0 + j4 * 4, TM);
-            if (split) {
+            if (mode == EPI_SPLIT) {
                 float h[4], l[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) { h[j] = tc::tf32_hi(o[j]); l[j] = o[j] - h[j]; }
@@ -254,100 +265,55 @@ __device__ __forceinline__ void epilogue(uint32_t tmem_d, int N, const float *__
     }
 }
 
-// one MLP-head linear for up to 16 graphs (fp32 FMA).  Thread = (graph tid/16, columns cg*4 and
-// 64+cg*4); the weights stream through a 4-stage cp.async ring (`ws`, 4 x [32][128] floats) so
-// three K tiles are in flight while one is consumed.  A may live in global or shared memory.
-__device__ __noinline__ void head_linear(float *ws, const float *A, int lda, int K, const float *Wt,
-                                         int ldw, const float *bias, int N, int act,
-                                         float *dst_smem, int ldo, float *dst_global, int ldg,
-                                         const int *gids, int n_rows)
+// MLP head (cpp:454-530) for up to 128 pending graphs on the tensor cores: the pooled vectors
+// [128][head_in] are the A operand, read from the per-CTA pending buffer in 128-wide K chunks that
+// accumulate into the same TMEM tile; later head layers take their A operand from the previous
+// epilogue exactly like GIN's hidden layer.  All threads call this.
+__device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, uint32_t tmem_d,
+                                           unsigned char *RX, unsigned char *RHI, unsigned char *RLO,
+                                           const float *pending, int n_rows, uint32_t &done_cnt)
 {
-    constexpr int BN = MAX_DIM;
     const int tid = threadIdx.x;
-    const int gi = tid >> 4, cg = tid & 15;
-    float acc[2][4];
-#pragma unroll
-    for (int q = 0; q < 2; q++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int col = q * 64 + cg * 4 + j;
-            acc[q][j] = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.0f;
-        }
-    const int nt = (K + HBK - 1) / HBK;
-    auto issue = [&](int t) {
-        constexpr int GPR = BN / 4;
-        float *w = ws + (t % HSTAGES) * HBK * BN;
-        const int k0 = t * HBK;
-        for (int g = tid; g < HBK * GPR; g += NTHREADS) {
-            const int kk = g / GPR, c4 = (g % GPR) * 4;
-            const bool valid = (k0 + kk < K) && (c4 < ldw);
-            const float *src = valid ? Wt + (size_t)(k0 + kk) * ldw + c4 : Wt;
-            cp_async16(w + kk * BN + c4, src, valid);
-        }
-        cp_async_commit();
-    };
-    const float *a = A + (size_t)(gi < n_rows ? gi : 0) * lda;
-    for (int t = 0; t < HSTAGES - 1 && t < nt; t++) issue(t);
-#pragma unroll 1
-    for (int t = 0; t < nt; t++) {
-        if (t + HSTAGES - 1 < nt) issue(t + HSTAGES - 1);
-        const int newer = min(HSTAGES - 1, nt - 1 - t);  // groups allowed to stay in flight
-        if (newer >= 3) cp_async_wait<3>();
-        else if (newer == 2) cp_async_wait<2>();
-        else if (newer == 1) cp_async_wait<1>();
-        else cp_async_wait<0>();
-        __syncthreads();
-        const float *w = ws + (t % HSTAGES) * HBK * BN;
-        const int k0 = t * HBK;
-        const int kn = min(HBK, K - k0);
-#pragma unroll 4
-        for (int kk = 0; kk < kn; kk++) {
-            const float av = a[k0 + kk];
-            const float4 w0 = *reinterpret_cast<const float4 *>(w + kk * BN + cg * 4);
-            const float4 w1 = *reinterpret_cast<const float4 *>(w + kk * BN + 64 + cg * 4);
-            acc[0][0] = fmaf(av, w0.x, acc[0][0]); acc[0][1] = fmaf(av, w0.y, acc[0][1]);
-            acc[0][2] = fmaf(av, w0.z, acc[0][2]); acc[0][3] = fmaf(av, w0.w, acc[0][3]);
-            acc[1][0] = fmaf(av, w1.x, acc[1][0]); acc[1][1] = fmaf(av, w1.y, acc[1][1]);
-            acc[1][2] = fmaf(av, w1.z, acc[1][2]); acc[1][3] = fmaf(av, w1.w, acc[1][3]);
-        }
-        __syncthreads();
-    }
-    if (gi < n_rows) {
-        float *drow = dst_global != nullptr ? dst_global + (size_t)gids[gi] * ldg : nullptr;
-#pragma unroll
-        for (int q = 0; q < 2; q++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int col = q * 64 + cg * 4 + j;
-                if (col >= N) continue;
-                const float v = act_apply_compact(act, acc[q][j]);
-                if (drow != nullptr) drow[col] = v;
-                else dst_smem[gi * ldo + col] = v;
-            }
-    }
-    __syncthreads();
-}
-
-// run the MLP head over the pending pooled vectors (all threads)
-__device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, unsigned char *RHI,
-                                           unsigned char *RLO, const float *pending, int n_rows)
-{
-    float *ws = reinterpret_cast<float *>(RHI);
-    float *hb0 = reinterpret_cast<float *>(RLO);
-    float *hb1 = hb0 + HEAD_G * HLD;
-    float *pin = hb1 + HEAD_G * HLD;  // [HEAD_G][PLD] copy of the pending pooled vectors
-    int hld = PLD, hk = p.emb * p.num_pools;
-    for (int idx = threadIdx.x; idx < n_rows * (PLD / 4); idx += NTHREADS)
-        reinterpret_cast<float4 *>(pin)[idx] = __ldcg(reinterpret_cast<const float4 *>(pending) + idx);
-    __syncthreads();
-    const float *hin = pin;
+    const int head_in = p.emb * p.num_pools;
     for (int j = 0; j < p.mlp_num_linear; j++) {
         const bool last = j == p.mlp_num_linear - 1;
-        float *hout = (j & 1) ? hb1 : hb0;
-        head_linear(ws, hin, hld, hk, p.head[j].Wt, p.head[j].ldw, p.head[j].bias, p.head[j].out,
-                    last ? p.out_act : p.mlp_act, hout, HLD, last ? p.out : nullptr, p.mlp_out,
-                    ms.pend_gid, n_rows);
-        hin = hout; hld = HLD; hk = p.head[j].out;
+        for (int c = 0; c < p.hchunks[j]; c++) {
+            const TLinear &L = p.hl[j][c];
+            if (j == 0) {  // A chunk: pending[:, 128c : 128c + K) -> (hi, lo), zero padded
+                const int kp = L.KA * tc::ATOM_K, q4 = kp / 4;
+                for (int idx = tid; idx < TM * q4; idx += NTHREADS) {
+                    const int r = idx / q4, cc = (idx - r * q4) * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < n_rows && c * 128 + cc < head_in)  // head_in % 4 == 0
+                        v = __ldcg(reinterpret_cast<const float4 *>(pending + (size_t)r * PLD + c * 128 + cc));
+                    const float4 h = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z),
+                                                 tc::tf32_hi(v.w));
+                    const uint32_t off = tc::canon_chunk_offset(r, cc, TM);
+                    *reinterpret_cast<float4 *>(RHI + off) = h;
+                    *reinterpret_cast<float4 *>(RLO + off) =
+                        make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                }
+                tc::fence_async_smem();
+                tc::tc_fence_before();
+                __syncthreads();
+            }
+            if (tid == 0) {
+                gemm_issue(ms, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, L, false, c > 0);
+                tc::mbar_wait(&ms.bar_done, done_cnt & 1);
+            }
+            done_cnt++;
+            __syncthreads();
+            tc::tc_fence_after();
+        }
+        const TLinear &L0 = p.hl[j][0];
+        if (last)
+            epilogue(tmem_d, L0.N, L0.bias, p.out_act, nullptr, EPI_GLOBAL, nullptr, nullptr, p.out,
+                     ms.pend_gid, n_rows, p.mlp_out, p.head_n[j]);
+        else
+            epilogue(tmem_d, L0.N, L0.bias, p.mlp_act, nullptr, EPI_SPLIT, RHI, RLO);
+        tc::fence_async_smem();
+        tc::tc_fence_before();
+        __syncthreads();
     }
 }
 
@@ -423,10 +389,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
                 // beyond the tile are zeroed too so no stale NaN/Inf ever enters an MMA
                 const int F = p.in_dim, Fp = (F + 31) & ~31;
                 const float *src = p.x + (size_t)cur_row0 * F;
-                for (int idx = tid; idx < TM * Fp; idx += NTHREADS) {
-                    const int r = idx / Fp, c = idx - r * Fp;
-                    const float v = (r < rows && c < F) ? __ldg(src + (size_t)r * F + c) : 0.0f;
-                    *reinterpret_cast<float *>(RX + tc::canon_offset(r, c, TM)) = v;
+                // batches of 8 independent loads per thread so the global latency is paid once per
+                // batch, not once per element
+                for (int b0 = 0; b0 < TM * Fp; b0 += NTHREADS * 8) {
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int idx = b0 + q * NTHREADS + tid;
+                        const int r = idx / Fp, c = idx - r * Fp;
+                        v[q] = (r < rows && c < F) ? __ldg(src + (size_t)r * F + c) : 0.0f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int idx = b0 + q * NTHREADS + tid;
+                        const int r = idx / Fp, c = idx - r * Fp;
+                        if (r < TM) *reinterpret_cast<float *>(RX + tc::canon_offset(r, c, TM)) = v[q];
+                    }
                 }
             }
             int2 my_edge[ECAP / NTHREADS];
@@ -604,11 +582,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
             tc::tc_fence_after();
             GNNB_PHASE(7)   // weight copies + MMAs until the accumulator is ready
             if (p.conv_type == GNNB_CONV_GCN) {
-                epilogue(tmem_d, p.l0[l].N, p.l0[l].bias, p.gnn_act, skip, false, RX, nullptr);
+                epilogue(tmem_d, p.l0[l].N, p.l0[l].bias, p.gnn_act, skip, EPI_X, RX, nullptr);
             } else {
                 // the ring is idle while the epilogue runs: start fetching the second GEMM's weights
                 if (tid == 0) gemm_prefetch(ms, RX, p.l1[l]);
-                epilogue(tmem_d, p.l0[l].N, p.l0[l].bias, GNNB_ACT_RELU, nullptr, true, RHI, RLO);
+                epilogue(tmem_d, p.l0[l].N, p.l0[l].bias, GNNB_ACT_RELU, nullptr, EPI_SPLIT, RHI, RLO);
                 tc::fence_async_smem();
                 tc::tc_fence_before();
                 __syncthreads();
@@ -621,7 +599,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
                 __syncthreads();
                 tc::tc_fence_after();
                 GNNB_PHASE(7)
-                epilogue(tmem_d, p.l1[l].N, p.l1[l].bias, p.gnn_act, skip, false, RX, nullptr);
+                epilogue(tmem_d, p.l1[l].N, p.l1[l].bias, p.gnn_act, skip, EPI_X, RX, nullptr);
             }
             tc::tc_fence_before();
             __syncthreads();
@@ -663,7 +641,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
             gdone += cnt;
             GNNB_PHASE(4)
             if (base_n + cnt == HEAD_G) {
-                head_flush(p, ms, RHI, RLO, pending, HEAD_G);
+                head_flush(p, ms, tmem_d, RX, RHI, RLO, pending, HEAD_G, done_cnt);
                 if (tid == 0) ms.pend_n = 0;
                 GNNB_PHASE(5)
             }
@@ -674,7 +652,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
     __syncthreads();
     {
         const int left = ms.pend_n;
-        if (left > 0) head_flush(p, ms, RHI, RLO, pending, left);
+        if (left > 0) head_flush(p, ms, tmem_d, RX, RHI, RLO, pending, left, done_cnt);
     }
     GNNB_PHASE(5)
 #undef GNNB_PHASE
@@ -726,14 +704,39 @@ int fused_tc_prepare(gnnb_model *m)
         m->layer_dims(k, &fi, &fo);
         if (d.conv_type == GNNB_CONV_GCN) {  // [bias, lin_weight]
             pend.push_back({img.size(), fi, fo});
-            build_weight_image(m->params[idx + 1].host.data(), fo, fi, fi, 0, img);
+            build_weight_image(m->params[idx + 1].host.data(), fo, fo, fi, fi, 0, img);
             idx += 2;
         } else {                              // [w0, b0, w1, b1]
             pend.push_back({img.size(), fi, fo});
-            build_weight_image(m->params[idx].host.data(), fo, fi, fi, 0, img);
+            build_weight_image(m->params[idx].host.data(), fo, fo, fi, fi, 0, img);
             pend.push_back({img.size(), fo, fo});
-            build_weight_image(m->params[idx + 2].host.data(), fo, fo, fo, 0, img);
+            build_weight_image(m->params[idx + 2].host.data(), fo, fo, fo, fo, 0, img);
             idx += 4;
+        }
+    }
+    // MLP head: N padded to a multiple of 16, K cut into 128-wide chunks, bias zero padded
+    struct HeadPending { size_t off[MAX_HCHUNK]; int K[MAX_HCHUNK]; int nch, N, n_true; size_t bias; };
+    std::vector<HeadPending> hpend;
+    {
+        int in = head_in;
+        for (int j = 0; j < d.mlp_num_linear; j++) {
+            const int out = (j == d.mlp_num_linear - 1) ? d.mlp_out : d.mlp_hidden;
+            HeadPending h{};
+            h.N = (out + 15) / 16 * 16;
+            h.n_true = out;
+            h.nch = (in + 127) / 128;
+            const float *W = m->params[2 * (size_t)j].host.data();
+            const float *b = m->params[2 * (size_t)j + 1].host.data();
+            for (int c = 0; c < h.nch; c++) {
+                h.K[c] = std::min(128, in - 128 * c);
+                h.off[c] = img.size();
+                build_weight_image(W, h.N, out, h.K[c], in, 128 * c, img);
+            }
+            h.bias = img.size();
+            img.resize(img.size() + h.N, 0.0f);
+            for (int i = 0; i < out; i++) img[h.bias + i] = b[i];
+            hpend.push_back(h);
+            in = out;
         }
     }
     int rc = plan->images.ensure(img.size() * sizeof(float));
@@ -765,10 +768,15 @@ int fused_tc_prepare(gnnb_model *m)
         if (d.conv_type == GNNB_CONV_GIN) p.l1[k] = mk(pend[pi++], L.b.bias);
     }
     for (int j = 0; j < d.mlp_num_linear; j++) {
-        HLinear h;
-        h.Wt = m->head[j].Wt; h.bias = m->head[j].bias; h.in = m->head[j].in;
-        h.out = m->head[j].out; h.ldw = m->head[j].ldw;
-        p.head[j] = h;
+        const HeadPending &h = hpend[j];
+        p.hchunks[j] = h.nch;
+        p.head_n[j] = h.n_true;
+        for (int c = 0; c < h.nch; c++) {
+            TLinear t;
+            t.img = base + h.off[c]; t.bias = base + h.bias; t.K = h.K[c]; t.N = h.N;
+            t.KA = (h.K[c] + tc::ATOM_K - 1) / tc::ATOM_K;
+            p.hl[j][c] = t;
+        }
     }
     plan->smem_bytes = 1024 + 3 * (size_t)REGION + sizeof(Misc);
     cudaError_t e = cudaFuncSetAttribute(fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -11,7 +11,9 @@ namespace gnnb {
 
 // Weight image for the tensor-core path: for every K atom (32 columns of K) the N x 128-byte
 // rows of W in the canonical swizzled layout, hi part followed by lo part.
-void build_weight_image(const float *W, int N, int K, int ld, int col0, std::vector<float> &img)
+// Rows >= n_valid of the image are zero (N padded up to the MMA granule).
+void build_weight_image(const float *W, int N, int n_valid, int K, int ld, int col0,
+                        std::vector<float> &img)
 {
     const int KA = (K + tc::ATOM_K - 1) / tc::ATOM_K;
     const size_t atom_floats = (size_t)2 * N * tc::ATOM_K;
@@ -23,7 +25,7 @@ void build_weight_image(const float *W, int N, int K, int ld, int col0, std::vec
         for (int n = 0; n < N; n++)
             for (int kk = 0; kk < tc::ATOM_K; kk++) {
                 const int k = ka * tc::ATOM_K + kk;
-                const float v = (k < K) ? W[(size_t)n * ld + col0 + k] : 0.0f;
+                const float v = (k < K && n < n_valid) ? W[(size_t)n * ld + col0 + k] : 0.0f;
                 const float h = tc::tf32_hi(v);
                 const uint32_t off = tc::canon_offset(n, kk, N) / 4;  // atom-local (k < 32)
                 hi[off] = h;
@@ -146,7 +148,7 @@ extern "C" int gnnb_debug_tc_gemm(const float *A, const float *W, float *C, int 
                  "tc gemm: 1 <= K <= 128, N a multiple of 16 up to 128");
     const int KA = (K + tc::ATOM_K - 1) / tc::ATOM_K;
     std::vector<float> img;
-    build_weight_image(W, N, K, K, 0, img);
+    build_weight_image(W, N, N, K, K, 0, img);
     float *dA = nullptr, *dB = nullptr, *dC = nullptr;
     GNNB_CUDA(cudaMalloc(&dA, sizeof(float) * 128 * K));
     GNNB_CUDA(cudaMalloc(&dB, sizeof(float) * img.size()));
