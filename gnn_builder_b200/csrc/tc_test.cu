@@ -135,6 +135,144 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_test_kernel(const float *__res
     if (warp == 0) tc::tmem_dealloc(tmem_d, 128);
 }
 
+
+// Second diagnostic: the primitives of the tensor-core aggregation path on one tile,
+//   C[128][N] = (ADJ[128][128] . X[128][F]) . W[N][F]^T
+// ADJ.X as kind::f16 MMAs (ADJ bf16 K-major, X as three bf16 planes MN-major), the product moved
+// to tensor memory as the hi/lo TF32 A operand with tcgen05.st, then the 3xTF32 transform with
+// A from tensor memory -- exactly the operand layouts and descriptors fused_tc.cu uses.
+__global__ void __launch_bounds__(256, 1) tc_agg_test_kernel(const float *__restrict__ Adj,
+                                                             const float *__restrict__ X,
+                                                             const float *__restrict__ Bimg,
+                                                             float *__restrict__ C,
+                                                             float *__restrict__ AggOut, int F, int N)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full, bar_empty, bar_done;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KA = (F + tc::ATOM_K - 1) / tc::ATOM_K, kp = KA * tc::ATOM_K;
+    unsigned char *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *ADJ = base;
+    unsigned char *XP = ADJ + tc::PLANE_BYTES;            // three planes
+    unsigned char *WS = XP + 3 * tc::PLANE_BYTES;         // one weight slot (N x 128 B)
+    const uint32_t slot_bytes = (uint32_t)N * tc::ROW_BYTES;
+
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    if (tid == 0) {
+        tc::mbar_init(&bar_full, 1); tc::mbar_init(&bar_empty, 1); tc::mbar_init(&bar_done, 1);
+        tc::mbar_fence_init();
+    }
+    // ADJ: 8 sources per thread-iteration -> one 16-byte chunk of bf16
+    for (int idx = tid; idx < TM * 16; idx += blockDim.x) {
+        const int d = idx >> 4, s0 = (idx & 15) * 8;
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t a = __float_as_uint(Adj[(size_t)d * TM + s0 + 2 * j]);
+            const uint32_t b = __float_as_uint(Adj[(size_t)d * TM + s0 + 2 * j + 1]);
+            w[j] = __byte_perm(a, b, 0x7632);
+        }
+        *reinterpret_cast<uint4 *>(ADJ + tc::adj_chunk_offset(d, s0)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    // X planes: thread (row, half) handles every second chunk of 8 features
+    {
+        const int r = tid & 127;
+        for (int c = tid >> 7; c < kp / 8; c += 2) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = (c * 8 + j < F) ? X[(size_t)r * F + c * 8 + j] : 0.0f;
+            uint4 h, m, l;
+            tc::split3_pack8(v, h, m, l);
+            const uint32_t off = tc::plane_chunk_offset(r, c * 8);
+            *reinterpret_cast<uint4 *>(XP + off) = h;
+            *reinterpret_cast<uint4 *>(XP + tc::PLANE_BYTES + off) = m;
+            *reinterpret_cast<uint4 *>(XP + 2 * tc::PLANE_BYTES + off) = l;
+        }
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = tmem_slot, tmem_ahi = tmem_slot + 128, tmem_alo = tmem_slot + 256;
+
+    if (tid == 0) {   // AGG = ADJ . (Xh + Xm + Xl): K = 128 source nodes, 16 per MMA
+        const uint32_t idesc = tc::make_idesc_bf16(TM, kp, 1);
+        for (int pl = 0; pl < 3; pl++)
+            for (int ks = 0; ks < 8; ks++) {
+                const uint32_t a = tc::smem_u32(ADJ) + (uint32_t)(ks >> 2) * tc::PLANE_BLOCK_BYTES +
+                                   (uint32_t)(ks & 3) * 32u;
+                const uint32_t b = tc::smem_u32(XP) + (uint32_t)pl * tc::PLANE_BYTES + (uint32_t)ks * 2048u;
+                tc::mma_bf16(tmem_d, tc::make_desc(a),
+                             tc::make_desc_mn(b, tc::PLANE_BLOCK_BYTES, 1024u), idesc,
+                             (pl == 0 && ks == 0) ? 0u : 1u);
+            }
+        tc::mma_commit(&bar_done);
+    }
+    tc::mbar_wait(&bar_done, 0);
+    tc::tc_fence_after();
+    {   // accumulator -> (hi, lo) A operand in tensor memory, thread per row
+        const int row = 32 * (warp & 3) + lane;
+        const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+        for (int c0 = (warp >> 2) * 32; c0 < kp; c0 += 64) {
+            float v[32], h[32], l[32];
+            tc::tmem_ld32(tmem_d + lane_base + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                h[j] = tc::tf32_hi(v[j]);
+                l[j] = v[j] - h[j];
+                if (AggOut != nullptr && c0 + j < F) AggOut[(size_t)row * F + c0 + j] = v[j];
+            }
+            tc::tmem_st32(tmem_ahi + lane_base + (uint32_t)c0, h);
+            tc::tmem_st32(tmem_alo + lane_base + (uint32_t)c0, l);
+        }
+        tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (tid == 0) {   // C = A . W^T with A from tensor memory, weight units through one slot
+        const uint32_t idesc = tc::make_idesc_tf32(TM, N);
+        const unsigned char *bsrc = reinterpret_cast<const unsigned char *>(Bimg);
+        for (int u = 0; u < 2 * KA; u++) {
+            const int part = u >= KA ? 1 : 0, ka = part ? u - KA : u;
+            if (u > 0) tc::mbar_wait(&bar_empty, (u - 1) & 1);
+            tc::mbar_expect_tx(&bar_full, slot_bytes);
+            tc::bulk_g2s(WS, bsrc + ((size_t)ka * 2 + part) * slot_bytes, slot_bytes, &bar_full);
+            tc::mbar_wait(&bar_full, u & 1);
+            tc::tc_fence_after();
+#pragma unroll
+            for (int k8 = 0; k8 < tc::ATOM_K / tc::MMA_K; k8++) {
+                const uint32_t col = (uint32_t)(ka * tc::ATOM_K + k8 * tc::MMA_K);
+                const uint64_t b = tc::make_desc(tc::smem_u32(WS) + (uint32_t)k8 * tc::MMA_K * 4);
+                if (part == 0) {
+                    tc::mma_tf32_ts(tmem_d, tmem_ahi + col, b, idesc, (u == 0 && k8 == 0) ? 0u : 1u);
+                    tc::mma_tf32_ts(tmem_d, tmem_alo + col, b, idesc, 1u);
+                } else {
+                    tc::mma_tf32_ts(tmem_d, tmem_ahi + col, b, idesc, 1u);
+                }
+            }
+            tc::mma_commit(&bar_empty);
+        }
+        tc::mma_commit(&bar_done);
+    }
+    tc::mbar_wait(&bar_done, 1);
+    tc::tc_fence_after();
+    {
+        const int row = 32 * (warp & 3) + lane;
+        for (int c0 = (warp >> 2) * 32; c0 < N; c0 += 64) {
+            float v[32];
+            tc::tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (c0 + j < N) C[(size_t)row * N + c0 + j] = v[j];
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_d, 512);
+}
+
 }  // namespace
 }  // namespace gnnb
 
@@ -163,5 +301,36 @@ extern "C" int gnnb_debug_tc_gemm(const float *A, const float *W, float *C, int 
     GNNB_CUDA(cudaDeviceSynchronize());
     GNNB_CUDA(cudaMemcpy(C, dC, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost));
     cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    return GNNB_OK;
+}
+
+// Diagnostic entry point: C[128][N] = (Adj[128][128] . X[128][F]) . W[N][F]^T, Adj holding small
+// non-negative integers (edge multiplicities); agg (optional, [128][F]) receives Adj . X.
+extern "C" int gnnb_debug_tc_agg_gemm(const float *Adj, const float *X, const float *W, float *C,
+                                      float *agg, int F, int N)
+{
+    GNNB_REQUIRE(Adj && X && W && C, "null argument");
+    GNNB_REQUIRE(F >= 1 && F <= 128 && N >= 16 && N <= 128 && N % 16 == 0,
+                 "tc agg gemm: 1 <= F <= 128, N a multiple of 16 up to 128");
+    std::vector<float> img;
+    build_weight_image(W, N, N, F, F, 0, img);
+    float *dAdj = nullptr, *dX = nullptr, *dB = nullptr, *dC = nullptr, *dAgg = nullptr;
+    GNNB_CUDA(cudaMalloc(&dAdj, sizeof(float) * 128 * 128));
+    GNNB_CUDA(cudaMalloc(&dX, sizeof(float) * 128 * F));
+    GNNB_CUDA(cudaMalloc(&dB, sizeof(float) * img.size()));
+    GNNB_CUDA(cudaMalloc(&dC, sizeof(float) * 128 * N));
+    GNNB_CUDA(cudaMalloc(&dAgg, sizeof(float) * 128 * F));
+    GNNB_CUDA(cudaMemcpy(dAdj, Adj, sizeof(float) * 128 * 128, cudaMemcpyHostToDevice));
+    GNNB_CUDA(cudaMemcpy(dX, X, sizeof(float) * 128 * F, cudaMemcpyHostToDevice));
+    GNNB_CUDA(cudaMemcpy(dB, img.data(), sizeof(float) * img.size(), cudaMemcpyHostToDevice));
+    const size_t smem = 1024 + (size_t)4 * tc::PLANE_BYTES + (size_t)N * tc::ROW_BYTES;
+    GNNB_CUDA(cudaFuncSetAttribute(tc_agg_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    tc_agg_test_kernel<<<1, 256, smem>>>(dAdj, dX, dB, dC, agg ? dAgg : nullptr, F, N);
+    GNNB_CUDA(cudaGetLastError());
+    GNNB_CUDA(cudaDeviceSynchronize());
+    GNNB_CUDA(cudaMemcpy(C, dC, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost));
+    if (agg) GNNB_CUDA(cudaMemcpy(agg, dAgg, sizeof(float) * 128 * F, cudaMemcpyDeviceToHost));
+    cudaFree(dAdj); cudaFree(dX); cudaFree(dB); cudaFree(dC); cudaFree(dAgg);
     return GNNB_OK;
 }

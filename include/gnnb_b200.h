@@ -207,6 +207,12 @@ int gnnb_gcn_conv_partition(int n_local, int row_begin, int n_total, int num_edg
 /* One-CTA tensor-core GEMM C[128][N] = A[128][K] . W[N][K]^T (tcgen05, 3xTF32) built from the
  * same primitives as the fused kernel's node transform; host buffers; K <= 128, N % 16 == 0. */
 int gnnb_debug_tc_gemm(const float *A, const float *W, float *C, int K, int N);
+/* One-tile check of the tensor-core aggregation path: C[128][N] = (Adj . X) . W^T where Adj
+ * [128][128] holds edge multiplicities (small non-negative integers), X is [128][F]; the
+ * aggregation runs as bf16x3 MMAs and the transform takes its A operand from tensor memory, as in
+ * the fused kernel.  agg (optional, [128][F]) receives Adj . X.  Host buffers. */
+int gnnb_debug_tc_agg_gemm(const float *Adj, const float *X, const float *W, float *C, float *agg,
+                           int F, int N);
 
 #ifdef __cplusplus
 }
