@@ -47,7 +47,7 @@ EXPORTS = [
     "gnnb_gcn_conv", "gnnb_gin_conv", "gnnb_sage_conv", "gnnb_pna_conv",
     "gnnb_global_add_pool", "gnnb_global_mean_pool", "gnnb_global_max_pool",
     "gnnb_partition_tables", "gnnb_degree_inv_sqrt", "gnnb_gcn_conv_partition",
-    "gnnb_debug_tc_gemm", "gnnb_debug_tc_agg_gemm",
+    "gnnb_debug_tc_gemm", "gnnb_debug_tc_agg_gemm", "gnnb_debug_tc_mma_rate",
 ]
 
 _lib = None
@@ -106,6 +106,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         getattr(lib, f"gnnb_global_{k}_pool").argtypes = [ci, ci, vp, vp, ci]
     lib.gnnb_debug_tc_gemm.argtypes = [vp, vp, vp, ci, ci]
     lib.gnnb_debug_tc_agg_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci]
+    lib.gnnb_debug_tc_mma_rate.argtypes = [ci, ci, ci, vp]
     lib.gnnb_partition_tables.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]
     lib.gnnb_degree_inv_sqrt.argtypes = [vp, vp, ci, vp]
     lib.gnnb_gcn_conv_partition.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci,

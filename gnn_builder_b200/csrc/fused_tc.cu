@@ -1,32 +1,43 @@
-// Kernel (1), tensor-core version: the persistent whole-model fused kernel of fused.cu with the
-// node-transform GEMMs on the 5th-generation tensor cores (tcgen05.mma.kind::tf32, accumulators in
-// tensor memory) using the error-compensated 3xTF32 split of tc.cuh, so results stay fp32-grade
-// (<= 1e-4 parity bound with two orders of magnitude of margin).
+// Kernel (1), tensor-core version: the persistent whole-model fused kernel for molecular-sized
+// graphs with BOTH halves of every conv layer on the 5th-generation tensor cores (tcgen05):
+//
+//   aggregation     AGG = ADJ . X       kind::f16 MMAs.  ADJ is the tile's 128x128 block-diagonal
+//                                       matrix of in-edge multiplicities (bf16, exact), X the layer
+//                                       input split into three bf16 planes (hi+mid+lo = 24 bits,
+//                                       tc.cuh), fp32 accumulation in tensor memory: fp32-grade.
+//   node transform  D = A . W^T         kind::tf32 MMAs, error-compensated 3xTF32 (tc.cuh), the A
+//                                       operand (hi/lo parts) read from TENSOR MEMORY, the weight
+//                                       atoms streamed L2 -> shared memory with cp.async.bulk.
+//
+// Every other step is "thread per row": the thread that owns TMEM lane r (row r of the tile) moves
+// its row accumulator -> registers (tcgen05.ld) -> bias / skip / activation / GCN-SAGE scaling ->
+// either back to tensor memory as the next A operand (tcgen05.st) or to the bf16 planes of the next
+// layer input (conflict-free 16-byte shared-memory stores).  No gather loops, no neighbor tables,
+// no shared-memory traffic for activations, and no bank conflicts anywhere on the layer path.
 //
 // Per CTA (one per SM, 256 threads, 128-row tile of packed graphs):
-//   shared memory   R_X  64 KB  layer input X, canonical K-major SWIZZLE_128B layout; while a GEMM
-//                               runs it is the ring of weight slots the bulk copies land in
-//                   R_HI 64 KB  A operand, hi parts   (aggregate, then the GIN hidden layer)
-//                   R_LO 64 KB  A operand, lo parts
-//   tensor memory   128 columns x 128 lanes fp32 accumulator
-//   weights         pre-split (hi/lo) and pre-swizzled on the host into the exact shared-memory
-//                   image of each 32-wide K atom, so one cp.async.bulk (TMA engine, no tensor map)
-//                   per atom lands them ready for the MMA; they stay L2 resident across CTAs.
-// One elected thread issues the bulk copies and the MMAs and signals completion through mbarriers.
-// A GEMM is a sequence of "units": first the hi weight atoms (each: A_hi.B_hi and A_lo.B_hi, four
-// k-steps of 8), then the lo atoms (A_hi.B_lo).  With N = 128 the ring holds 4 slots of 16 KB, so
-// ALL hi atoms of a K = 128 GEMM are in flight at once (one L2 latency), and each lo atom is
-// fetched into the slot of a finished hi unit while later units run.  GIN's second GEMM has its
-// first slots prefetched while the first GEMM's epilogue runs.  All 8 warps run the aggregation
-// before and the TMEM -> register -> shared epilogue (bias, skip, activation, hi/lo re-split) after.
-// The skip connection of interior layers needs X after R_X has been recycled for the weight ring:
-// X is parked in a per-CTA global scratch (64 KB, L2 resident) and re-read in the epilogue.
-// The MLP head (fp32 FMA, 16 graphs per call) is deferred: pooled vectors queue in a per-CTA
-// pending buffer and the head runs once 16 graphs are waiting, so its weight streaming is
-// amortised over ~3 tiles.
+//   shared memory   ADJ  32 KB   bf16 [dst][src], K-major SWIZZLE_128B (A operand of the aggregation)
+//                   XP   96 KB   three bf16 planes [node][feature], MN-major SWIZZLE_128B (B operand)
+//                   RING 64 KB   4 slots of 16 KB for weight atoms (TMA bulk copies, mbarriers)
+//                   CNT  16 KB   u8 edge multiplicities built with shared-memory atomics
+//   tensor memory   512 columns: D accumulator [0,128), A_hi [128,256), A_lo [256,384)
+// One elected thread issues the bulk copies and all MMAs; completion flows through mbarriers
+// (tcgen05.commit).  The weight stream is continuous across GEMMs: while a GEMM drains, the first
+// atoms of the next one (known statically: next linear of the layer / next layer / head / next tile)
+// are already in flight.
 //
-// Supported: GCN and GIN, every layer width a multiple of 16 up to 128 (BASELINE configs 1 and 2);
-// everything else uses fused.cu / the layerwise path.
+// GCN   planes hold dinv (.) X, ADJ gets +I, the row result is scaled by dinv_v: lib:1246-1278
+// GIN   ADJ gets +I, eps * x_v is added in registers: lib:1519-1529; hidden layer stays in TMEM
+// SAGE  mean = (ADJ . X) / deg, two transforms accumulate in the same TMEM tile: lib:2180-2207
+// Pooling reads the planes (warp per graph); the MLP head runs on the tensor cores for 128 pooled
+// graphs at a time (pending buffer in L2), cpp:454-530.
+//
+// Non-finite activations would leak between the graphs of a tile through 0 * Inf inside the
+// aggregation MMA (the reference keeps graphs independent), so every value written to the planes
+// is checked and the batch is re-run on the layerwise path if any is Inf/NaN (status 3).
+//
+// Supported: GCN, GIN and SAGE, layer widths a multiple of 16 up to 128; everything else uses
+// fused.cu / the layerwise path.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -42,19 +53,22 @@ void build_weight_image(const float *W, int N, int n_valid, int K, int ld, int c
 namespace {
 
 constexpr int TM = 128;
-constexpr int ECAP = 2048;
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 256;            // worker threads (8 warps; warp 0 also issues the MMAs)
 constexpr int NWARPS = NTHREADS / 32;
+constexpr int CTA_THREADS = NTHREADS + 32;   // + the weight-producer warp
 constexpr int MAX_LAYERS = 8;
 constexpr int MAX_HEAD = 6;
 constexpr int HEAD_G = 128;      // pooled graphs per head call (one 128-row MMA tile)
 constexpr int MAX_HCHUNK = 4;    // 128-wide K chunks of the first head layer (head_in <= 512)
 constexpr int MAX_DIM = 128;
 constexpr int PLD = 520;         // row stride of the pending pooled vectors (>= 512 + 4)
-constexpr int REGION = TM * MAX_DIM * 4;  // 64 KB
-constexpr int MAX_SLOTS = 8;
+constexpr int NSLOT = 4;
+constexpr int SLOT_STRIDE = 16384;
+constexpr int RING_BYTES = NSLOT * SLOT_STRIDE;
+constexpr int CNT_BYTES = TM * TM;
 constexpr int MAX_NODES_PER_GRAPH = 64;
-constexpr int AGG_R = 4;         // destination rows aggregated concurrently per warp
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TM_D = 0, TM_AHI = 128, TM_ALO = 256;
 
 struct TLinear {
     const float *img;   // weight image: per K atom [hi N x 128 B | lo N x 128 B]
@@ -67,10 +81,10 @@ struct TcParams {
     int mlp_num_linear, mlp_act, out_act, emb, mlp_out;
     float gin_eps;
     int fi[MAX_LAYERS], fo[MAX_LAYERS];
-    TLinear l0[MAX_LAYERS], l1[MAX_LAYERS];
-    TLinear hl[MAX_HEAD][MAX_HCHUNK];   // MLP head linears, K cut into 128-wide chunks
+    TLinear l0[MAX_LAYERS], l1[MAX_LAYERS];   // l1: GIN second linear / SAGE root weight
+    TLinear hl[MAX_HEAD][MAX_HCHUNK];         // MLP head linears, K cut into 128-wide chunks
     int hchunks[MAX_HEAD];
-    int head_n[MAX_HEAD];               // true output widths (N of the images is padded to 16)
+    int head_n[MAX_HEAD];                     // true output widths (N of the images is padded to 16)
     const float *x;
     const int32_t *coo;
     const int64_t *node_ptr, *edge_ptr;
@@ -79,39 +93,29 @@ struct TcParams {
     const int32_t *tile_bounds;
     int n_tiles;
     int *error_flag;
-    float *scratch;               // [grid][128][128] parked X for the skip connection
     float *pending;               // [grid][HEAD_G][PLD] pooled vectors waiting for the head
     unsigned long long *timing;
+    size_t img_copy_bytes;        // distance between the replicas of the weight images
+    int img_copies;
 };
 
 struct Misc {
-    uint64_t bar_full[MAX_SLOTS], bar_empty[MAX_SLOTS], bar_done;
-    uint32_t full_cnt[MAX_SLOTS], empty_cnt[MAX_SLOTS];
+    uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_done;
     uint32_t tmem_slot;
     int pend_n;
+    int nonfinite;
     int pend_gid[HEAD_G];
-    float dinv[TM];
     int deg[TM];
-    int off[TM + 1];
-    int rowg[TM];
     int grow[TM + 2];
     int gedge[TM + 2];
-    int scan_tmp[8];
-    unsigned short edges[ECAP];
-    unsigned char nbr[ECAP];
 };
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool valid)
+// linear ids: 2 * layer + {0: l0, 1: l1}; 64 + 4 * head_layer + chunk
+constexpr int LIN_HEAD = 64;
+__device__ __forceinline__ const TLinear &lin(const TcParams &p, int id)
 {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gsrc), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+    if (id >= LIN_HEAD) return p.hl[(id - LIN_HEAD) >> 2][(id - LIN_HEAD) & 3];
+    return (id & 1) ? p.l1[id >> 1] : p.l0[id >> 1];
 }
 
 __device__ __forceinline__ int lower_bound64(const int64_t *__restrict__ ptr, int n, int64_t v)
@@ -133,196 +137,373 @@ __global__ void tc_tile_bounds_kernel(const int64_t *__restrict__ node_ptr, int 
 }
 
 // ---------------------------------------------------------------------------------------
-// GEMM issue (ONE thread).  D[128][N] (tensor memory) = A(hi,lo)[128][KA*32] . W^T, 3xTF32.
-__device__ __forceinline__ int gemm_slots(const TLinear &L)
+// Weight stream.  A dedicated producer warp walks the (static) sequence of linears the CTA will
+// run -- per tile: the conv layers' linears in order, then the head's if 128 pooled graphs are
+// waiting -- and keeps the 4-slot ring full of weight "units" (one 32-wide K atom of the hi or
+// the lo image, N x 128 bytes) with TMA bulk copies; the MMA-issuing warp consumes units in the
+// same order.  full[s] / empty[s] mbarriers carry the hand-off, so the stream runs ahead across
+// GEMM, layer and tile boundaries without any bookkeeping on the consumer side.
+//
+// Both warps execute warp-uniform control flow (every value they use is broadcast from lane 0 or
+// comes from the kernel parameters), so the compiler keeps descriptors and addresses in uniform
+// registers and a tcgen05.mma costs one instruction; only the MMA / commit / bulk-copy
+// instructions themselves are predicated on the elected lane.  Issued from a divergent
+// `if (tid == 0)` region the same loop costs ~110 cycles per MMA (a register -> uniform-register
+// waterfall per instruction), 1.7x the MMA itself (tools/mma_rate.py).
+__device__ __forceinline__ void produce_linear(Misc &ms, uint32_t ring, uint32_t &prod,
+                                               const TLinear &L, size_t copy_off, bool leader)
 {
-    const int s = REGION / (L.N * tc::ROW_BYTES);
-    return s < MAX_SLOTS ? s : MAX_SLOTS;
-}
-__device__ __forceinline__ const unsigned char *unit_src(const TLinear &L, int u)
-{
-    const int part = u >= L.KA ? 1 : 0, ka = part ? u - L.KA : u;
-    return reinterpret_cast<const unsigned char *>(L.img) +
-           ((size_t)ka * 2 + part) * (size_t)L.N * tc::ROW_BYTES;
-}
-// start the bulk copies of the first min(slots, units) weight slots
-__device__ __forceinline__ void gemm_prefetch(Misc &ms, unsigned char *ring, const TLinear &L)
-{
-    const uint32_t slot_bytes = (uint32_t)L.N * tc::ROW_BYTES;
-    const int U = 2 * L.KA, ns = gemm_slots(L);
-    for (int u = 0; u < ns && u < U; u++) {
-        tc::mbar_expect_tx(&ms.bar_full[u], slot_bytes);
-        tc::bulk_g2s(ring + (size_t)u * slot_bytes, unit_src(L, u), slot_bytes, &ms.bar_full[u]);
-    }
-}
-__device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo,
-                                           unsigned char *ring, const TLinear &L, bool prefetched,
-                                           bool accumulate = false)
-{
-    const uint32_t slot_bytes = (uint32_t)L.N * tc::ROW_BYTES;
-    const uint32_t idesc = tc::make_idesc_tf32(TM, L.N);
-    const int U = 2 * L.KA, ns = gemm_slots(L);
-    if (!prefetched) gemm_prefetch(ms, ring, L);
-    tc::tc_fence_after();
-    for (int u = 0; u < U; u++) {
-        const int s = u % ns;
-        tc::mbar_wait(&ms.bar_full[s], ms.full_cnt[s] & 1);
-        ms.full_cnt[s]++;
-        tc::tc_fence_after();
-        const int part = u >= L.KA ? 1 : 0, ka = part ? u - L.KA : u;
-        const uint32_t ah = a_hi + (uint32_t)ka * TM * tc::ROW_BYTES;
-        const uint32_t al = a_lo + (uint32_t)ka * TM * tc::ROW_BYTES;
-        const uint32_t b = tc::smem_u32(ring) + (uint32_t)s * slot_bytes;
-#pragma unroll
-        for (int k8 = 0; k8 < tc::ATOM_K / tc::MMA_K; k8++) {
-            const uint32_t ko = (uint32_t)k8 * tc::MMA_K * 4;
-            if (part == 0) {
-                tc::mma_tf32(tmem_d, tc::make_desc(ah + ko), tc::make_desc(b + ko), idesc,
-                             (u == 0 && k8 == 0 && !accumulate) ? 0u : 1u);
-                tc::mma_tf32(tmem_d, tc::make_desc(al + ko), tc::make_desc(b + ko), idesc, 1u);
-            } else {
-                tc::mma_tf32(tmem_d, tc::make_desc(ah + ko), tc::make_desc(b + ko), idesc, 1u);
+    const uint32_t bytes = (uint32_t)L.N * tc::ROW_BYTES;
+    const unsigned char *hi = reinterpret_cast<const unsigned char *>(L.img) + copy_off;
+    const unsigned char *lo = hi + bytes;
+    for (int part = 0; part < 2; part++) {
+        const unsigned char *src = part ? lo : hi;
+        for (int ka = 0; ka < L.KA; ka++) {
+            const uint32_t s = prod & (NSLOT - 1), use = prod / NSLOT;
+            if (use > 0) tc::mbar_wait(&ms.bar_empty[s], (use - 1) & 1);
+            if (leader) {
+                tc::mbar_expect_tx(&ms.bar_full[s], bytes);
+                tc::bulk_g2s_addr(ring + s * SLOT_STRIDE, src, bytes, &ms.bar_full[s]);
             }
-        }
-        tc::mma_commit(&ms.bar_empty[s]);
-        ms.empty_cnt[s]++;
-        // refill the slot of the PREVIOUS unit (its MMAs were issued before this unit's, so the
-        // wait is short and this unit's MMAs keep the tensor core busy meanwhile)
-        if (u >= 1 && u - 1 + ns < U) {
-            const int sp = (u - 1) % ns;
-            tc::mbar_wait(&ms.bar_empty[sp], (ms.empty_cnt[sp] - 1) & 1);
-            tc::mbar_expect_tx(&ms.bar_full[sp], slot_bytes);
-            tc::bulk_g2s(ring + (size_t)sp * slot_bytes, unit_src(L, u - 1 + ns), slot_bytes,
-                         &ms.bar_full[sp]);
+            src += 2 * (size_t)bytes;
+            prod++;
         }
     }
-    tc::mma_commit(&ms.bar_done);
+}
+// D[128][N] (+)= A(hi,lo in tensor memory)[128][KA*32] . W^T, 3xTF32: first the hi weight atoms
+// (A_hi.B_hi and A_lo.B_hi), then the lo atoms (A_hi.B_lo).  All lanes of warp 0.
+__device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &cons, uint32_t tmem_base,
+                                           const TLinear &L, bool accumulate)
+{
+    const bool leader = tc::elect_one();
+    const int KA = L.KA;
+    const uint32_t idesc = tc::make_idesc_tf32(TM, L.N);
+    const uint32_t tmem_d = tmem_base + TM_D, ahi = tmem_base + TM_AHI, alo = tmem_base + TM_ALO;
+    tc::tc_fence_after();
+    for (int ka = 0; ka < KA; ka++) {   // hi atoms
+        const uint32_t s = cons & (NSLOT - 1);
+        tc::mbar_wait(&ms.bar_full[s], (cons / NSLOT) & 1);
+        tc::tc_fence_after();
+        const uint32_t col = (uint32_t)(ka * tc::ATOM_K);
+        const uint64_t bd = tc::make_desc(ring + s * SLOT_STRIDE);
+        const uint32_t first = (ka == 0 && !accumulate) ? 0u : 1u;
+        if (leader) {
+#pragma unroll
+            for (int k8 = 0; k8 < tc::ATOM_K / tc::MMA_K; k8++) {
+                // +2 per k-step: 8 TF32 = 32 bytes along K inside the swizzle atom (>> 4)
+                tc::mma_tf32_ts(tmem_d, ahi + col + k8 * tc::MMA_K, bd + (uint64_t)(2 * k8), idesc,
+                                k8 == 0 ? first : 1u);
+                tc::mma_tf32_ts(tmem_d, alo + col + k8 * tc::MMA_K, bd + (uint64_t)(2 * k8), idesc, 1u);
+            }
+            tc::mma_commit(&ms.bar_empty[s]);
+        }
+        cons++;
+    }
+    for (int ka = 0; ka < KA; ka++) {   // lo atoms
+        const uint32_t s = cons & (NSLOT - 1);
+        tc::mbar_wait(&ms.bar_full[s], (cons / NSLOT) & 1);
+        tc::tc_fence_after();
+        const uint32_t col = (uint32_t)(ka * tc::ATOM_K);
+        const uint64_t bd = tc::make_desc(ring + s * SLOT_STRIDE);
+        if (leader) {
+#pragma unroll
+            for (int k8 = 0; k8 < tc::ATOM_K / tc::MMA_K; k8++)
+                tc::mma_tf32_ts(tmem_d, ahi + col + k8 * tc::MMA_K, bd + (uint64_t)(2 * k8), idesc, 1u);
+            tc::mma_commit(&ms.bar_empty[s]);
+        }
+        cons++;
+    }
+    if (leader) tc::mma_commit(&ms.bar_done);
 }
 
-// All threads: accumulator -> (+bias, +skip, activation) -> destination.
-//   EPI_X      : write the values into dst_hi (the X region, canonical layout)
-//   EPI_SPLIT  : write hi / lo parts into dst_hi / dst_lo (the next GEMM's A operand)
-//   EPI_GLOBAL : write columns [0, n_true) of rows [0, n_rows) to gout[gids[row]][col] (model output)
-// Columns [N, round_up(N, 32)) of the last K atom are zero filled (shared-memory modes).
-// `skip` is written by this CTA earlier in the same kernel: read it with ld.global.cg (L2), never
-// through the non-coherent read-only path.
-enum { EPI_X = 0, EPI_SPLIT = 1, EPI_GLOBAL = 2 };
-__device__ __forceinline__ void epilogue(uint32_t tmem_d, int N, const float *__restrict__ bias,
-                                         int act, const float *skip, int mode,
-                                         unsigned char *dst_hi, unsigned char *dst_lo,
-                                         float *gout = nullptr, const int *gids = nullptr,
-                                         int n_rows = 0, int ldg = 0, int n_true = 0)
+// AGG[128][n_cols] = ADJ . (Xh + Xm + Xl), K = source nodes (16 per MMA, only the k-steps that
+// cover the tile's rows).  Warp-uniform, like gemm_issue.
+__device__ __forceinline__ void agg_issue(Misc &ms, uint32_t tmem_d, uint32_t adj, uint32_t xp,
+                                          int n_cols, int rows)
+{
+    const bool leader = tc::elect_one();
+    const uint32_t idesc = tc::make_idesc_bf16(TM, n_cols, 1);
+    const int nks = (rows + 15) >> 4;
+    tc::tc_fence_after();
+    // ADJ: k-step ks lives in K atom ks >> 2 at byte 32 (ks & 3); planes: 16 nodes = 2048 bytes
+    const uint64_t a0 = tc::make_desc(adj), a1 = tc::make_desc(adj + tc::PLANE_BLOCK_BYTES);
+#pragma unroll
+    for (int pl = 0; pl < 3; pl++) {
+        const uint64_t b0 = tc::make_desc_mn(xp + (uint32_t)pl * tc::PLANE_BYTES, tc::PLANE_BLOCK_BYTES, 1024u);
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+            if (ks < nks && leader)
+                tc::mma_bf16(tmem_d, (ks < 4 ? a0 : a1) + (uint64_t)(2 * (ks & 3)), b0 + (uint64_t)(128 * ks),
+                             idesc, (pl == 0 && ks == 0) ? 0u : 1u);
+        }
+    }
+    if (leader) tc::mma_commit(&ms.bar_done);
+}
+
+// ---------------------------------------------------------------------------------------
+// Thread-per-row helpers.  Warp w owns TMEM lanes [32 (w & 3), +32) and the column blocks
+// c0 = 32 (w >> 2), +64, ...
+__device__ __forceinline__ void load_row8(const unsigned char *XP, int row, int c, float (&v)[8])
+{
+    const uint32_t off = tc::plane_chunk_offset(row, c);
+    const uint4 h = *reinterpret_cast<const uint4 *>(XP + off);
+    const uint4 m = *reinterpret_cast<const uint4 *>(XP + tc::PLANE_BYTES + off);
+    const uint4 l = *reinterpret_cast<const uint4 *>(XP + 2 * tc::PLANE_BYTES + off);
+    tc::join3_unpack8(h, m, l, v);
+}
+__device__ __forceinline__ void store_row8(unsigned char *XP, int row, int c, const float (&v)[8])
+{
+    uint4 h, m, l;
+    tc::split3_pack8(v, h, m, l);
+    const uint32_t off = tc::plane_chunk_offset(row, c);
+    *reinterpret_cast<uint4 *>(XP + off) = h;
+    *reinterpret_cast<uint4 *>(XP + tc::PLANE_BYTES + off) = m;
+    *reinterpret_cast<uint4 *>(XP + 2 * tc::PLANE_BYTES + off) = l;
+}
+__device__ __forceinline__ void split_store32(uint32_t ahi, uint32_t alo, const float (&v)[32])
+{
+    float h[32], l[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) { h[j] = tc::tf32_hi(v[j]); l[j] = v[j] - h[j]; }
+    tc::tmem_st32(ahi, h);
+    tc::tmem_st32(alo, l);
+}
+
+// aggregation accumulator -> A operand.  scale: GCN dinv_v, SAGE 1/deg (0 when deg = 0), else 1;
+// self_coef != 0: add self_coef * x_v (GIN eps).  Columns [0, kp).
+__device__ __forceinline__ void cvt_agg(uint32_t tmem_base, const unsigned char *XP, int kp,
+                                        float scale, bool divide, float divisor, float self_coef)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = 32 * (warp & 3) + lane;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    for (int c0 = (warp >> 2) * 32; c0 < kp; c0 += 64) {
+        float v[32];
+        tc::tmem_ld32(tmem_base + TM_D + lane_base + (uint32_t)c0, v);
+        if (self_coef != 0.0f) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; j8++) {
+                float xs[8];
+                load_row8(XP, row, c0 + 8 * j8, xs);
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[8 * j8 + j] = fmaf(self_coef, xs[j], v[8 * j8 + j]);
+            }
+        }
+        if (divide) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = v[j] / divisor;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] *= scale;
+        }
+        split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
+                      tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
+    }
+    tc::tmem_st_wait();
+}
+
+// own row of the planes -> A operand (SAGE root term), columns [0, kp); unscale undoes a plane scale
+__device__ __forceinline__ void cvt_self(uint32_t tmem_base, const unsigned char *XP, int kp)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = 32 * (warp & 3) + lane;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    for (int c0 = (warp >> 2) * 32; c0 < kp; c0 += 64) {
+        float v[32];
+#pragma unroll
+        for (int j8 = 0; j8 < 4; j8++) {
+            float xs[8];
+            load_row8(XP, row, c0 + 8 * j8, xs);
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[8 * j8 + j] = xs[j];
+        }
+        split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
+                      tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
+    }
+    tc::tmem_st_wait();
+}
+
+// accumulator -> (+bias, activation) -> A operand (GIN hidden layer, head hidden layers).
+// Columns [N, round_up(N, 32)) are zero filled.
+__device__ __forceinline__ void epilogue_tmem(uint32_t tmem_base, int N, const float *__restrict__ bias,
+                                              int act)
+{
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     const int npad = (N + 31) & ~31;
-    float *grow = nullptr;
-    if (mode == EPI_GLOBAL && row < n_rows) grow = gout + (size_t)gids[row] * ldg;
     for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += 64) {
         float v[32];
-        tc::tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
-        // bias (warp-uniform addresses) and the parked skip rows: issue all loads of this block
-        // up front so that their latencies overlap
-        float4 bsv[8], skv[8];
+        tc::tmem_ld32(tmem_base + TM_D + lane_base + (uint32_t)c0, v);
 #pragma unroll
         for (int j4 = 0; j4 < 8; j4++) {
-            const bool in_range = c0 + j4 * 4 < N;  // N % 4 == 0
-            bsv[j4] = in_range ? __ldg(reinterpret_cast<const float4 *>(bias + c0 + j4 * 4))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-            skv[j4] = (in_range && skip != nullptr)
-                          ? __ldcg(reinterpret_cast<const float4 *>(skip + (size_t)row * MAX_DIM + c0 + j4 * 4))
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int j4 = 0; j4 < 8; j4++) {
-            float o[4];
-            const float4 sk = skv[j4], bs = bsv[j4];
-            const bool in_range = c0 + j4 * 4 < N;
-            const float sks[4] = {sk.x, sk.y, sk.z, sk.w};
+            const bool in_range = c0 + j4 * 4 < N;   // N % 4 == 0
+            const float4 bs = in_range ? __ldg(reinterpret_cast<const float4 *>(bias + c0 + j4 * 4))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
             const float bss[4] = {bs.x, bs.y, bs.z, bs.w};
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                o[j] = in_range ? act_apply_compact(act, v[j4 * 4 + j] + bss[j] + sks[j]) : 0.0f;
-            if (mode == EPI_GLOBAL) {
-                if (grow != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (c0 + j4 * 4 + j < n_true) grow[c0 + j4 * 4 + j] = o[j];
-                }
-                continue;
-            }
-            const uint32_t off = tc::canon_chunk_offset(row, c0 + j4 * 4, TM);
-            if (mode == EPI_SPLIT) {
-                float h[4], l[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) { h[j] = tc::tf32_hi(o[j]); l[j] = o[j] - h[j]; }
-                *reinterpret_cast<float4 *>(dst_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4 *>(dst_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
-            } else {
-                *reinterpret_cast<float4 *>(dst_hi + off) = make_float4(o[0], o[1], o[2], o[3]);
-            }
+                v[j4 * 4 + j] = in_range ? act_apply_compact(act, v[j4 * 4 + j] + bss[j]) : 0.0f;
         }
+        split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
+                      tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
+    }
+    tc::tmem_st_wait();
+}
+
+// accumulator -> (+bias, +skip, activation, * out_scale) -> bf16 planes (the next layer's input).
+// skip: add the row's current plane content times skip_unscale (cpp:269-279).  Returns nonzero if
+// a non-finite value was written.  Columns [N, round_up(N, 32)) are zero filled.
+__device__ __forceinline__ int epilogue_planes(uint32_t tmem_base, unsigned char *XP, int N,
+                                               const float *__restrict__ bias, int act, bool skip,
+                                               float skip_unscale, float out_scale)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = 32 * (warp & 3) + lane;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    const int npad = (N + 31) & ~31;
+    uint32_t bad = 0;
+    for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += 64) {
+        float v[32];
+        tc::tmem_ld32(tmem_base + TM_D + lane_base + (uint32_t)c0, v);
+#pragma unroll
+        for (int j8 = 0; j8 < 4; j8++) {
+            const int c = c0 + 8 * j8;
+            const bool in_range = c < N;   // N % 8 == 0
+            float o[8];
+            if (in_range) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + c));
+                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + c + 4));
+                const float bss[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float xs[8];
+                if (skip) load_row8(XP, row, c, xs);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    float t = v[8 * j8 + j] + bss[j];
+                    if (skip) t = fmaf(xs[j], skip_unscale, t);
+                    t = act_apply_compact(act, t) * out_scale;
+                    bad |= ((__float_as_uint(t) & 0x7f800000u) == 0x7f800000u) ? 1u : 0u;
+                    o[j] = t;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) o[j] = 0.0f;
+            }
+            store_row8(XP, row, c, o);
+        }
+    }
+    return (int)bad;
+}
+
+// head output: columns [0, n_true) of rows [0, n_rows) -> gout[gids[row]][col]
+__device__ __forceinline__ void epilogue_global(uint32_t tmem_base, int N, const float *__restrict__ bias,
+                                                int act, float *gout, const int *gids, int n_rows,
+                                                int ldg, int n_true)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = 32 * (warp & 3) + lane;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    const int npad = (N + 31) & ~31;
+    float *grow = row < n_rows ? gout + (size_t)gids[row] * ldg : nullptr;
+    for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += 64) {
+        float v[32];
+        tc::tmem_ld32(tmem_base + TM_D + lane_base + (uint32_t)c0, v);
+        if (grow == nullptr) continue;
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+            if (c0 + j < n_true) grow[c0 + j] = act_apply_compact(act, v[j] + __ldg(bias + c0 + j));
     }
 }
 
-// MLP head (cpp:454-530) for up to 128 pending graphs on the tensor cores: the pooled vectors
-// [128][head_in] are the A operand, read from the per-CTA pending buffer in 128-wide K chunks that
-// accumulate into the same TMEM tile; later head layers take their A operand from the previous
-// epilogue exactly like GIN's hidden layer.  All threads call this.
-__device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, uint32_t tmem_d,
-                                           unsigned char *RX, unsigned char *RHI, unsigned char *RLO,
-                                           const float *pending, int n_rows, uint32_t &done_cnt)
+// 4 consecutive features of a row from the planes (pooling), cc % 4 == 0
+__device__ __forceinline__ float4 load_row4(const unsigned char *XP, int row, int cc)
 {
-    const int tid = threadIdx.x;
+    const uint32_t off = tc::plane_chunk_offset(row, cc & ~7) + (uint32_t)(cc & 4) * 2u;
+    const uint2 h = *reinterpret_cast<const uint2 *>(XP + off);
+    const uint2 m = *reinterpret_cast<const uint2 *>(XP + tc::PLANE_BYTES + off);
+    const uint2 l = *reinterpret_cast<const uint2 *>(XP + 2 * tc::PLANE_BYTES + off);
+    float4 v;
+    v.x = (__uint_as_float(h.x << 16) + __uint_as_float(m.x << 16)) + __uint_as_float(l.x << 16);
+    v.y = (__uint_as_float(h.x & 0xffff0000u) + __uint_as_float(m.x & 0xffff0000u)) +
+          __uint_as_float(l.x & 0xffff0000u);
+    v.z = (__uint_as_float(h.y << 16) + __uint_as_float(m.y << 16)) + __uint_as_float(l.y << 16);
+    v.w = (__uint_as_float(h.y & 0xffff0000u) + __uint_as_float(m.y & 0xffff0000u)) +
+          __uint_as_float(l.y & 0xffff0000u);
+    return v;
+}
+
+// barrier over the 256 worker threads (the producer warp never joins it)
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+#define GNNB_WAIT_DONE()                                                            \
+    do {                                                                            \
+        if (warp_u == 0) tc::mbar_wait(&ms.bar_done, done_cnt & 1);                 \
+        done_cnt++;                                                                 \
+        worker_sync();                                                              \
+        tc::tc_fence_after();                                                       \
+    } while (0)
+#define GNNB_PUBLISH_TMEM()                                                         \
+    do {                                                                            \
+        tc::tc_fence_before();                                                      \
+        worker_sync();                                                              \
+    } while (0)
+
+// MLP head (cpp:454-530) for up to 128 pending graphs: the pooled vectors [128][head_in] go from the
+// per-CTA pending buffer (L2) to tensor memory in 128-wide K chunks that accumulate into the same
+// accumulator; later head layers take their A operand from the previous epilogue like GIN's hidden
+// layer.  All worker threads call this.
+__device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, uint32_t ring, int warp_u,
+                                           uint32_t &cons, uint32_t tmem_base, const float *pending,
+                                           int n_rows, uint32_t &done_cnt)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = 32 * (warp & 3) + lane;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     const int head_in = p.emb * p.num_pools;
     for (int j = 0; j < p.mlp_num_linear; j++) {
         const bool last = j == p.mlp_num_linear - 1;
         for (int c = 0; c < p.hchunks[j]; c++) {
             const TLinear &L = p.hl[j][c];
             if (j == 0) {  // A chunk: pending[:, 128c : 128c + K) -> (hi, lo), zero padded
-                const int kp = L.KA * tc::ATOM_K, q4 = kp / 4;
-                for (int idx = tid; idx < TM * q4; idx += NTHREADS) {
-                    const int r = idx / q4, cc = (idx - r * q4) * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < n_rows && c * 128 + cc < head_in)  // head_in % 4 == 0
-                        v = __ldcg(reinterpret_cast<const float4 *>(pending + (size_t)r * PLD + c * 128 + cc));
-                    const float4 h = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z),
-                                                 tc::tf32_hi(v.w));
-                    const uint32_t off = tc::canon_chunk_offset(r, cc, TM);
-                    *reinterpret_cast<float4 *>(RHI + off) = h;
-                    *reinterpret_cast<float4 *>(RLO + off) =
-                        make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                const int kp = L.KA * tc::ATOM_K;
+                const float *src = pending + (size_t)row * PLD + c * 128;
+                for (int c0 = (warp >> 2) * 32; c0 < kp; c0 += 64) {
+                    float v[32];
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; j4++) {
+                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row < n_rows && c * 128 + c0 + j4 * 4 < head_in)   // head_in % 4 == 0
+                            t = __ldcg(reinterpret_cast<const float4 *>(src + c0 + j4 * 4));
+                        v[j4 * 4] = t.x; v[j4 * 4 + 1] = t.y; v[j4 * 4 + 2] = t.z; v[j4 * 4 + 3] = t.w;
+                    }
+                    split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
+                                  tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
                 }
-                tc::fence_async_smem();
-                tc::tc_fence_before();
-                __syncthreads();
+                tc::tmem_st_wait();
+                GNNB_PUBLISH_TMEM();
             }
-            if (tid == 0) {
-                gemm_issue(ms, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, L, false, c > 0);
-                tc::mbar_wait(&ms.bar_done, done_cnt & 1);
-            }
-            done_cnt++;
-            __syncthreads();
-            tc::tc_fence_after();
+            if (warp_u == 0) gemm_issue(ms, ring, cons, tmem_base, L, c > 0);
+            GNNB_WAIT_DONE();
         }
         const TLinear &L0 = p.hl[j][0];
-        if (last)
-            epilogue(tmem_d, L0.N, L0.bias, p.out_act, nullptr, EPI_GLOBAL, nullptr, nullptr, p.out,
-                     ms.pend_gid, n_rows, p.mlp_out, p.head_n[j]);
-        else
-            epilogue(tmem_d, L0.N, L0.bias, p.mlp_act, nullptr, EPI_SPLIT, RHI, RLO);
-        tc::fence_async_smem();
-        tc::tc_fence_before();
-        __syncthreads();
+        if (last) {
+            epilogue_global(tmem_base, L0.N, L0.bias, p.out_act, p.out, ms.pend_gid, n_rows, p.mlp_out,
+                            p.head_n[j]);
+        } else {
+            epilogue_tmem(tmem_base, L0.N, L0.bias, p.mlp_act);
+        }
+        GNNB_PUBLISH_TMEM();
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
+__global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_constant__ TcParams p)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char *RX = base, *RHI = base + REGION, *RLO = base + 2 * REGION;
-    Misc &ms = *reinterpret_cast<Misc *>(base + 3 * REGION);
+    unsigned char *ADJ = base;
+    unsigned char *XP = ADJ + tc::PLANE_BYTES;
+    unsigned char *RING = XP + 3 * tc::PLANE_BYTES;
+    uint32_t *CNT = reinterpret_cast<uint32_t *>(RING + RING_BYTES);
+    Misc &ms = *reinterpret_cast<Misc *>(RING + RING_BYTES + CNT_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long t_prev = clock64();
 #define GNNB_PHASE(idx)                                                             \
@@ -332,26 +513,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
         t_prev = t_now;                                                             \
     }
 
-    if (warp == 0) tc::tmem_alloc(&ms.tmem_slot, 128);
+    if (warp == 0) tc::tmem_alloc(&ms.tmem_slot, TMEM_COLS);
     if (tid == 0) {
-        for (int i = 0; i < MAX_SLOTS; i++) {
+        for (int i = 0; i < NSLOT; i++) {
             tc::mbar_init(&ms.bar_full[i], 1);
             tc::mbar_init(&ms.bar_empty[i], 1);
-            ms.full_cnt[i] = 0;
-            ms.empty_cnt[i] = 0;
         }
         tc::mbar_init(&ms.bar_done, 1);
         tc::mbar_fence_init();
         ms.pend_n = 0;
+        ms.nonfinite = 0;
     }
+    for (int i = tid; i < CNT_BYTES / 16; i += CTA_THREADS)
+        reinterpret_cast<uint4 *>(CNT)[i] = make_uint4(0u, 0u, 0u, 0u);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_d = ms.tmem_slot;
-    uint32_t done_cnt = 0;
-    float *scratch = p.scratch + (size_t)blockIdx.x * TM * MAX_DIM;
+    // warp-uniform copies (broadcast from lane 0) of everything the issuing warp touches
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, ms.tmem_slot, 0);
+    const uint32_t adj_addr = __shfl_sync(0xffffffffu, tc::smem_u32(ADJ), 0);
+    const uint32_t xp_addr = adj_addr + tc::PLANE_BYTES;
+    const uint32_t ring_addr = adj_addr + 4 * tc::PLANE_BYTES;
+    uint32_t done_cnt = 0, cons = 0;
+
+    if (warp_u == NWARPS) {
+        // ------------------------------------------------------------ weight-producer warp
+        // mirrors the workers' control flow (which tiles run, when the head runs) from the tile
+        // geometry alone and streams the weight units of every linear in execution order.
+        // All CTAs stream the same weights at about the same time: each uses one of a few
+        // replicas at different addresses so that the reads spread over the L2 slices.
+        const bool leader = tc::elect_one();
+        const size_t copy_off = (size_t)(blockIdx.x % p.img_copies) * p.img_copy_bytes;
+        uint32_t prod = 0;
+        int pend = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int tg0 = __ldg(p.tile_bounds + tile), tg1 = __ldg(p.tile_bounds + tile + 1);
+            const int tng = tg1 - tg0;
+            const int64_t trows = __ldg(p.node_ptr + tg1) - __ldg(p.node_ptr + tg0);
+            if (tng <= 0 || trows > TM || tng > TM) continue;
+            for (int l = 0; l < p.num_layers; l++) {
+                produce_linear(ms, ring_addr, prod, p.l0[l], copy_off, leader);
+                if (p.conv_type != GNNB_CONV_GCN) produce_linear(ms, ring_addr, prod, p.l1[l], copy_off, leader);
+            }
+            pend += tng;
+            if (pend >= HEAD_G) {
+                for (int j = 0; j < p.mlp_num_linear; j++)
+                    for (int c = 0; c < p.hchunks[j]; c++)
+                        produce_linear(ms, ring_addr, prod, p.hl[j][c], copy_off, leader);
+                pend -= HEAD_G;
+            }
+        }
+        if (pend > 0)
+            for (int j = 0; j < p.mlp_num_linear; j++)
+                for (int c = 0; c < p.hchunks[j]; c++)
+                    produce_linear(ms, ring_addr, prod, p.hl[j][c], copy_off, leader);
+    } else {
+    // ---------------------------------------------------------------- worker warps
     float *pending = p.pending + (size_t)blockIdx.x * HEAD_G * PLD;
     const int emb = p.emb;
+    const int conv = p.conv_type;
+    const bool self_loop = conv == GNNB_CONV_GCN || conv == GNNB_CONV_GIN;
+    int bad_values = 0;
 
     // geometry of the first tile; later tiles are prefetched one iteration ahead
     int g0 = 0, g1 = 0;
@@ -369,61 +592,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
         const int ne = (int)(e1 - e0);
         const int cur_g0 = g0;
         const int64_t cur_row0 = row0, cur_e0 = e0;
-        // next tile's graph range: issue the loads now, consume them after the table build
         const int nxt = tile + gridDim.x;
         int ng0 = 0, ng1 = 0;
         if (nxt < p.n_tiles) {
             ng0 = __ldg(p.tile_bounds + nxt);
             ng1 = __ldg(p.tile_bounds + nxt + 1);
         }
-        const bool bad = rows > TM || ne > ECAP || ng > TM;
+        const bool bad = rows > TM || ng > TM;
         if (bad && tid == 0) atomicExch(p.error_flag, 1);
-        if (ng > 0 && !bad) {
-            __syncthreads();
+        const bool run = ng > 0 && !bad;
+        const int r_own = tid & (TM - 1), c_half = tid >> 7;   // staging role: (row, chunk parity)
+        const int kp0 = (p.in_dim + 31) & ~31;
+        if (run) {
+            worker_sync();   // the previous tile's pooling has finished reading the planes
             // ---------------------------------------------------------------- stage inputs
             for (int i = tid; i <= ng; i += NTHREADS) {
                 ms.grow[i] = (int)(__ldg(p.node_ptr + cur_g0 + i) - cur_row0);
                 ms.gedge[i] = (int)(__ldg(p.edge_ptr + cur_g0 + i) - cur_e0);
             }
-            {   // node features -> R_X (canonical layout), zero padded to whole K atoms; rows
-                // beyond the tile are zeroed too so no stale NaN/Inf ever enters an MMA
-                const int F = p.in_dim, Fp = (F + 31) & ~31;
-                const float *src = p.x + (size_t)cur_row0 * F;
-                // batches of 8 independent loads per thread so the global latency is paid once per
-                // batch, not once per element
-                for (int b0 = 0; b0 < TM * Fp; b0 += NTHREADS * 8) {
-                    float v[8];
+            if (tid < TM) ms.deg[tid] = 0;
+            // first two feature chunks of this thread's row: loads in flight during the edge pass
+            float xv[2][8];
+            {
+                const int F = p.in_dim;
+                const float *src = p.x + (size_t)(cur_row0 + r_own) * F;
 #pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int idx = b0 + q * NTHREADS + tid;
-                        const int r = idx / Fp, c = idx - r * Fp;
-                        v[q] = (r < rows && c < F) ? __ldg(src + (size_t)r * F + c) : 0.0f;
-                    }
+                for (int q = 0; q < 2; q++) {
+                    const int c = (c_half + 2 * q) * 8;
 #pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int idx = b0 + q * NTHREADS + tid;
-                        const int r = idx / Fp, c = idx - r * Fp;
-                        if (r < TM) *reinterpret_cast<float *>(RX + tc::canon_offset(r, c, TM)) = v[q];
-                    }
+                    for (int j = 0; j < 8; j++)
+                        xv[q][j] = (r_own < rows && c + j < F) ? __ldg(src + c + j) : 0.0f;
                 }
             }
-            int2 my_edge[ECAP / NTHREADS];
-            {   // edge list: issue the global loads before the barrier, localise after it
+            worker_sync();
+            {   // edges -> multiplicity counts + in-degrees (lib:1051-1083)
                 const int2 *coo = reinterpret_cast<const int2 *>(p.coo) + cur_e0;
-#pragma unroll
-                for (int q = 0; q < ECAP / NTHREADS; q++) {
-                    const int j = tid + q * NTHREADS;
-                    my_edge[q] = (j < ne) ? __ldg(coo + j) : make_int2(0, 0);
-                }
-            }
-            __syncthreads();
-            for (int i = tid; i < ng; i += NTHREADS)
-                for (int r = ms.grow[i]; r < ms.grow[i + 1]; r++) ms.rowg[r] = i;
-#pragma unroll
-            for (int q = 0; q < ECAP / NTHREADS; q++) {
-                const int j = tid + q * NTHREADS;
-                if (j < ne) {
-                    const int2 sd = my_edge[q];
+                for (int j = tid; j < ne; j += NTHREADS) {
+                    const int2 sd = __ldg(coo + j);
                     int lo = 0, hi = ng;
                     while (hi - lo > 1) {
                         const int mid = (lo + hi) >> 1;
@@ -432,49 +637,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
                     const int b = ms.grow[lo], n_i = ms.grow[lo + 1] - b;
                     if ((unsigned)sd.x >= (unsigned)n_i || (unsigned)sd.y >= (unsigned)n_i) {
                         atomicExch(p.error_flag, 2);
-                        ms.edges[j] = 0xffff;
                     } else {
-                        ms.edges[j] = (unsigned short)(((sd.y + b) << 8) | (sd.x + b));
+                        const int ls = sd.x + b, ld = sd.y + b;
+                        const uint32_t sh = 8u * (uint32_t)(ls & 3);
+                        const uint32_t old = atomicAdd(&CNT[ld * (TM / 4) + (ls >> 2)], 1u << sh);
+                        if (((old >> sh) & 0xffu) == 0xffu) atomicExch(p.error_flag, 1);
+                        atomicAdd(&ms.deg[ld], 1);
                     }
                 }
             }
-            __syncthreads();
+            worker_sync();
             GNNB_PHASE(0)
-            // ---------------------------------------------------------------- tables (lib:1051-1124)
-            int my_deg = 0;
-            if (tid < TM) {
-                if (tid < rows) {
-                    const int gi = ms.rowg[tid];
-                    for (int j = ms.gedge[gi]; j < ms.gedge[gi + 1]; j++)
-                        my_deg += ((ms.edges[j] >> 8) == tid) ? 1 : 0;
-                }
-                ms.deg[tid] = my_deg;
-                ms.dinv[tid] = 1.0f / sqrtf(1.0f + (float)my_deg);
-                int incl = my_deg;
+            // ---------------------------------------------------------------- ADJ, planes
+            for (int idx = tid; idx < TM * 8; idx += NTHREADS) {   // 16 sources per iteration
+                const int d = idx >> 3, s0 = (idx & 7) * 16;
+                uint4 *cp = reinterpret_cast<uint4 *>(CNT) + idx;
+                const uint4 cw = *cp;
+                *cp = make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
+                uint32_t o[8];
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += v;
+                for (int q = 0; q < 4; q++) {
+                    float f[4];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int s = s0 + 4 * q + b;
+                        f[b] = (float)((w4[q] >> (8 * b)) & 0xffu) +
+                               ((self_loop && s == d && d < rows) ? 1.0f : 0.0f);
+                    }
+                    o[2 * q] = __byte_perm(__float_as_uint(f[0]), __float_as_uint(f[1]), 0x7632);
+                    o[2 * q + 1] = __byte_perm(__float_as_uint(f[2]), __float_as_uint(f[3]), 0x7632);
                 }
-                if (lane == 31) ms.scan_tmp[warp] = incl;
-                ms.off[tid] = incl - my_deg;
+                *reinterpret_cast<uint4 *>(ADJ + tc::adj_chunk_offset(d, s0)) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4 *>(ADJ + tc::adj_chunk_offset(d, s0 + 8)) = make_uint4(o[4], o[5], o[6], o[7]);
             }
-            __syncthreads();
-            if (tid < TM) {
-                int b = 0;
-                for (int w = 0; w < warp; w++) b += ms.scan_tmp[w];
-                const int o = ms.off[tid] + b;
-                ms.off[tid] = o;
-                if (tid < rows) {
-                    const int gi = ms.rowg[tid];
-                    int pos = o;
-                    for (int j = ms.gedge[gi]; j < ms.gedge[gi + 1]; j++) {
-                        const unsigned short ed = ms.edges[j];
-                        if ((ed >> 8) == tid) ms.nbr[pos++] = (unsigned char)(ed & 0xff);
+            {   // node features -> planes (GCN: pre-scaled by dinv), zero padded to whole K atoms
+                const int F = p.in_dim;
+                const float sc = conv == GNNB_CONV_GCN ? 1.0f / sqrtf(1.0f + (float)ms.deg[r_own]) : 1.0f;
+                const float *src = p.x + (size_t)(cur_row0 + r_own) * F;
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int c = (c_half + 2 * q) * 8;
+                    if (c < kp0) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            o[j] = xv[q][j] * sc;
+                            bad_values |= ((__float_as_uint(o[j]) & 0x7f800000u) == 0x7f800000u) ? 1 : 0;
+                        }
+                        store_row8(XP, r_own, c, o);
                     }
                 }
+                for (int c = (c_half + 4) * 8; c < kp0; c += 16) {   // in_dim > 32
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        o[j] = ((r_own < rows && c + j < F) ? __ldg(src + c + j) : 0.0f) * sc;
+                        bad_values |= ((__float_as_uint(o[j]) & 0x7f800000u) == 0x7f800000u) ? 1 : 0;
+                    }
+                    store_row8(XP, r_own, c, o);
+                }
             }
-            __syncthreads();
+            tc::fence_async_smem();
+            GNNB_PUBLISH_TMEM();
             GNNB_PHASE(1)
         }
         // second half of the next tile's geometry (the bounds have arrived by now)
@@ -483,126 +708,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
             row0 = __ldg(p.node_ptr + ng0); row1 = __ldg(p.node_ptr + ng1);
             e0 = __ldg(p.edge_ptr + ng0); e1 = __ldg(p.edge_ptr + ng1);
         }
-        if (ng <= 0 || bad) continue;
+        if (!run) continue;
+
+        const int my_deg = ms.deg[32 * (warp & 3) + lane];   // row owned in the thread-per-row phases
+        const float my_dinv = 1.0f / sqrtf(1.0f + (float)my_deg);
+        const int rows_u = __shfl_sync(0xffffffffu, rows, 0);
 
         // -------------------------------------------------------------------- conv layers
         for (int l = 0; l < p.num_layers; l++) {
             const int fi = p.fi[l];
             const int kp = (fi + 31) & ~31;
-            const bool do_skip = p.skip && l != 0 && l != p.num_layers - 1;  // cpp:269-279
-            // aggregate X -> (hi, lo) A operand: a warp works on AGG_R rows at a time (independent
-            // gather chains), lanes across K (float4 each)
-            const int c = lane * 4;
-            if (c < kp) {
-                for (int rb = warp * AGG_R; rb < TM; rb += NWARPS * AGG_R) {
-                    int d[AGG_R], o[AGG_R];
-                    float4 acc[AGG_R];
-                    int kmax = 0;
-#pragma unroll
-                    for (int j = 0; j < AGG_R; j++) {
-                        const int r = rb + j;
-                        d[j] = r < rows ? ms.deg[r] : 0;
-                        o[j] = ms.off[r];
-                        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        kmax = max(kmax, d[j]);
-                    }
-                    // branch-free body: all AGG_R gather chains (index -> row -> add) issue back to
-                    // back; rows that have run out of neighbors read slot 0 and select 0
-                    const bool gcn = p.conv_type == GNNB_CONV_GCN;
-                    for (int k = 0; k < kmax; k++) {
-                        int u[AGG_R];
-                        float4 v[AGG_R];
-                        float s[AGG_R];
-#pragma unroll
-                        for (int j = 0; j < AGG_R; j++) u[j] = ms.nbr[(k < d[j]) ? o[j] + k : 0];
-#pragma unroll
-                        for (int j = 0; j < AGG_R; j++) {
-                            v[j] = *reinterpret_cast<const float4 *>(
-                                RX + tc::canon_chunk_offset(u[j], c, TM));
-                            s[j] = gcn ? ms.dinv[u[j]] : 1.0f;
-                        }
-#pragma unroll
-                        for (int j = 0; j < AGG_R; j++) {
-                            const bool on = k < d[j];
-                            const float4 t = make_float4(on ? v[j].x : 0.0f, on ? v[j].y : 0.0f,
-                                                         on ? v[j].z : 0.0f, on ? v[j].w : 0.0f);
-                            if (gcn) {
-                                acc[j].x = fmaf(t.x, s[j], acc[j].x); acc[j].y = fmaf(t.y, s[j], acc[j].y);
-                                acc[j].z = fmaf(t.z, s[j], acc[j].z); acc[j].w = fmaf(t.w, s[j], acc[j].w);
-                            } else {
-                                acc[j].x += t.x; acc[j].y += t.y; acc[j].z += t.z; acc[j].w += t.w;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < AGG_R; j++) {
-                        const int r = rb + j;
-                        float4 a = acc[j];
-                        if (r < rows) {
-                            const float4 xs = *reinterpret_cast<const float4 *>(
-                                RX + tc::canon_chunk_offset(r, c, TM));
-                            if (p.conv_type == GNNB_CONV_GCN) {  // lib:1249-1278, factorised
-                                const float dv = ms.dinv[r], ss = dv * dv;
-                                a.x = fmaf(xs.x, ss, a.x * dv); a.y = fmaf(xs.y, ss, a.y * dv);
-                                a.z = fmaf(xs.z, ss, a.z * dv); a.w = fmaf(xs.w, ss, a.w * dv);
-                            } else {  // GIN, lib:1519-1529
-                                const float s = 1.0f + p.gin_eps;
-                                a.x += xs.x * s; a.y += xs.y * s; a.z += xs.z * s; a.w += xs.w * s;
-                            }
-                        }
-                        const float4 h = make_float4(tc::tf32_hi(a.x), tc::tf32_hi(a.y),
-                                                     tc::tf32_hi(a.z), tc::tf32_hi(a.w));
-                        const uint32_t off = tc::canon_chunk_offset(r, c, TM);
-                        *reinterpret_cast<float4 *>(RHI + off) = h;
-                        *reinterpret_cast<float4 *>(RLO + off) =
-                            make_float4(a.x - h.x, a.y - h.y, a.z - h.z, a.w - h.w);
-                    }
-                }
+            const bool last_layer = l == p.num_layers - 1;
+            const bool do_skip = p.skip && l != 0 && !last_layer;  // cpp:269-279
+            if (warp_u == 0) agg_issue(ms, tmem_base + TM_D, adj_addr, xp_addr, kp, rows_u);
+            GNNB_WAIT_DONE();
+            GNNB_PHASE(2)
+            if (conv == GNNB_CONV_GCN) cvt_agg(tmem_base, XP, kp, my_dinv, false, 1.0f, 0.0f);
+            else if (conv == GNNB_CONV_GIN) cvt_agg(tmem_base, XP, kp, 1.0f, false, 1.0f, p.gin_eps);
+            else cvt_agg(tmem_base, XP, kp, my_deg > 0 ? 1.0f : 0.0f, my_deg > 0, (float)my_deg, 0.0f);
+            GNNB_PUBLISH_TMEM();
+            GNNB_PHASE(3)
+            if (warp_u == 0) gemm_issue(ms, ring_addr, cons, tmem_base, p.l0[l], false);
+            GNNB_WAIT_DONE();
+            GNNB_PHASE(7)
+            if (conv == GNNB_CONV_GIN) {
+                epilogue_tmem(tmem_base, p.l0[l].N, p.l0[l].bias, GNNB_ACT_RELU);
+                GNNB_PUBLISH_TMEM();
+                GNNB_PHASE(3)
+                if (warp_u == 0) gemm_issue(ms, ring_addr, cons, tmem_base, p.l1[l], false);
+                GNNB_WAIT_DONE();
+                GNNB_PHASE(7)
+            } else if (conv == GNNB_CONV_SAGE) {
+                cvt_self(tmem_base, XP, kp);
+                GNNB_PUBLISH_TMEM();
+                GNNB_PHASE(3)
+                if (warp_u == 0) gemm_issue(ms, ring_addr, cons, tmem_base, p.l1[l], true);
+                GNNB_WAIT_DONE();
+                GNNB_PHASE(7)
             }
-            GNNB_PHASE(2)   // this warp's own aggregation time (no barrier yet)
-            if (do_skip) {  // park X: R_X is about to become the weight ring
-                for (int idx = tid; idx < TM * (kp / 4); idx += NTHREADS) {
-                    const int r = idx / (kp / 4), cc = (idx % (kp / 4)) * 4;
-                    const float4 v = *reinterpret_cast<const float4 *>(
-                        RX + tc::canon_chunk_offset(r, cc, TM));
-                    *reinterpret_cast<float4 *>(scratch + (size_t)r * MAX_DIM + cc) = v;
-                }
+            {
+                const TLinear &Lb = conv == GNNB_CONV_GIN ? p.l1[l] : p.l0[l];
+                const bool gcn = conv == GNNB_CONV_GCN;
+                bad_values |= epilogue_planes(tmem_base, XP, Lb.N, Lb.bias, p.gnn_act, do_skip,
+                                              gcn ? sqrtf(1.0f + (float)my_deg) : 1.0f,
+                                              (gcn && !last_layer) ? my_dinv : 1.0f);
             }
             tc::fence_async_smem();
-            tc::tc_fence_before();
-            __syncthreads();
-            GNNB_PHASE(6)   // skip spill + proxy fence + barrier (waiting for the slowest warp)
-            const float *skip = do_skip ? scratch : nullptr;
-            if (tid == 0) {
-                gemm_issue(ms, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, p.l0[l], false);
-                tc::mbar_wait(&ms.bar_done, done_cnt & 1);  // one poller; the rest park on bar.sync
-            }
-            done_cnt++;
-            __syncthreads();
-            tc::tc_fence_after();
-            GNNB_PHASE(7)   // weight copies + MMAs until the accumulator is ready
-            if (p.conv_type == GNNB_CONV_GCN) {
-                epilogue(tmem_d, p.l0[l].N, p.l0[l].bias, p.gnn_act, skip, EPI_X, RX, nullptr);
-            } else {
-                // the ring is idle while the epilogue runs: start fetching the second GEMM's weights
-                if (tid == 0) gemm_prefetch(ms, RX, p.l1[l]);
-                epilogue(tmem_d, p.l0[l].N, p.l0[l].bias, GNNB_ACT_RELU, nullptr, EPI_SPLIT, RHI, RLO);
-                tc::fence_async_smem();
-                tc::tc_fence_before();
-                __syncthreads();
-                GNNB_PHASE(3)
-                if (tid == 0) {
-                    gemm_issue(ms, tmem_d, tc::smem_u32(RHI), tc::smem_u32(RLO), RX, p.l1[l], true);
-                    tc::mbar_wait(&ms.bar_done, done_cnt & 1);
-                }
-                done_cnt++;
-                __syncthreads();
-                tc::tc_fence_after();
-                GNNB_PHASE(7)
-                epilogue(tmem_d, p.l1[l].N, p.l1[l].bias, p.gnn_act, skip, EPI_X, RX, nullptr);
-            }
-            tc::tc_fence_before();
-            __syncthreads();
+            GNNB_PUBLISH_TMEM();
             GNNB_PHASE(3)
         }
 
@@ -616,8 +768,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
                 for (int cc = lane * 4; cc < emb; cc += 128) {   // emb % 16 == 0
                     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), mx = sum;
                     for (int r = r0; r < r1; r++) {
-                        const float4 v = *reinterpret_cast<const float4 *>(
-                            RX + tc::canon_chunk_offset(r, cc, TM));
+                        const float4 v = load_row4(XP, r, cc);
                         sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
                         const bool first = r == r0;                       // lib:748-759
                         mx.x = (first || v.x > mx.x) ? v.x : mx.x; mx.y = (first || v.y > mx.y) ? v.y : mx.y;
@@ -636,36 +787,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_tc_kernel(const TcParams p)
                 }
                 if (lane == 0) ms.pend_gid[base_n + gi] = cur_g0 + gdone + gi;
             }
-            __syncthreads();
+            worker_sync();
             if (tid == 0) ms.pend_n = base_n + cnt;
             gdone += cnt;
             GNNB_PHASE(4)
             if (base_n + cnt == HEAD_G) {
-                head_flush(p, ms, tmem_d, RX, RHI, RLO, pending, HEAD_G, done_cnt);
+                head_flush(p, ms, ring_addr, warp_u, cons, tmem_base, pending, HEAD_G, done_cnt);
                 if (tid == 0) ms.pend_n = 0;
                 GNNB_PHASE(5)
             }
-            __syncthreads();
+            worker_sync();
         }
     }
     // graphs still waiting for the head
-    __syncthreads();
+    worker_sync();
     {
         const int left = ms.pend_n;
-        if (left > 0) head_flush(p, ms, tmem_d, RX, RHI, RLO, pending, left, done_cnt);
+        if (left > 0) head_flush(p, ms, ring_addr, warp_u, cons, tmem_base, pending, left, done_cnt);
     }
     GNNB_PHASE(5)
 #undef GNNB_PHASE
+    if (bad_values) atomicExch(p.error_flag, 3);
+    }   // worker warps
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_d, 128);
+    if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 }  // namespace
 
 struct TcPlan {
     TcParams params{};
-    DeviceBuf images, bounds, flag, scratch, pending, timing;
+    DeviceBuf images, bounds, flag, pending, timing;
     size_t smem_bytes = 0;
 };
 
@@ -674,11 +827,12 @@ int fused_tc_prepare(gnnb_model *m)
     m->fused_tc = nullptr;
     const gnnb_model_desc &d = m->d;
     if (getenv("GNNB_DISABLE_TC") != nullptr) return GNNB_OK;
-    const bool conv_ok = d.conv_type == GNNB_CONV_GCN || d.conv_type == GNNB_CONV_GIN;
+    const bool conv_ok = d.conv_type == GNNB_CONV_GCN || d.conv_type == GNNB_CONV_GIN ||
+                         d.conv_type == GNNB_CONV_SAGE;
     const int head_in = m->emb_dim() * d.num_pools;
-    bool dims_ok = d.num_layers >= 1 && d.num_layers <= MAX_LAYERS && d.mlp_num_linear <= MAX_HEAD &&
-                   d.in_dim <= MAX_DIM && d.mlp_hidden <= MAX_DIM && d.mlp_out <= MAX_DIM &&
-                   head_in <= 512;
+    bool dims_ok = d.num_layers >= 1 && d.num_layers <= MAX_LAYERS && d.mlp_num_linear >= 1 &&
+                   d.mlp_num_linear <= MAX_HEAD && d.in_dim <= MAX_DIM && d.mlp_hidden <= MAX_DIM &&
+                   d.mlp_out <= MAX_DIM && head_in <= 512;
     for (int k = 0; k < d.num_layers && dims_ok; k++) {
         int fi, fo;
         m->layer_dims(k, &fi, &fo);
@@ -706,12 +860,18 @@ int fused_tc_prepare(gnnb_model *m)
             pend.push_back({img.size(), fi, fo});
             build_weight_image(m->params[idx + 1].host.data(), fo, fo, fi, fi, 0, img);
             idx += 2;
-        } else {                              // [w0, b0, w1, b1]
+        } else if (d.conv_type == GNNB_CONV_GIN) {  // [w0, b0, w1, b1]
             pend.push_back({img.size(), fi, fo});
             build_weight_image(m->params[idx].host.data(), fo, fo, fi, fi, 0, img);
             pend.push_back({img.size(), fo, fo});
             build_weight_image(m->params[idx + 2].host.data(), fo, fo, fo, fo, 0, img);
             idx += 4;
+        } else {                                    // SAGE: [lin_l.weight, lin_l.bias, lin_r.weight]
+            pend.push_back({img.size(), fi, fo});
+            build_weight_image(m->params[idx].host.data(), fo, fo, fi, fi, 0, img);
+            pend.push_back({img.size(), fi, fo});
+            build_weight_image(m->params[idx + 2].host.data(), fo, fo, fi, fi, 0, img);
+            idx += 3;
         }
     }
     // MLP head: N padded to a multiple of 16, K cut into 128-wide chunks, bias zero padded
@@ -739,14 +899,21 @@ int fused_tc_prepare(gnnb_model *m)
             in = out;
         }
     }
-    int rc = plan->images.ensure(img.size() * sizeof(float));
-    if (rc == GNNB_OK) {
-        cudaError_t e = cudaMemcpy(plan->images.ptr, img.data(), img.size() * sizeof(float),
-                                   cudaMemcpyHostToDevice);
+    int copies = 8;
+    if (const char *e = getenv("GNNB_TC_WEIGHT_COPIES")) copies = std::max(1, std::min(64, atoi(e)));
+    // replica stride: the image size rounded up to 256 B plus an odd number of 256-byte lines so
+    // that equal offsets of different replicas fall on different L2 slices
+    const size_t img_bytes = img.size() * sizeof(float);
+    const size_t copy_bytes = (img_bytes + 255) / 256 * 256 + 256 * 37;
+    int rc = plan->images.ensure(copy_bytes * (size_t)copies);
+    for (int c = 0; c < copies && rc == GNNB_OK; c++) {
+        cudaError_t e = cudaMemcpy(static_cast<unsigned char *>(plan->images.ptr) + c * copy_bytes,
+                                   img.data(), img_bytes, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) rc = cuda_fail(e, "upload weight images", __FILE__, __LINE__);
     }
+    p.img_copy_bytes = copy_bytes;
+    p.img_copies = copies;
     if (rc == GNNB_OK) rc = plan->flag.ensure(sizeof(int));
-    if (rc == GNNB_OK) rc = plan->scratch.ensure((size_t)kNumSMs * TM * MAX_DIM * sizeof(float));
     if (rc == GNNB_OK) rc = plan->pending.ensure((size_t)kNumSMs * HEAD_G * PLD * sizeof(float));
     if (rc == GNNB_OK && getenv("GNNB_FUSED_TIMING") != nullptr) {
         rc = plan->timing.ensure(16 * sizeof(unsigned long long));
@@ -766,6 +933,7 @@ int fused_tc_prepare(gnnb_model *m)
         };
         p.l0[k] = mk(pend[pi++], L.a.bias);
         if (d.conv_type == GNNB_CONV_GIN) p.l1[k] = mk(pend[pi++], L.b.bias);
+        else if (d.conv_type == GNNB_CONV_SAGE) p.l1[k] = mk(pend[pi++], nullptr);
     }
     for (int j = 0; j < d.mlp_num_linear; j++) {
         const HeadPending &h = hpend[j];
@@ -778,7 +946,7 @@ int fused_tc_prepare(gnnb_model *m)
             p.hl[j][c] = t;
         }
     }
-    plan->smem_bytes = 1024 + 3 * (size_t)REGION + sizeof(Misc);
+    plan->smem_bytes = 1024 + (size_t)4 * tc::PLANE_BYTES + RING_BYTES + CNT_BYTES + sizeof(Misc);
     cudaError_t e = cudaFuncSetAttribute(fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)plan->smem_bytes);
     if (e != cudaSuccess) {
@@ -794,7 +962,7 @@ void fused_tc_release(gnnb_model *m)
     TcPlan *plan = m->fused_tc;
     if (plan) {
         plan->images.release(); plan->bounds.release(); plan->flag.release();
-        plan->scratch.release(); plan->pending.release(); plan->timing.release();
+        plan->pending.release(); plan->timing.release();
         delete plan;
         m->fused_tc = nullptr;
     }
@@ -802,8 +970,8 @@ void fused_tc_release(gnnb_model *m)
 
 bool fused_tc_supports(const gnnb_model *m, int max_nodes_in_batch, int max_edges_in_batch)
 {
-    return m->fused_tc != nullptr && max_nodes_in_batch <= MAX_NODES_PER_GRAPH &&
-           max_edges_in_batch <= ECAP / 4;
+    (void)max_edges_in_batch;   // edges stream through the multiplicity counters: no capacity limit
+    return m->fused_tc != nullptr && max_nodes_in_batch <= MAX_NODES_PER_GRAPH;
 }
 
 int fused_tc_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_t *node_ptr,
@@ -828,11 +996,10 @@ int fused_tc_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_
     p.x = x; p.coo = coo; p.node_ptr = node_ptr; p.edge_ptr = edge_ptr; p.n_graphs = n_graphs;
     p.out = out; p.tile_bounds = plan->bounds.as<int32_t>(); p.n_tiles = n_tiles;
     p.error_flag = plan->flag.as<int>();
-    p.scratch = plan->scratch.as<float>();
     p.pending = plan->pending.as<float>();
     p.timing = plan->timing.as<unsigned long long>();
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    fused_tc_kernel<<<grid, NTHREADS, plan->smem_bytes, s>>>(p);
+    fused_tc_kernel<<<grid, CTA_THREADS, plan->smem_bytes, s>>>(p);
     GNNB_CUDA(cudaGetLastError());
     if (launches) *launches += 2;
     return GNNB_OK;
@@ -848,13 +1015,14 @@ int fused_tc_status(gnnb_model *m, int *status)
         unsigned long long t[16];
         GNNB_CUDA(cudaMemcpy(t, plan->timing.ptr, sizeof(t), cudaMemcpyDeviceToHost));
         GNNB_CUDA(cudaMemset(plan->timing.ptr, 0, sizeof(t)));
-        const char *names[8] = {"stage", "tables", "aggregate", "epilogue", "pool", "head",
-                                "agg-barrier", "mma"};
+        const char *names[8] = {"stage", "adj+planes", "agg-mma", "convert/epilogue", "pool", "head",
+                                "-", "transform-mma"};
         unsigned long long tot = 0;
         for (int i = 0; i < 8; i++) tot += t[i];
         fprintf(stderr, "[gnnb fused-tc phases]");
         for (int i = 0; i < 8; i++)
-            fprintf(stderr, " %s %.1f%%", names[i], tot ? 100.0 * (double)t[i] / (double)tot : 0.0);
+            if (i != 6)
+                fprintf(stderr, " %s %.1f%%", names[i], tot ? 100.0 * (double)t[i] / (double)tot : 0.0);
         fprintf(stderr, " (total %.3g cycles over all CTAs)\n", (double)tot);
     }
     return GNNB_OK;

@@ -391,6 +391,12 @@ extern "C" int gnnb_model_synchronize(gnnb_model_t *m)
             set_error("edge_list holds a node index outside its graph");
             return GNNB_ERR_INVALID;
         }
+        if (status == 3) {
+            set_error("fused kernel: non-finite activations (Inf/NaN) cannot be kept apart between "
+                      "the graphs of a tile; use gnnb_model_run_batch, which re-runs such batches "
+                      "on the layerwise path");
+            return GNNB_ERR_INVALID;
+        }
     }
     return GNNB_OK;
 }
@@ -728,9 +734,12 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
             set_error("edge_list holds a node index outside its graph");
             return GNNB_ERR_INVALID;
         }
-        if (status == 1) {  // a tile overflowed its edge capacity: redo the batch layerwise
+        if (status == 1 || status == 3) {  // a tile overflowed its capacity, or non-finite
+                                            // activations appeared: redo the batch layerwise
             if (m->path == GNNB_PATH_FUSED) {
-                set_error("fused path requested but a tile exceeded its edge capacity");
+                set_error(status == 1 ? "fused path requested but a tile exceeded its capacity"
+                                      : "fused path requested but the batch produced non-finite "
+                                        "activations (graphs of a tile would contaminate each other)");
                 return GNNB_ERR_INVALID;
             }
             m->last_path = GNNB_PATH_LAYERWISE;

@@ -97,6 +97,16 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
         : "memory");
 }
 
+__device__ __forceinline__ void bulk_g2s_addr(uint32_t smem_dst_addr, const void *gsrc, uint32_t bytes,
+                                              uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+            "r"(smem_dst_addr),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_async_smem()
 {
@@ -304,6 +314,20 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32])
         "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])),
         "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
         : "memory");
+}
+// one lane of a converged warp (warp-uniform code keeps descriptors in uniform registers; only the
+// tcgen05 / bulk-copy instruction itself is predicated on the elected lane)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tmem_st_wait()
 {

@@ -273,6 +273,175 @@ __global__ void __launch_bounds__(256, 1) tc_agg_test_kernel(const float *__rest
     if (warp == 0) tc::tmem_dealloc(tmem_d, 512);
 }
 
+
+// Third diagnostic: issue-to-completion cycles of back-to-back tcgen05.mma instructions of the
+// flavours the fused kernel uses (M = 128, N columns): 0 tf32 SS, 1 tf32 TS (A in tensor memory),
+// 2 bf16 SS K-major, 3 bf16 SS with MN-major B.  One CTA, zeroed operands.
+__global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int flavour_in, int N, int reps, int nacc,
+                                                             long long *cycles)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar_done;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    int flavour = flavour_in;
+    unsigned char *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    for (int i = tid; i < 3 * tc::PLANE_BYTES / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(base)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    if (tid == 0) { tc::mbar_init(&bar_done, 1); tc::mbar_fence_init(); }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+    {   // zero the A region of tensor memory (columns 128..383)
+        float z[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) z[j] = 0.0f;
+        for (int c = 128; c < 384; c += 32) tc::tmem_st32(tmem_d + ((uint32_t)(32 * warp) << 16) + c, z);
+        tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const bool uniform = flavour >= 10;
+    if (uniform) flavour -= 10;
+    // broadcast from lane 0 so that the compiler treats the values as warp-uniform (uniform
+    // registers, no per-instruction R2UR)
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
+    const uint32_t a_u = __shfl_sync(0xffffffffu, tc::smem_u32(base), 0);
+    if (uniform ? warp_u == 0 : tid == 0) {
+        const uint32_t tmem_d = tmem_u;
+        const uint32_t a = a_u, b = a + tc::PLANE_BYTES;
+        const uint32_t id_tf = tc::make_idesc_tf32(TM, N);
+        const uint32_t id_bk = tc::make_idesc_bf16(TM, N, 0), id_bm = tc::make_idesc_bf16(TM, N, 1);
+        const long long t0 = clock64();
+        if (!uniform) {
+            for (int r = 0; r < reps; r++) {
+                const uint32_t ko = (uint32_t)(r & 3) * 32u;
+                const uint32_t tmem_d = tmem_u + (uint32_t)(r % nacc) * (uint32_t)N;
+                if (flavour == 0)
+                    tc::mma_tf32(tmem_d, tc::make_desc(a + ko), tc::make_desc(b + ko), id_tf, r ? 1u : 0u);
+                else if (flavour == 1)
+                    tc::mma_tf32_ts(tmem_d, tmem_u + 256 + (uint32_t)(r & 15) * 8u, tc::make_desc(b + ko), id_tf,
+                                    r ? 1u : 0u);
+                else if (flavour == 2)
+                    tc::mma_bf16(tmem_d, tc::make_desc(a + ko), tc::make_desc(b + ko), id_bk, r ? 1u : 0u);
+                else
+                    tc::mma_bf16(tmem_d, tc::make_desc(a + ko),
+                                 tc::make_desc_mn(b + (uint32_t)(r & 7) * 2048u, tc::PLANE_BLOCK_BYTES, 1024u),
+                                 id_bm, r ? 1u : 0u);
+            }
+        } else {   // the whole warp runs the loop, one elected lane issues
+            for (int r0 = 0; r0 < reps; r0 += 4) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int r = r0 + k;
+                    const uint32_t ko = (uint32_t)k * 32u;
+                    if (flavour == 0) {
+                        const uint64_t da = tc::make_desc(a + ko), db = tc::make_desc(b + ko);
+                        if (tc::elect_one()) tc::mma_tf32(tmem_d, da, db, id_tf, r ? 1u : 0u);
+                    } else if (flavour == 1) {
+                        const uint64_t db = tc::make_desc(b + ko);
+                        const uint32_t ta = tmem_d + 128 + (uint32_t)((r0 & 12) + k) * 8u;
+                        if (tc::elect_one()) tc::mma_tf32_ts(tmem_d, ta, db, id_tf, r ? 1u : 0u);
+                    } else if (flavour == 2) {
+                        const uint64_t da = tc::make_desc(a + ko), db = tc::make_desc(b + ko);
+                        if (tc::elect_one()) tc::mma_bf16(tmem_d, da, db, id_bk, r ? 1u : 0u);
+                    } else {
+                        const uint64_t da = tc::make_desc(a + ko);
+                        const uint64_t db = tc::make_desc_mn(b + (uint32_t)((r0 & 4) + k) * 2048u,
+                                                             tc::PLANE_BLOCK_BYTES, 1024u);
+                        if (tc::elect_one()) tc::mma_bf16(tmem_d, da, db, id_bm, r ? 1u : 0u);
+                    }
+                }
+            }
+        }
+        const long long t1 = clock64();
+        if (!uniform) tc::mma_commit(&bar_done);          // (elect.sync needs the whole warp)
+        else if (tc::elect_one()) tc::mma_commit(&bar_done);
+        tc::mbar_wait(&bar_done, 0);
+        const long long t2 = clock64();
+        if (tid == 0) {
+            cycles[0] = t1 - t0;
+            cycles[1] = t2 - t0;
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_d, 512);
+}
+
+
+// Lean issue loop: the whole of warp 0 runs warp-uniform code (values broadcast from lane 0 so
+// that the compiler keeps them in uniform registers), 16 MMAs unrolled per iteration with
+// compile-time offsets, one elected lane executes the instruction.
+template <int FLAVOUR>
+__global__ void __launch_bounds__(128, 1) tc_mma_rate_lean_kernel(int N, int reps, long long *cycles)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar_done;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    unsigned char *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    for (int i = tid; i < 3 * tc::PLANE_BYTES / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(base)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    if (tid == 0) { tc::mbar_init(&bar_done, 1); tc::mbar_fence_init(); }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_slot, 0);
+    {
+        float z[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) z[j] = 0.0f;
+        for (int c = 128; c < 384; c += 32) tc::tmem_st32(tmem_d + ((uint32_t)(32 * warp) << 16) + c, z);
+        tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (warp == 0) {
+        const uint32_t a = __shfl_sync(0xffffffffu, tc::smem_u32(base), 0), b = a + tc::PLANE_BYTES;
+        const uint32_t idesc = FLAVOUR <= 1 ? tc::make_idesc_tf32(TM, N) : tc::make_idesc_bf16(TM, N, FLAVOUR == 3);
+        const uint64_t da0 = tc::make_desc(a), db0 = tc::make_desc(b);
+        const uint64_t dm0 = tc::make_desc_mn(b, tc::PLANE_BLOCK_BYTES, 1024u);
+        const bool leader = tc::elect_one();
+        const long long t0 = clock64();
+        for (int r0 = 0; r0 < reps; r0 += 16) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const uint32_t acc = (r0 + k) ? 1u : 0u;
+                if (FLAVOUR == 0) {
+                    if (leader) tc::mma_tf32(tmem_d, da0 + (uint64_t)((k & 3) * 2), db0 + (uint64_t)((k & 3) * 2), idesc, acc);
+                } else if (FLAVOUR == 1) {
+                    if (leader) tc::mma_tf32_ts(tmem_d, tmem_d + 128 + k * 8, db0 + (uint64_t)((k & 3) * 2), idesc, acc);
+                } else if (FLAVOUR == 2) {
+                    if (leader) tc::mma_bf16(tmem_d, da0 + (uint64_t)((k & 3) * 2), db0 + (uint64_t)((k & 3) * 2), idesc, acc);
+                } else {
+                    if (leader) tc::mma_bf16(tmem_d, da0 + (uint64_t)((k & 3) * 2), dm0 + (uint64_t)((k & 7) * 128), idesc, acc);
+                }
+            }
+        }
+        const long long t1 = clock64();
+        if (leader) tc::mma_commit(&bar_done);
+        tc::mbar_wait(&bar_done, 0);
+        const long long t2 = clock64();
+        if (tid == 0) {
+            cycles[0] = t1 - t0;
+            cycles[1] = t2 - t0;
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_d, 512);
+}
+
 }  // namespace
 }  // namespace gnnb
 
@@ -332,5 +501,41 @@ extern "C" int gnnb_debug_tc_agg_gemm(const float *Adj, const float *X, const fl
     GNNB_CUDA(cudaMemcpy(C, dC, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost));
     if (agg) GNNB_CUDA(cudaMemcpy(agg, dAgg, sizeof(float) * 128 * F, cudaMemcpyDeviceToHost));
     cudaFree(dAdj); cudaFree(dX); cudaFree(dB); cudaFree(dC); cudaFree(dAgg);
+    return GNNB_OK;
+}
+
+// Diagnostic: cycles[0] = cycles to ISSUE `reps` back-to-back MMAs, cycles[1] = until they completed.
+extern "C" int gnnb_debug_tc_mma_rate(int flavour, int N, int reps, long long *cycles)
+{
+    const int nacc = flavour / 100 > 0 ? flavour / 100 : 1;   // hundreds digit: accumulators to alternate
+    flavour %= 100;
+    GNNB_REQUIRE(cycles != nullptr && flavour >= 0 && flavour <= 23 && N >= 16 && N <= 256 && N % 16 == 0 &&
+                 reps >= 1, "bad argument");
+    long long *d = nullptr;
+    GNNB_CUDA(cudaMalloc(&d, 2 * sizeof(long long)));
+    const size_t smem = 1024 + (size_t)3 * tc::PLANE_BYTES;
+    GNNB_CUDA(cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    if (flavour >= 20) {
+        switch (flavour - 20) {
+        case 0:
+            GNNB_CUDA(cudaFuncSetAttribute(tc_mma_rate_lean_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tc_mma_rate_lean_kernel<0><<<1, 128, smem>>>(N, reps, d); break;
+        case 1:
+            GNNB_CUDA(cudaFuncSetAttribute(tc_mma_rate_lean_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tc_mma_rate_lean_kernel<1><<<1, 128, smem>>>(N, reps, d); break;
+        case 2:
+            GNNB_CUDA(cudaFuncSetAttribute(tc_mma_rate_lean_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tc_mma_rate_lean_kernel<2><<<1, 128, smem>>>(N, reps, d); break;
+        default:
+            GNNB_CUDA(cudaFuncSetAttribute(tc_mma_rate_lean_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tc_mma_rate_lean_kernel<3><<<1, 128, smem>>>(N, reps, d); break;
+        }
+    } else
+        tc_mma_rate_kernel<<<1, 128, smem>>>(flavour, N, reps, nacc, d);
+    GNNB_CUDA(cudaGetLastError());
+    GNNB_CUDA(cudaDeviceSynchronize());
+    GNNB_CUDA(cudaMemcpy(cycles, d, 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d);
     return GNNB_OK;
 }
