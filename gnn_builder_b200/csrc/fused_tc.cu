@@ -66,7 +66,7 @@ constexpr int NSLOT = 4;
 constexpr int SLOT_STRIDE = 16384;
 constexpr int RING_BYTES = NSLOT * SLOT_STRIDE;
 constexpr int CNT_BYTES = TM * TM;
-constexpr int MAX_NODES_PER_GRAPH = 64;
+constexpr int MAX_NODES_PER_GRAPH = TM;   // a graph must fit one tile
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_D = 0, TM_AHI = 128, TM_ALO = 256;
 
@@ -90,8 +90,8 @@ struct TcParams {
     const int64_t *node_ptr, *edge_ptr;
     int n_graphs;
     float *out;
-    const int32_t *tile_bounds;
-    int n_tiles;
+    const int32_t *tile_bounds;   // [n_tiles + 1] first graph of every tile (device-built)
+    const int32_t *n_tiles_ptr;   // number of tiles (device-built)
     int *error_flag;
     float *pending;               // [grid][HEAD_G][PLD] pooled vectors waiting for the head
     unsigned long long *timing;
@@ -118,22 +118,93 @@ __device__ __forceinline__ const TLinear &lin(const TcParams &p, int id)
     return (id & 1) ? p.l1[id >> 1] : p.l0[id >> 1];
 }
 
-__device__ __forceinline__ int lower_bound64(const int64_t *__restrict__ ptr, int n, int64_t v)
+// Tile packing on the device: consecutive graphs are packed greedily into tiles of <= 128 rows
+// (and <= 128 graphs).  The greedy walk is sequential, so the batch is cut into chunks of
+// PACK_CHUNK graphs that are packed independently (one CTA each: every thread finds, for "its"
+// graph, where a tile starting there would end; one thread then follows those links), followed
+// by a scan of the per-chunk tile counts and a compaction into the final tile list.  A chunk
+// boundary costs at most one partly filled tile per 2048 graphs.
+constexpr int PACK_CHUNK = 2048;
+__global__ void __launch_bounds__(256) tc_pack_chunk_kernel(const int64_t *__restrict__ node_ptr,
+                                                            int n_graphs, int32_t *__restrict__ starts_tmp,
+                                                            int32_t *__restrict__ counts)
 {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(ptr + mid) < v) lo = mid + 1; else hi = mid;
+    __shared__ int np[PACK_CHUNK + 1];
+    __shared__ unsigned short nxt[PACK_CHUNK];
+    const int g0 = blockIdx.x * PACK_CHUNK;
+    const int cnt = min(PACK_CHUNK, n_graphs - g0);
+    const int64_t base = __ldg(node_ptr + g0);
+    for (int i = threadIdx.x; i <= cnt; i += blockDim.x) {
+        const int64_t d = __ldg(node_ptr + g0 + i) - base;
+        np[i] = d > (int64_t)0x3fffffff ? 0x3fffffff : (int)d;
     }
-    return lo;
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        // largest e in [i + 1, min(cnt, i + TM)] with np[e] - np[i] <= TM (i + 1 always taken)
+        int lo = i + 1, hi = min(cnt, i + TM);
+        const int lim = np[i] + TM;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (np[mid] <= lim) lo = mid; else hi = mid - 1;
+        }
+        nxt[i] = (unsigned short)lo;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int pos = 0; pos < cnt; pos = nxt[pos]) starts_tmp[(size_t)blockIdx.x * PACK_CHUNK + n++] = g0 + pos;
+        counts[blockIdx.x] = n;
+    }
 }
-
-__global__ void tc_tile_bounds_kernel(const int64_t *__restrict__ node_ptr, int n_graphs,
-                                      int window, int n_tiles, int32_t *__restrict__ bounds)
+// exclusive scan of the per-chunk tile counts (one CTA), total -> *n_tiles
+__global__ void __launch_bounds__(1024) tc_pack_scan_kernel(const int32_t *__restrict__ counts,
+                                                            int n_chunks, int32_t *__restrict__ offsets,
+                                                            int32_t *__restrict__ n_tiles)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > n_tiles) return;
-    bounds[t] = (t == n_tiles) ? n_graphs : lower_bound64(node_ptr, n_graphs, (int64_t)t * window);
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c0 = 0; c0 < n_chunks; c0 += 1024) {
+        const int i = c0 + threadIdx.x;
+        const int v = i < n_chunks ? counts[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += t;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const int before = carry + (warp > 0 ? warp_sums[warp - 1] : 0) + incl - v;
+        if (i < n_chunks) offsets[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_tiles = carry;
+}
+__global__ void __launch_bounds__(256) tc_pack_compact_kernel(const int32_t *__restrict__ starts_tmp,
+                                                              const int32_t *__restrict__ counts,
+                                                              const int32_t *__restrict__ offsets,
+                                                              int n_chunks, int n_graphs,
+                                                              int32_t *__restrict__ bounds)
+{
+    const int c = blockIdx.x;
+    const int n = counts[c], off = offsets[c];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) bounds[off + i] = starts_tmp[(size_t)c * PACK_CHUNK + i];
+    if (c == n_chunks - 1 && threadIdx.x == 0) bounds[off + n] = n_graphs;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -223,7 +294,7 @@ __device__ __forceinline__ void agg_issue(Misc &ms, uint32_t tmem_d, uint32_t ad
 {
     const bool leader = tc::elect_one();
     const uint32_t idesc = tc::make_idesc_bf16(TM, n_cols, 1);
-    const int nks = (rows + 15) >> 4;
+    const int nks = rows > 0 ? (rows + 15) >> 4 : 1;   // (an all-empty tile still defines D)
     tc::tc_fence_after();
     // ADJ: k-step ks lives in K atom ks >> 2 at byte 32 (ks & 3); planes: 16 nodes = 2048 bytes
     const uint64_t a0 = tc::make_desc(adj), a1 = tc::make_desc(adj + tc::PLANE_BLOCK_BYTES);
@@ -269,18 +340,47 @@ __device__ __forceinline__ void split_store32(uint32_t ahi, uint32_t alo, const 
     tc::tmem_st32(alo, l);
 }
 
-// aggregation accumulator -> A operand.  scale: GCN dinv_v, SAGE 1/deg (0 when deg = 0), else 1;
-// self_coef != 0: add self_coef * x_v (GIN eps).  Columns [0, kp).
-__device__ __forceinline__ void cvt_agg(uint32_t tmem_base, const unsigned char *XP, int kp,
-                                        float scale, bool divide, float divisor, float self_coef)
+// One pass over the accumulator columns this warp owns ([32 h, +32) and [32 h + 64, +32), h = warp
+// >> 2, limited to ncols): f(c0, lane_base, v) runs per 32-column block.
+#ifdef GNNB_TC_SUBTIMING
+__device__ unsigned long long g_sub[8];
+#define SUBT(i, expr) do { const long long t0_ = clock64(); expr; if (threadIdx.x == 0) atomicAdd(&g_sub[i], (unsigned long long)(clock64() - t0_)); } while (0)
+#else
+#define SUBT(i, expr) do { expr; } while (0)
+#endif
+template <class F>
+__device__ __forceinline__ void row_pass(uint32_t tmem_src, int ncols, F &&f)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = 32 * (warp & 3) + lane;
+    const int warp = threadIdx.x >> 5;
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-    for (int c0 = (warp >> 2) * 32; c0 < kp; c0 += 64) {
+#pragma unroll 1
+    for (int c0 = (warp >> 2) * 32; c0 < ncols; c0 += 64) {
+        uint32_t r[32];
+        SUBT(0, tc::tmem_ld32_nowait(tmem_src + lane_base + (uint32_t)c0, r); tc::tmem_ld_wait());
+        SUBT(1, f(c0, lane_base, r));
+    }
+}
+template <int ACT>   // 0 identity, 1 relu, 2 anything else (one out-of-line call)
+__device__ __forceinline__ float act_fast(int act, float x)
+{
+    if (ACT == 0) return x;
+    if (ACT == 1) return fmaxf(x, 0.0f);   // NaN -> 0 like the reference's (x > 0 ? x : 0)
+    return act_apply_general(act, x);
+}
+
+// aggregation accumulator -> A operand.  MODE 0: v * scale (GCN dinv_v; 1 for plain sums), MODE 1:
+// v / divisor when on, else 0 (SAGE mean, lib:2180-2207), MODE 2: v + self_coef * x_v (GIN eps).
+// Columns [0, kp).
+template <int MODE>
+__device__ __forceinline__ void cvt_agg(uint32_t tmem_base, const unsigned char *XP, int kp,
+                                        float scale, bool on, float divisor, float self_coef)
+{
+    const int row = 32 * ((threadIdx.x >> 5) & 3) + (threadIdx.x & 31);
+    row_pass(tmem_base + TM_D, kp, [&](int c0, uint32_t lane_base, const uint32_t (&r)[32]) {
         float v[32];
-        tc::tmem_ld32(tmem_base + TM_D + lane_base + (uint32_t)c0, v);
-        if (self_coef != 0.0f) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+        if (MODE == 2) {
 #pragma unroll
             for (int j8 = 0; j8 < 4; j8++) {
                 float xs[8];
@@ -288,21 +388,20 @@ __device__ __forceinline__ void cvt_agg(uint32_t tmem_base, const unsigned char 
 #pragma unroll
                 for (int j = 0; j < 8; j++) v[8 * j8 + j] = fmaf(self_coef, xs[j], v[8 * j8 + j]);
             }
-        }
-        if (divide) {
+        } else if (MODE == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = v[j] / divisor;
+            for (int j = 0; j < 32; j++) v[j] = on ? v[j] / divisor : 0.0f;
         } else {
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] *= scale;
         }
         split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
                       tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
-    }
-    tc::tmem_st_wait();
+    });
+    SUBT(2, tc::tmem_st_wait());
 }
 
-// own row of the planes -> A operand (SAGE root term), columns [0, kp); unscale undoes a plane scale
+// own row of the planes -> A operand (SAGE root term), columns [0, kp)
 __device__ __forceinline__ void cvt_self(uint32_t tmem_base, const unsigned char *XP, int kp)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -325,15 +424,12 @@ __device__ __forceinline__ void cvt_self(uint32_t tmem_base, const unsigned char
 
 // accumulator -> (+bias, activation) -> A operand (GIN hidden layer, head hidden layers).
 // Columns [N, round_up(N, 32)) are zero filled.
-__device__ __forceinline__ void epilogue_tmem(uint32_t tmem_base, int N, const float *__restrict__ bias,
-                                              int act)
+template <int ACT>
+__device__ __forceinline__ void epilogue_tmem_t(uint32_t tmem_base, int N, const float *__restrict__ bias,
+                                                int act)
 {
-    const int warp = threadIdx.x >> 5;
-    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-    const int npad = (N + 31) & ~31;
-    for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += 64) {
+    row_pass(tmem_base + TM_D, (N + 31) & ~31, [&](int c0, uint32_t lane_base, const uint32_t (&r)[32]) {
         float v[32];
-        tc::tmem_ld32(tmem_base + TM_D + lane_base + (uint32_t)c0, v);
 #pragma unroll
         for (int j4 = 0; j4 < 8; j4++) {
             const bool in_range = c0 + j4 * 4 < N;   // N % 4 == 0
@@ -342,46 +438,50 @@ __device__ __forceinline__ void epilogue_tmem(uint32_t tmem_base, int N, const f
             const float bss[4] = {bs.x, bs.y, bs.z, bs.w};
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                v[j4 * 4 + j] = in_range ? act_apply_compact(act, v[j4 * 4 + j] + bss[j]) : 0.0f;
+                v[j4 * 4 + j] = in_range ? act_fast<ACT>(act, __uint_as_float(r[j4 * 4 + j]) + bss[j]) : 0.0f;
         }
         split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
                       tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
-    }
+    });
     tc::tmem_st_wait();
+}
+__device__ __forceinline__ void epilogue_tmem(uint32_t tmem_base, int N, const float *__restrict__ bias,
+                                              int act)
+{
+    if (act == GNNB_ACT_RELU) epilogue_tmem_t<1>(tmem_base, N, bias, act);
+    else if (act == GNNB_ACT_IDENTITY) epilogue_tmem_t<0>(tmem_base, N, bias, act);
+    else epilogue_tmem_t<2>(tmem_base, N, bias, act);
 }
 
 // accumulator -> (+bias, +skip, activation, * out_scale) -> bf16 planes (the next layer's input).
 // skip: add the row's current plane content times skip_unscale (cpp:269-279).  Returns nonzero if
-// a non-finite value was written.  Columns [N, round_up(N, 32)) are zero filled.
-__device__ __forceinline__ int epilogue_planes(uint32_t tmem_base, unsigned char *XP, int N,
-                                               const float *__restrict__ bias, int act, bool skip,
-                                               float skip_unscale, float out_scale)
+// a non-finite value was written (chk accumulates t * 0, which is NaN exactly then).  Columns
+// [N, round_up(N, 32)) are zero filled.
+template <int ACT, bool SKIP, bool SCALE>
+__device__ __forceinline__ int epilogue_planes_t(uint32_t tmem_base, unsigned char *XP, int N,
+                                                 const float *__restrict__ bias, int act,
+                                                 float skip_unscale, float out_scale)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = 32 * (warp & 3) + lane;
-    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-    const int npad = (N + 31) & ~31;
-    uint32_t bad = 0;
-    for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += 64) {
-        float v[32];
-        tc::tmem_ld32(tmem_base + TM_D + lane_base + (uint32_t)c0, v);
+    const int row = 32 * ((threadIdx.x >> 5) & 3) + (threadIdx.x & 31);
+    float chk = 0.0f;
+    row_pass(tmem_base + TM_D, (N + 31) & ~31, [&](int c0, uint32_t, const uint32_t (&r)[32]) {
 #pragma unroll
         for (int j8 = 0; j8 < 4; j8++) {
             const int c = c0 + 8 * j8;
-            const bool in_range = c < N;   // N % 8 == 0
             float o[8];
-            if (in_range) {
+            if (c < N) {   // N % 8 == 0
                 const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + c));
                 const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + c + 4));
                 const float bss[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 float xs[8];
-                if (skip) load_row8(XP, row, c, xs);
+                if (SKIP) load_row8(XP, row, c, xs);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    float t = v[8 * j8 + j] + bss[j];
-                    if (skip) t = fmaf(xs[j], skip_unscale, t);
-                    t = act_apply_compact(act, t) * out_scale;
-                    bad |= ((__float_as_uint(t) & 0x7f800000u) == 0x7f800000u) ? 1u : 0u;
+                    float t = __uint_as_float(r[8 * j8 + j]) + bss[j];
+                    if (SKIP) t = SCALE ? fmaf(xs[j], skip_unscale, t) : t + xs[j];
+                    t = act_fast<ACT>(act, t);
+                    if (SCALE) t *= out_scale;
+                    chk = fmaf(t, 0.0f, chk);
                     o[j] = t;
                 }
             } else {
@@ -390,8 +490,27 @@ __device__ __forceinline__ int epilogue_planes(uint32_t tmem_base, unsigned char
             }
             store_row8(XP, row, c, o);
         }
+    });
+    return chk == 0.0f ? 0 : 1;
+}
+// SCALE (GCN only): skip_unscale undoes the dinv factor stored in the planes, out_scale applies the
+// next layer's.  The common cases (ReLU / identity, with and without skip) get lean instantiations.
+__device__ __forceinline__ int epilogue_planes(uint32_t tmem_base, unsigned char *XP, int N,
+                                               const float *__restrict__ bias, int act, bool skip,
+                                               bool scale, float skip_unscale, float out_scale)
+{
+    if (scale) {
+        if (act == GNNB_ACT_RELU)
+            return skip ? epilogue_planes_t<1, true, true>(tmem_base, XP, N, bias, act, skip_unscale, out_scale)
+                        : epilogue_planes_t<1, false, true>(tmem_base, XP, N, bias, act, skip_unscale, out_scale);
+        return skip ? epilogue_planes_t<2, true, true>(tmem_base, XP, N, bias, act, skip_unscale, out_scale)
+                    : epilogue_planes_t<2, false, true>(tmem_base, XP, N, bias, act, skip_unscale, out_scale);
     }
-    return (int)bad;
+    if (act == GNNB_ACT_RELU)
+        return skip ? epilogue_planes_t<1, true, false>(tmem_base, XP, N, bias, act, 1.0f, 1.0f)
+                    : epilogue_planes_t<1, false, false>(tmem_base, XP, N, bias, act, 1.0f, 1.0f);
+    return skip ? epilogue_planes_t<2, true, false>(tmem_base, XP, N, bias, act, 1.0f, 1.0f)
+                : epilogue_planes_t<2, false, false>(tmem_base, XP, N, bias, act, 1.0f, 1.0f);
 }
 
 // head output: columns [0, n_true) of rows [0, n_rows) -> gout[gids[row]][col]
@@ -436,15 +555,14 @@ __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;\n
 
 #define GNNB_WAIT_DONE()                                                            \
     do {                                                                            \
-        if (warp_u == 0) tc::mbar_wait(&ms.bar_done, done_cnt & 1);                 \
+        tc::mbar_wait(&ms.bar_done, done_cnt & 1);   /* every worker polls: no barrier */ \
         done_cnt++;                                                                 \
-        worker_sync();                                                              \
         tc::tc_fence_after();                                                       \
     } while (0)
 #define GNNB_PUBLISH_TMEM()                                                         \
     do {                                                                            \
         tc::tc_fence_before();                                                      \
-        worker_sync();                                                              \
+        SUBT(3, worker_sync());                                                     \
     } while (0)
 
 // MLP head (cpp:454-530) for up to 128 pending graphs: the pooled vectors [128][head_in] go from the
@@ -536,6 +654,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
     const uint32_t xp_addr = adj_addr + tc::PLANE_BYTES;
     const uint32_t ring_addr = adj_addr + 4 * tc::PLANE_BYTES;
     uint32_t done_cnt = 0, cons = 0;
+    const int n_tiles = __shfl_sync(0xffffffffu, __ldg(p.n_tiles_ptr), 0);
 
     if (warp_u == NWARPS) {
         // ------------------------------------------------------------ weight-producer warp
@@ -547,7 +666,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
         const size_t copy_off = (size_t)(blockIdx.x % p.img_copies) * p.img_copy_bytes;
         uint32_t prod = 0;
         int pend = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int tg0 = __ldg(p.tile_bounds + tile), tg1 = __ldg(p.tile_bounds + tile + 1);
             const int tng = tg1 - tg0;
             const int64_t trows = __ldg(p.node_ptr + tg1) - __ldg(p.node_ptr + tg0);
@@ -579,14 +698,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
     // geometry of the first tile; later tiles are prefetched one iteration ahead
     int g0 = 0, g1 = 0;
     int64_t row0 = 0, e0 = 0, row1 = 0, e1 = 0;
-    if ((int)blockIdx.x < p.n_tiles) {
+    if ((int)blockIdx.x < n_tiles) {
         g0 = __ldg(p.tile_bounds + blockIdx.x);
         g1 = __ldg(p.tile_bounds + blockIdx.x + 1);
         row0 = __ldg(p.node_ptr + g0); row1 = __ldg(p.node_ptr + g1);
         e0 = __ldg(p.edge_ptr + g0); e1 = __ldg(p.edge_ptr + g1);
     }
 
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int ng = g1 - g0;
         const int rows = (int)(row1 - row0);
         const int ne = (int)(e1 - e0);
@@ -594,7 +713,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
         const int64_t cur_row0 = row0, cur_e0 = e0;
         const int nxt = tile + gridDim.x;
         int ng0 = 0, ng1 = 0;
-        if (nxt < p.n_tiles) {
+        if (nxt < n_tiles) {
             ng0 = __ldg(p.tile_bounds + nxt);
             ng1 = __ldg(p.tile_bounds + nxt + 1);
         }
@@ -703,7 +822,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             GNNB_PHASE(1)
         }
         // second half of the next tile's geometry (the bounds have arrived by now)
-        if (nxt < p.n_tiles) {
+        if (nxt < n_tiles) {
             g0 = ng0; g1 = ng1;
             row0 = __ldg(p.node_ptr + ng0); row1 = __ldg(p.node_ptr + ng1);
             e0 = __ldg(p.edge_ptr + ng0); e1 = __ldg(p.edge_ptr + ng1);
@@ -723,9 +842,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             if (warp_u == 0) agg_issue(ms, tmem_base + TM_D, adj_addr, xp_addr, kp, rows_u);
             GNNB_WAIT_DONE();
             GNNB_PHASE(2)
-            if (conv == GNNB_CONV_GCN) cvt_agg(tmem_base, XP, kp, my_dinv, false, 1.0f, 0.0f);
-            else if (conv == GNNB_CONV_GIN) cvt_agg(tmem_base, XP, kp, 1.0f, false, 1.0f, p.gin_eps);
-            else cvt_agg(tmem_base, XP, kp, my_deg > 0 ? 1.0f : 0.0f, my_deg > 0, (float)my_deg, 0.0f);
+            if (conv == GNNB_CONV_GCN) cvt_agg<0>(tmem_base, XP, kp, my_dinv, true, 1.0f, 0.0f);
+            else if (conv == GNNB_CONV_SAGE) cvt_agg<1>(tmem_base, XP, kp, 1.0f, my_deg > 0, (float)my_deg, 0.0f);
+            else if (p.gin_eps != 0.0f) cvt_agg<2>(tmem_base, XP, kp, 1.0f, true, 1.0f, p.gin_eps);
+            else cvt_agg<0>(tmem_base, XP, kp, 1.0f, true, 1.0f, 0.0f);
             GNNB_PUBLISH_TMEM();
             GNNB_PHASE(3)
             if (warp_u == 0) gemm_issue(ms, ring_addr, cons, tmem_base, p.l0[l], false);
@@ -749,9 +869,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             {
                 const TLinear &Lb = conv == GNNB_CONV_GIN ? p.l1[l] : p.l0[l];
                 const bool gcn = conv == GNNB_CONV_GCN;
-                bad_values |= epilogue_planes(tmem_base, XP, Lb.N, Lb.bias, p.gnn_act, do_skip,
-                                              gcn ? sqrtf(1.0f + (float)my_deg) : 1.0f,
-                                              (gcn && !last_layer) ? my_dinv : 1.0f);
+                bad_values |= epilogue_planes(tmem_base, XP, Lb.N, Lb.bias, p.gnn_act, do_skip, gcn,
+                                              sqrtf(1.0f + (float)my_deg), last_layer ? 1.0f : my_dinv);
             }
             tc::fence_async_smem();
             GNNB_PUBLISH_TMEM();
@@ -818,7 +937,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
 
 struct TcPlan {
     TcParams params{};
-    DeviceBuf images, bounds, flag, pending, timing;
+    DeviceBuf images, bounds, pack_tmp, flag, pending, timing;
     size_t smem_bytes = 0;
 };
 
@@ -961,7 +1080,7 @@ void fused_tc_release(gnnb_model *m)
 {
     TcPlan *plan = m->fused_tc;
     if (plan) {
-        plan->images.release(); plan->bounds.release(); plan->flag.release();
+        plan->images.release(); plan->bounds.release(); plan->pack_tmp.release(); plan->flag.release();
         plan->pending.release(); plan->timing.release();
         delete plan;
         m->fused_tc = nullptr;
@@ -982,26 +1101,33 @@ int fused_tc_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_
     GNNB_REQUIRE(plan != nullptr, "tensor-core fused kernel not available for this model");
     if (max_nodes < 1) max_nodes = 1;
     GNNB_REQUIRE(max_nodes <= MAX_NODES_PER_GRAPH, "graph too large for the fused kernel");
-    const int window = TM - max_nodes + 1;
-    const int64_t n_tiles64 = total_nodes / window + 1;
-    GNNB_REQUIRE(n_tiles64 < (1ll << 30), "too many tiles");
-    const int n_tiles = (int)n_tiles64;
-    GNNB_TRY(plan->bounds.ensure(sizeof(int32_t) * ((size_t)n_tiles + 1)));
+    // device-side greedy packing of the graphs into tiles (three tiny kernels, no host sync)
+    const int n_chunks = (n_graphs + PACK_CHUNK - 1) / PACK_CHUNK;
+    // consecutive tiles hold > 128 rows together (or 128 graphs): an upper bound for the list
+    const size_t max_tiles = (size_t)(2 * (total_nodes / TM) + 2 * ((int64_t)n_graphs / TM) + n_chunks + 4);
+    GNNB_REQUIRE(max_tiles < ((size_t)1 << 30), "too many tiles");
+    GNNB_TRY(plan->bounds.ensure(sizeof(int32_t) * (max_tiles + 2)));
+    GNNB_TRY(plan->pack_tmp.ensure(sizeof(int32_t) * ((size_t)n_chunks * PACK_CHUNK + 2 * (size_t)n_chunks + 2)));
+    int32_t *starts_tmp = plan->pack_tmp.as<int32_t>();
+    int32_t *counts = starts_tmp + (size_t)n_chunks * PACK_CHUNK;
+    int32_t *offsets = counts + n_chunks;
+    int32_t *n_tiles_dev = offsets + n_chunks;
     GNNB_CUDA(cudaMemsetAsync(plan->flag.ptr, 0, sizeof(int), s));
-    tc_tile_bounds_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, s>>>(node_ptr, n_graphs, window,
-                                                                    n_tiles,
-                                                                    plan->bounds.as<int32_t>());
+    tc_pack_chunk_kernel<<<n_chunks, 256, 0, s>>>(node_ptr, n_graphs, starts_tmp, counts);
+    tc_pack_scan_kernel<<<1, 1024, 0, s>>>(counts, n_chunks, offsets, n_tiles_dev);
+    tc_pack_compact_kernel<<<n_chunks, 256, 0, s>>>(starts_tmp, counts, offsets, n_chunks, n_graphs,
+                                                    plan->bounds.as<int32_t>());
     GNNB_CUDA(cudaGetLastError());
     TcParams p = plan->params;
     p.x = x; p.coo = coo; p.node_ptr = node_ptr; p.edge_ptr = edge_ptr; p.n_graphs = n_graphs;
-    p.out = out; p.tile_bounds = plan->bounds.as<int32_t>(); p.n_tiles = n_tiles;
+    p.out = out; p.tile_bounds = plan->bounds.as<int32_t>(); p.n_tiles_ptr = n_tiles_dev;
     p.error_flag = plan->flag.as<int>();
     p.pending = plan->pending.as<float>();
     p.timing = plan->timing.as<unsigned long long>();
-    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+    const int grid = n_graphs < kNumSMs ? n_graphs : kNumSMs;
     fused_tc_kernel<<<grid, CTA_THREADS, plan->smem_bytes, s>>>(p);
     GNNB_CUDA(cudaGetLastError());
-    if (launches) *launches += 2;
+    if (launches) *launches += 4;
     return GNNB_OK;
 }
 
@@ -1024,6 +1150,14 @@ int fused_tc_status(gnnb_model *m, int *status)
             if (i != 6)
                 fprintf(stderr, " %s %.1f%%", names[i], tot ? 100.0 * (double)t[i] / (double)tot : 0.0);
         fprintf(stderr, " (total %.3g cycles over all CTAs)\n", (double)tot);
+#ifdef GNNB_TC_SUBTIMING
+        unsigned long long sub[8];
+        cudaMemcpyFromSymbol(sub, g_sub, sizeof(sub));
+        unsigned long long zero[8] = {0};
+        cudaMemcpyToSymbol(g_sub, zero, sizeof(zero));
+        fprintf(stderr, "[gnnb fused-tc sub] tmem-ld %.1f%% row-work %.1f%% st-wait(cvt) %.1f%% publish-barrier %.1f%%\n",
+                100.0 * sub[0] / tot, 100.0 * sub[1] / tot, 100.0 * sub[2] / tot, 100.0 * sub[3] / tot);
+#endif
     }
     return GNNB_OK;
 }
