@@ -513,6 +513,44 @@ __device__ __forceinline__ int epilogue_planes(uint32_t tmem_base, unsigned char
                 : epilogue_planes_t<2, false, false>(tmem_base, XP, N, bias, act, 1.0f, 1.0f);
 }
 
+// Last conv layer: accumulator -> (+bias, +skip, activation) -> plain fp32 rows in the (now dead)
+// plane region, for pooling only: row r at 512 r bytes, 16-byte chunk c stored at position
+// c ^ (r & 7) so that thread-per-row stores and lane-per-chunk pooling reads are both conflict free.
+// No non-finite check: pooling and the head never mix graphs.
+__device__ __forceinline__ uint32_t out_chunk_offset(int row, int c4)   // c4 % 4 == 0
+{
+    return (uint32_t)row * 512u + (uint32_t)(((c4 >> 2) ^ (row & 7)) << 4);
+}
+template <int ACT>
+__device__ __forceinline__ void epilogue_rows_t(uint32_t tmem_base, unsigned char *XP, int N,
+                                                const float *__restrict__ bias, int act)
+{
+    const int row = 32 * ((threadIdx.x >> 5) & 3) + (threadIdx.x & 31);
+    row_pass(tmem_base + TM_D, (N + 31) & ~31, [&](int c0, uint32_t, const uint32_t (&r)[32]) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++) {
+            const int c = c0 + 4 * j4;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < N) {   // N % 4 == 0
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + c));
+                o.x = act_fast<ACT>(act, __uint_as_float(r[4 * j4]) + b.x);
+                o.y = act_fast<ACT>(act, __uint_as_float(r[4 * j4 + 1]) + b.y);
+                o.z = act_fast<ACT>(act, __uint_as_float(r[4 * j4 + 2]) + b.z);
+                o.w = act_fast<ACT>(act, __uint_as_float(r[4 * j4 + 3]) + b.w);
+            }
+            *reinterpret_cast<float4 *>(XP + out_chunk_offset(row, c)) = o;
+        }
+    });
+}
+// (the last layer never has a skip connection, cpp:269-279, and GCN leaves it unscaled)
+__device__ __forceinline__ void epilogue_rows(uint32_t tmem_base, unsigned char *XP, int N,
+                                              const float *__restrict__ bias, int act)
+{
+    if (act == GNNB_ACT_RELU) epilogue_rows_t<1>(tmem_base, XP, N, bias, act);
+    else if (act == GNNB_ACT_IDENTITY) epilogue_rows_t<0>(tmem_base, XP, N, bias, act);
+    else epilogue_rows_t<2>(tmem_base, XP, N, bias, act);
+}
+
 // head output: columns [0, n_true) of rows [0, n_rows) -> gout[gids[row]][col]
 __device__ __forceinline__ void epilogue_global(uint32_t tmem_base, int N, const float *__restrict__ bias,
                                                 int act, float *gout, const int *gids, int n_rows,
@@ -531,23 +569,6 @@ __device__ __forceinline__ void epilogue_global(uint32_t tmem_base, int N, const
         for (int j = 0; j < 32; j++)
             if (c0 + j < n_true) grow[c0 + j] = act_apply_compact(act, v[j] + __ldg(bias + c0 + j));
     }
-}
-
-// 4 consecutive features of a row from the planes (pooling), cc % 4 == 0
-__device__ __forceinline__ float4 load_row4(const unsigned char *XP, int row, int cc)
-{
-    const uint32_t off = tc::plane_chunk_offset(row, cc & ~7) + (uint32_t)(cc & 4) * 2u;
-    const uint2 h = *reinterpret_cast<const uint2 *>(XP + off);
-    const uint2 m = *reinterpret_cast<const uint2 *>(XP + tc::PLANE_BYTES + off);
-    const uint2 l = *reinterpret_cast<const uint2 *>(XP + 2 * tc::PLANE_BYTES + off);
-    float4 v;
-    v.x = (__uint_as_float(h.x << 16) + __uint_as_float(m.x << 16)) + __uint_as_float(l.x << 16);
-    v.y = (__uint_as_float(h.x & 0xffff0000u) + __uint_as_float(m.x & 0xffff0000u)) +
-          __uint_as_float(l.x & 0xffff0000u);
-    v.z = (__uint_as_float(h.y << 16) + __uint_as_float(m.y << 16)) + __uint_as_float(l.y << 16);
-    v.w = (__uint_as_float(h.y & 0xffff0000u) + __uint_as_float(m.y & 0xffff0000u)) +
-          __uint_as_float(l.y & 0xffff0000u);
-    return v;
 }
 
 // barrier over the 256 worker threads (the producer warp never joins it)
@@ -743,11 +764,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
                         xv[q][j] = (r_own < rows && c + j < F) ? __ldg(src + c + j) : 0.0f;
                 }
             }
+            // first edge of this thread: in flight across the barrier as well
+            const int2 *coo = reinterpret_cast<const int2 *>(p.coo) + cur_e0;
+            const int2 first_edge = tid < ne ? __ldg(coo + tid) : make_int2(0, 0);
             worker_sync();
             {   // edges -> multiplicity counts + in-degrees (lib:1051-1083)
-                const int2 *coo = reinterpret_cast<const int2 *>(p.coo) + cur_e0;
                 for (int j = tid; j < ne; j += NTHREADS) {
-                    const int2 sd = __ldg(coo + j);
+                    const int2 sd = j == tid ? first_edge : __ldg(coo + j);
                     int lo = 0, hi = ng;
                     while (hi - lo > 1) {
                         const int mid = (lo + hi) >> 1;
@@ -821,11 +844,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             GNNB_PUBLISH_TMEM();
             GNNB_PHASE(1)
         }
-        // second half of the next tile's geometry (the bounds have arrived by now)
+        // second half of the next tile's geometry (the bounds have arrived by now), and a hint to
+        // pull that tile's features / edges / offsets into L2 while this tile computes
         if (nxt < n_tiles) {
             g0 = ng0; g1 = ng1;
             row0 = __ldg(p.node_ptr + ng0); row1 = __ldg(p.node_ptr + ng1);
             e0 = __ldg(p.edge_ptr + ng0); e1 = __ldg(p.edge_ptr + ng1);
+            const char *xb = reinterpret_cast<const char *>(p.x + (size_t)row0 * p.in_dim);
+            const char *eb = reinterpret_cast<const char *>(p.coo + 2 * (size_t)e0);
+            const size_t xbytes = (size_t)(row1 - row0) * p.in_dim * 4, ebytes = (size_t)(e1 - e0) * 8;
+            for (size_t o = (size_t)tid * 128; o < xbytes; o += (size_t)NTHREADS * 128) tc::prefetch_l2(xb + o);
+            for (size_t o = (size_t)tid * 128; o < ebytes; o += (size_t)NTHREADS * 128) tc::prefetch_l2(eb + o);
         }
         if (!run) continue;
 
@@ -869,8 +898,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             {
                 const TLinear &Lb = conv == GNNB_CONV_GIN ? p.l1[l] : p.l0[l];
                 const bool gcn = conv == GNNB_CONV_GCN;
-                bad_values |= epilogue_planes(tmem_base, XP, Lb.N, Lb.bias, p.gnn_act, do_skip, gcn,
-                                              sqrtf(1.0f + (float)my_deg), last_layer ? 1.0f : my_dinv);
+                if (last_layer)   // only pooling reads it: plain fp32 rows
+                    epilogue_rows(tmem_base, XP, Lb.N, Lb.bias, p.gnn_act);
+                else
+                    bad_values |= epilogue_planes(tmem_base, XP, Lb.N, Lb.bias, p.gnn_act, do_skip, gcn,
+                                                  sqrtf(1.0f + (float)my_deg), my_dinv);
             }
             tc::fence_async_smem();
             GNNB_PUBLISH_TMEM();
@@ -887,7 +919,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
                 for (int cc = lane * 4; cc < emb; cc += 128) {   // emb % 16 == 0
                     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), mx = sum;
                     for (int r = r0; r < r1; r++) {
-                        const float4 v = load_row4(XP, r, cc);
+                        const float4 v = *reinterpret_cast<const float4 *>(XP + out_chunk_offset(r, cc));
                         sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
                         const bool first = r == r0;                       // lib:748-759
                         mx.x = (first || v.x > mx.x) ? v.x : mx.x; mx.y = (first || v.y > mx.y) ? v.y : mx.y;

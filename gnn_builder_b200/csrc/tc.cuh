@@ -107,6 +107,11 @@ __device__ __forceinline__ void bulk_g2s_addr(uint32_t smem_dst_addr, const void
         : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *gptr)
+{
+    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gptr));
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_async_smem()
 {
