@@ -1127,7 +1127,7 @@ bool fused_tc_supports(const gnnb_model *m, int max_nodes_in_batch, int max_edge
 
 int fused_tc_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_t *node_ptr,
                  const int64_t *edge_ptr, int n_graphs, int64_t total_nodes, int max_nodes,
-                 float *out, cudaStream_t s, int *launches)
+                 float *out, cudaStream_t s, int *launches, bool reset_status)
 {
     TcPlan *plan = m->fused_tc;
     GNNB_REQUIRE(plan != nullptr, "tensor-core fused kernel not available for this model");
@@ -1144,7 +1144,7 @@ int fused_tc_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_
     int32_t *counts = starts_tmp + (size_t)n_chunks * PACK_CHUNK;
     int32_t *offsets = counts + n_chunks;
     int32_t *n_tiles_dev = offsets + n_chunks;
-    GNNB_CUDA(cudaMemsetAsync(plan->flag.ptr, 0, sizeof(int), s));
+    if (reset_status) GNNB_CUDA(cudaMemsetAsync(plan->flag.ptr, 0, sizeof(int), s));
     tc_pack_chunk_kernel<<<n_chunks, 256, 0, s>>>(node_ptr, n_graphs, starts_tmp, counts);
     tc_pack_scan_kernel<<<1, 1024, 0, s>>>(counts, n_chunks, offsets, n_tiles_dev);
     tc_pack_compact_kernel<<<n_chunks, 256, 0, s>>>(starts_tmp, counts, offsets, n_chunks, n_graphs,

@@ -203,6 +203,15 @@ extern "C" int gnnb_model_create(const gnnb_model_desc *desc, int device, gnnb_m
         delete m;
         return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
     }
+    bool ok = cudaStreamCreateWithFlags(&m->h2d_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&m->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++)
+        ok = cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        gnnb_model_destroy(m);
+        return cuda_fail(cudaGetLastError(), "creating the ingest streams/events", __FILE__, __LINE__);
+    }
     enumerate_params(m);
     *out = m;
     return GNNB_OK;
@@ -224,6 +233,13 @@ extern "C" int gnnb_model_destroy(gnnb_model_t *m)
                          &m->tws.heavy_partial,
                          &m->tws.counters};
     for (DeviceBuf *b : bufs) b->release();
+    for (int i = 0; i < 2; i++) {
+        m->ch_x[i].release(); m->ch_coo[i].release(); m->ch_nptr[i].release(); m->ch_eptr[i].release();
+        if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
+        if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
+    }
+    if (m->h2d_stream) cudaStreamDestroy(m->h2d_stream);
+    if (m->d2h_stream) cudaStreamDestroy(m->d2h_stream);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
     return GNNB_OK;
@@ -680,6 +696,91 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
     const int64_t T = hn[n_graphs], E = he[n_graphs];
     GNNB_REQUIRE(T == 0 || x != nullptr, "x is null");
     GNNB_REQUIRE(E == 0 || edge_list != nullptr, "edge_list is null");
+
+    // ---- host buffers + tensor-core fused kernel: chunked ingest pipeline.  The batch is cut into
+    // chunks of graphs; chunk k+1 is copied in (h2d stream) while chunk k computes (compute stream)
+    // and chunk k-1's outputs are copied out (d2h stream), through double-buffered chunk staging.
+    // End to end the step then costs max(PCIe, kernel) instead of their sum.
+    if (!dev) {
+        int path0, kernel0;
+        GNNB_TRY(choose_path(m, (int)max_n, (int)max_e, &path0, &kernel0));
+        if (path0 == GNNB_PATH_FUSED && kernel0 == 3 && getenv("GNNB_NO_INGEST_PIPELINE") == nullptr) {
+            int chunk_graphs = 32768;
+            if (const char *e = getenv("GNNB_INGEST_CHUNK_GRAPHS")) chunk_graphs = std::max(1024, atoi(e));
+            const int n_chunks = (n_graphs + chunk_graphs - 1) / chunk_graphs;
+            int64_t max_cn = 1, max_ce = 1;
+            for (int k = 0; k < n_chunks; k++) {
+                const int a = k * chunk_graphs, b = std::min(n_graphs, a + chunk_graphs);
+                max_cn = std::max(max_cn, hn[b] - hn[a]);
+                max_ce = std::max(max_ce, he[b] - he[a]);
+            }
+            for (int i = 0; i < 2; i++) {
+                GNNB_TRY(m->ch_x[i].ensure(sizeof(float) * (size_t)max_cn * d.in_dim));
+                GNNB_TRY(m->ch_coo[i].ensure(sizeof(int32_t) * 2 * (size_t)max_ce));
+                GNNB_TRY(m->ch_nptr[i].ensure(8 * ((size_t)chunk_graphs + 1)));
+                GNNB_TRY(m->ch_eptr[i].ensure(8 * ((size_t)chunk_graphs + 1)));
+            }
+            GNNB_TRY(m->st_out.ensure(sizeof(float) * (size_t)n_graphs * d.mlp_out));
+            float *dout_all = m->st_out.as<float>();
+            m->last_launches = 0;
+            m->last_path = GNNB_PATH_FUSED;
+            m->last_kernel = 3;
+            {
+                ProfScope ps(m->prof, PROF_FUSED, s);
+                for (int k = 0; k < n_chunks; k++) {
+                    const int a = k * chunk_graphs, b = std::min(n_graphs, a + chunk_graphs), bi = k & 1;
+                    const int64_t cn = hn[b] - hn[a], ce = he[b] - he[a];
+                    if (k >= 2) GNNB_CUDA(cudaStreamWaitEvent(m->h2d_stream, m->ev_done[bi], 0));
+                    if (cn > 0)
+                        GNNB_CUDA(cudaMemcpyAsync(m->ch_x[bi].ptr, x + (size_t)hn[a] * d.in_dim,
+                                                  sizeof(float) * (size_t)cn * d.in_dim,
+                                                  cudaMemcpyHostToDevice, m->h2d_stream));
+                    if (ce > 0)
+                        GNNB_CUDA(cudaMemcpyAsync(m->ch_coo[bi].ptr, edge_list + 2 * (size_t)he[a],
+                                                  sizeof(int32_t) * 2 * (size_t)ce, cudaMemcpyHostToDevice,
+                                                  m->h2d_stream));
+                    GNNB_CUDA(cudaMemcpyAsync(m->ch_nptr[bi].ptr, node_ptr + a, 8 * (size_t)(b - a + 1),
+                                              cudaMemcpyHostToDevice, m->h2d_stream));
+                    GNNB_CUDA(cudaMemcpyAsync(m->ch_eptr[bi].ptr, edge_ptr + a, 8 * (size_t)(b - a + 1),
+                                              cudaMemcpyHostToDevice, m->h2d_stream));
+                    GNNB_CUDA(cudaEventRecord(m->ev_h2d[bi], m->h2d_stream));
+                    GNNB_CUDA(cudaStreamWaitEvent(s, m->ev_h2d[bi], 0));
+                    // the offsets stay absolute (relative to the whole batch): rebase the data pointers
+                    const float *xb = m->ch_x[bi].as<float>() - (size_t)hn[a] * d.in_dim;
+                    const int32_t *cb = m->ch_coo[bi].as<int32_t>() - 2 * (size_t)he[a];
+                    GNNB_TRY(fused_tc_run(m, xb, cb, m->ch_nptr[bi].as<int64_t>(), m->ch_eptr[bi].as<int64_t>(),
+                                          b - a, cn, (int)max_n, dout_all + (size_t)a * d.mlp_out, s,
+                                          &m->last_launches, k == 0));
+                    GNNB_CUDA(cudaEventRecord(m->ev_done[bi], s));
+                    GNNB_CUDA(cudaStreamWaitEvent(m->d2h_stream, m->ev_done[bi], 0));
+                    GNNB_CUDA(cudaMemcpyAsync(out + (size_t)a * d.mlp_out, dout_all + (size_t)a * d.mlp_out,
+                                              sizeof(float) * (size_t)(b - a) * d.mlp_out,
+                                              cudaMemcpyDeviceToHost, m->d2h_stream));
+                }
+            }
+            GNNB_CUDA(cudaStreamSynchronize(s));
+            GNNB_CUDA(cudaStreamSynchronize(m->d2h_stream));
+            int status = 0;
+            GNNB_TRY(fused_any_status(m, &status));
+            if (status == 2) {
+                set_error("edge_list holds a node index outside its graph");
+                return GNNB_ERR_INVALID;
+            }
+            if (status == 0) return GNNB_OK;
+            if (m->path == GNNB_PATH_FUSED) {
+                set_error(status == 1 ? "fused path requested but a tile exceeded its capacity"
+                                      : "fused path requested but the batch produced non-finite "
+                                        "activations (graphs of a tile would contaminate each other)");
+                return GNNB_ERR_INVALID;
+            }
+            // capacity overflow or non-finite activations: fall through to the whole-batch upload
+            // below and redo everything on the layerwise path
+            m->path = GNNB_PATH_LAYERWISE;
+            const int rc = gnnb_model_run_batch(m, x, edge_list, node_ptr, edge_ptr, n_graphs, out);
+            m->path = GNNB_PATH_AUTO;
+            return rc;
+        }
+    }
 
     const float *dx = x;
     const int32_t *dcoo = edge_list;

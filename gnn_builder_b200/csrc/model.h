@@ -91,6 +91,11 @@ struct gnnb_model {
 
     // staging for host-pointer calls
     gnnb::DeviceBuf st_x, st_coo, st_nptr, st_eptr, st_out;
+    // chunked ingest pipeline (host buffers -> fused kernel): double-buffered chunk staging, a
+    // copy-in and a copy-out stream beside the compute stream, events for the hand-offs
+    gnnb::DeviceBuf ch_x[2], ch_coo[2], ch_nptr[2], ch_eptr[2];
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     // layerwise workspaces
     gnnb::DeviceBuf in_deg, out_deg, offsets, nbr, dinv, feat[2], agg, hid, wide, pooled, hbuf[2],
         pool_tmp, ptr_tmp;
@@ -134,9 +139,10 @@ int fused_tile_rows(const gnnb_model *m);
 int fused_tc_prepare(gnnb_model *m);
 void fused_tc_release(gnnb_model *m);
 bool fused_tc_supports(const gnnb_model *m, int max_nodes_in_batch, int max_edges_in_batch);
+// reset_status: clear the device status word first (false when a batch is run as several chunks)
 int fused_tc_run(gnnb_model *m, const float *x, const int32_t *coo, const int64_t *node_ptr,
                  const int64_t *edge_ptr, int n_graphs, int64_t total_nodes, int max_nodes,
-                 float *out, cudaStream_t s, int *launches);
+                 float *out, cudaStream_t s, int *launches, bool reset_status = true);
 int fused_tc_status(gnnb_model *m, int *status);
 
 }  // namespace gnnb
