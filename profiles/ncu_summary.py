@@ -51,5 +51,51 @@ def main():
                 print(f"   {short:75s} {r[i]:>16s} {units[i]}")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 2 and sys.argv[1] == "--stalls"):
     main()
+
+
+def stalls(rep, top=25):
+    """warp-stall sampling totals and the hottest CUDA source lines (needs -lineinfo +
+    --import-source on): python profiles/ncu_summary.py --stalls <file.ncu-rep>"""
+    import collections
+
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source",
+                          "cuda,sass"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    kernel, hdr, cur = None, None, None
+    agg, st = collections.Counter(), collections.Counter()
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            if agg:
+                break           # first kernel of the report only
+            kernel = r[1]
+            continue
+        if "# Samples" in r:
+            hdr = r
+            i_n = hdr.index("# Samples")
+            cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+            continue
+        if hdr is None or len(r) < len(hdr):
+            continue
+        if r[0] != "" and r[2] == "-":
+            cur = (r[0], r[1].strip()[:100])
+        elif r[0] == "" and r[2].startswith("0x"):
+            try:
+                agg[cur] += int(r[i_n])
+                for i in cols:
+                    st[hdr[i]] += int(r[i])
+            except ValueError:
+                pass
+    tot = max(1, sum(agg.values()))
+    print(f"# kernel: {kernel}")
+    print(f"# warp stall sampling, {tot} samples")
+    for k, v in st.most_common(10):
+        print(f"   {k:28s} {v:9d} {100.0 * v / tot:5.1f} %")
+    print("# hottest source lines (share of all samples)")
+    for (ln, src), n in agg.most_common(top):
+        print(f"   {100.0 * n / tot:5.2f} %  line {ln:>5s}  {src}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[1] == "--stalls":
+    stalls(sys.argv[2])

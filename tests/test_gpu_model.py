@@ -210,3 +210,69 @@ def test_project_flow(gnnb, tmp_path):
     assert data_b["model_output_mae"] < 1e-5
     with pytest.raises(NotImplementedError):
         proj.run_vitis_hls_synthesis()
+
+
+def test_fused_tc_used_for_gcn_gin_sage(gnnb, orc):
+    """the tensor-core fused kernel is the AUTO choice for the three molecular configs it covers"""
+    for name in ("c1_gcn_esol", "c2_gin_qm9", "c3_sage_hiv"):
+        w, model, params = model_and_params(name)
+        batch = gnnb.make_molecular_batch(200, w.mu_nodes, w.mu_edges, w.in_dim, seed=3)
+        ref = orc.model_forward_batch(model.describe(), list(params.values()), batch)
+        with gnnb.Engine(model) as eng:
+            out = eng.run(batch)
+            assert eng.last_kernel == "fused-tcgen05", (name, eng.last_kernel)
+            assert rel_err(out, ref) < TOL, name
+
+
+def test_tile_packing_edge_cases(gnnb, orc):
+    """greedy device-side tile packing: runs of empty graphs, > 128 one-node graphs in a row, graphs
+    of exactly 128 nodes, a batch that spans several 2048-graph packing chunks"""
+    w, model, params = model_and_params("c2_gin_qm9_small")
+    rng = np.random.default_rng(9)
+    graphs = []
+    for _ in range(300):
+        graphs.append((np.zeros((0, w.in_dim), np.float32), np.zeros((0, 2), np.int32)))
+    for _ in range(400):
+        graphs.append((rng.uniform(-1, 1, (1, w.in_dim)), np.zeros((0, 2), np.int32)))
+    for n in (128, 127, 128, 1, 128):
+        graphs.append((rng.uniform(-1, 1, (n, w.in_dim)),
+                       np.stack([rng.integers(0, n, 3 * n), rng.integers(0, n, 3 * n)], 1)))
+    mol = gnnb.make_molecular_batch(5000, w.mu_nodes, w.mu_edges, w.in_dim, seed=21)
+    graphs += [mol.graph(g) for g in range(mol.n_graphs)]
+    graphs.append((np.zeros((0, w.in_dim), np.float32), np.zeros((0, 2), np.int32)))
+    batch = gnnb.GraphBatch.from_graphs(graphs)
+    ref = orc.model_forward_batch(model.describe(), list(params.values()), batch)
+    with gnnb.Engine(model) as eng:
+        out = eng.run(batch)
+        assert eng.last_kernel == "fused-tcgen05"
+        assert rel_err(out, ref) < TOL
+
+
+def test_non_finite_inputs_do_not_leak_between_graphs(gnnb, orc):
+    """Inside the tensor-core aggregation 0 x Inf would poison the other graphs of a tile; the
+    kernel detects non-finite activations and the batch is redone on the layerwise path, so every
+    graph's output is what the reference computes for that graph alone."""
+    w, model, params = model_and_params("c2_gin_qm9_small")
+    batch = gnnb.make_molecular_batch(64, w.mu_nodes, w.mu_edges, w.in_dim, seed=5)
+    x = batch.x.copy()
+    r0 = int(batch.node_ptr[7])
+    x[r0, 2] = np.inf
+    x[int(batch.node_ptr[20]) + 1, 0] = np.nan
+    bad = gnnb.GraphBatch(x, batch.coo, batch.node_ptr, batch.edge_ptr)
+    ref = orc.model_forward_batch(model.describe(), list(params.values()), bad)
+    clean = orc.model_forward_batch(model.describe(), list(params.values()), batch)
+    with gnnb.Engine(model) as eng:
+        out = eng.run(bad)
+        assert eng.last_path == gnnb.PATH_LAYERWISE      # fell back
+        ok = np.ones(64, bool)
+        ok[[7, 20]] = False
+        assert np.isfinite(out[ok]).all()
+        assert rel_err(out[ok], clean[ok]) < TOL
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        # an explicit request for the fused path reports the problem instead of falling back
+        eng.set_path(gnnb.PATH_FUSED)
+        with pytest.raises(gnnb._lib.GnnbError):
+            eng.run(bad)
+        eng.set_path(gnnb.PATH_AUTO)
+        assert rel_err(eng.run(batch), clean) < TOL
+        assert eng.last_kernel == "fused-tcgen05"
