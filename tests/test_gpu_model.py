@@ -227,7 +227,7 @@ def test_fused_tc_used_for_gcn_gin_sage(gnnb, orc):
 def test_tile_packing_edge_cases(gnnb, orc):
     """greedy device-side tile packing: runs of empty graphs, > 128 one-node graphs in a row, graphs
     of exactly 128 nodes, a batch that spans several 2048-graph packing chunks"""
-    w, model, params = model_and_params("c2_gin_qm9_small")
+    w, model, params = model_and_params("c2_gin_qm9")
     rng = np.random.default_rng(9)
     graphs = []
     for _ in range(300):
@@ -252,7 +252,7 @@ def test_non_finite_inputs_do_not_leak_between_graphs(gnnb, orc):
     """Inside the tensor-core aggregation 0 x Inf would poison the other graphs of a tile; the
     kernel detects non-finite activations and the batch is redone on the layerwise path, so every
     graph's output is what the reference computes for that graph alone."""
-    w, model, params = model_and_params("c2_gin_qm9_small")
+    w, model, params = model_and_params("c2_gin_qm9")
     batch = gnnb.make_molecular_batch(64, w.mu_nodes, w.mu_edges, w.in_dim, seed=5)
     x = batch.x.copy()
     r0 = int(batch.node_ptr[7])
