@@ -45,6 +45,7 @@ EXPORTS = [
     "gnnb_compute_degree_tables", "gnnb_compute_neighbor_tables",
     "gnnb_compute_neighbor_and_edge_index_tables", "gnnb_linear", "gnnb_apply_activation",
     "gnnb_gcn_conv", "gnnb_gin_conv", "gnnb_sage_conv", "gnnb_pna_conv",
+    "gnnb_gine_conv", "gnnb_lg_conv", "gnnb_simple_conv",
     "gnnb_global_add_pool", "gnnb_global_mean_pool", "gnnb_global_max_pool",
     "gnnb_partition_tables", "gnnb_degree_inv_sqrt", "gnnb_gcn_conv_partition",
     "gnnb_debug_tc_gemm", "gnnb_debug_tc_agg_gemm", "gnnb_debug_tc_mma_rate",
@@ -102,6 +103,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.gnnb_sage_conv.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci]
     lib.gnnb_pna_conv.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, cf,
                                   ci, ci]
+    lib.gnnb_gine_conv.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                   cf, ci, ci, ci, ci, ci]
+    lib.gnnb_lg_conv.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, vp, ci, ci]
+    lib.gnnb_simple_conv.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, vp, ci, ci]
     for k in ("add", "mean", "max"):
         getattr(lib, f"gnnb_global_{k}_pool").argtypes = [ci, ci, vp, vp, ci]
     lib.gnnb_debug_tc_gemm.argtypes = [vp, vp, vp, ci, ci]

@@ -425,4 +425,86 @@ int launch_pna_agg(const PnaAggArgs &a, cudaStream_t s, int *launches)
     return GNNB_OK;
 }
 
+// ------------------------------------------------------------------------------------ GINE
+//
+// lib:1555-1623 gine_conv_agg: agg_v = sum_k relu(x[u_k] + proj[eid_k]) over the in-edges of v in
+// table order, where proj = edge_feat . W_e^T + b_e was computed per edge by one GEMM; then the GIN
+// self term (1 + eps) x_v (lib:1519-1529).  A (sub-)warp per destination row like agg_rows_kernel;
+// additions are separately rounded in reference order, so STRICT and FAST agree bit for bit.
+namespace {
+
+template <int VEC, int LPR>
+__global__ void __launch_bounds__(256) gine_agg_kernel(const GineAggArgs a)
+{
+    constexpr int ROWS_PER_WARP = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int lg = lane % LPR, sub = lane / LPR;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int64_t warp_stride = (int64_t)gridDim.x * warps_per_block;
+    const float self_scale = __fadd_rn(1.0f, a.eps);   // lib:1522
+    for (int64_t row0 = warp_global * ROWS_PER_WARP; row0 < a.n; row0 += warp_stride * ROWS_PER_WARP) {
+        const int v = (int)row0 + sub;
+        if (v >= a.n) continue;
+        const int deg = __ldg(a.in_deg + v);
+        const int off = __ldg(a.offsets + v);
+        for (int c = lg * VEC; c < a.F; c += LPR * VEC) {
+            Vec<VEC> acc;
+#pragma unroll
+            for (int i = 0; i < VEC; i++) acc.v[i] = 0.0f;
+            for (int k = 0; k < deg; k++) {
+                const int u = __ldg(a.nbr + off + k);
+                const int eid = __ldg(a.edge_index + off + k);
+                Vec<VEC> xu, pe;
+                xu.load(a.x + (size_t)u * a.ldx + c);
+                pe.load(a.proj + (size_t)eid * a.ldp + c);
+#pragma unroll
+                for (int i = 0; i < VEC; i++) {
+                    const float m = __fadd_rn(xu.v[i], pe.v[i]);                  // lib:1603
+                    acc.v[i] = __fadd_rn(acc.v[i], m > 0.0f ? m : 0.0f);         // lib:1606-1610
+                }
+            }
+            Vec<VEC> xs;
+            xs.load(a.x + (size_t)v * a.ldx + c);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) acc.v[i] = __fadd_rn(acc.v[i], __fmul_rn(xs.v[i], self_scale));
+            acc.store(a.out + (size_t)v * a.ldo + c);
+        }
+    }
+}
+
+template <int VEC>
+int launch_gine_lpr(const GineAggArgs &a, int lpr, int grid, cudaStream_t s)
+{
+    switch (lpr) {
+    case 1: gine_agg_kernel<VEC, 1><<<grid, 256, 0, s>>>(a); break;
+    case 2: gine_agg_kernel<VEC, 2><<<grid, 256, 0, s>>>(a); break;
+    case 4: gine_agg_kernel<VEC, 4><<<grid, 256, 0, s>>>(a); break;
+    case 8: gine_agg_kernel<VEC, 8><<<grid, 256, 0, s>>>(a); break;
+    case 16: gine_agg_kernel<VEC, 16><<<grid, 256, 0, s>>>(a); break;
+    default: gine_agg_kernel<VEC, 32><<<grid, 256, 0, s>>>(a); break;
+    }
+    return GNNB_OK;
+}
+
+}  // namespace
+
+int launch_gine_agg(const GineAggArgs &a, cudaStream_t s, int *launches)
+{
+    if (a.n <= 0) return GNNB_OK;
+    const bool v4 = (a.F % 4 == 0) && (a.ldx % 4 == 0) && (a.ldp % 4 == 0) && (a.ldo % 4 == 0) &&
+                    aligned16(a.x) && aligned16(a.proj) && aligned16(a.out);
+    const int vec = v4 ? 4 : 1;
+    int lpr = 1;
+    while (lpr < 32 && lpr * vec < a.F) lpr *= 2;
+    const int rows_per_block = 8 * (32 / lpr);
+    int64_t grid64 = ceil_div64(a.n, rows_per_block);
+    const int64_t cap = (int64_t)kNumSMs * 8 * 4;
+    const int grid = (int)(grid64 < cap ? grid64 : cap);
+    GNNB_TRY(vec == 4 ? launch_gine_lpr<4>(a, lpr, grid, s) : launch_gine_lpr<1>(a, lpr, grid, s));
+    GNNB_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+    return GNNB_OK;
+}
+
 }  // namespace gnnb

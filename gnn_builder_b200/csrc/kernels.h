@@ -64,6 +64,20 @@ struct AggArgs {
 };
 int launch_agg(const AggArgs &a, bool strict, cudaStream_t s, int *launches);
 
+// GINE aggregation (lib:1555-1623): sum_k relu(x[nbr_k] + proj[edge_index_k]) + (1 + eps) x_v
+struct GineAggArgs {
+    const float *x;        // [n][ldx]
+    int ldx, F;
+    const float *proj;     // [E][ldp] projected edge features (edge id order)
+    int ldp;
+    float *out;            // [n][ldo]
+    int ldo;
+    const int32_t *offsets, *nbr, *edge_index, *in_deg;
+    int n;
+    float eps;
+};
+int launch_gine_agg(const GineAggArgs &a, cudaStream_t s, int *launches);
+
 struct PnaAggArgs {
     const float *ab;       // [n][2F]: cols [0,F) = x.W_nbr^T, cols [F,2F) = x.W_self^T + b_pre
     int F;

@@ -3,6 +3,7 @@
 // They exist so that every function of the hot path can be parity-tested in isolation against
 // the reference; each call stages host buffers, runs the same kernels the model path uses on
 // the default stream, and returns when the results are back.
+#include <algorithm>
 #include <vector>
 
 #include "kernels.h"
@@ -318,6 +319,97 @@ extern "C" int gnnb_sage_conv(int num_nodes, int num_edges, const float *x_in, f
     g.second_separate = 1;
     GNNB_TRY(launch_gemm(g, strict, 0, nullptr));
     return st.finish();
+}
+
+// lib:1627-1742 gine_conv: per-edge projection of the edge features (one GEMM over the edges),
+// gather-reduce of relu(x_u + proj_e) in neighbor-table order, then the GIN MLP.
+extern "C" int gnnb_gine_conv(int num_nodes, int num_edges, const float *x_in, float *x_out,
+                              const float *edge_feature_table, const int32_t *edge_list,
+                              const int32_t *neighbor_table_offsets, const int32_t *neighbor_table,
+                              const int32_t *edge_index_table, const int32_t *in_degree_table,
+                              const int32_t *out_degree_table, const float *edge_proj_weight,
+                              const float *edge_proj_bias, const float *mlp_0_weight,
+                              const float *mlp_0_bias, const float *mlp_1_weight,
+                              const float *mlp_1_bias, float gin_eps, int emb_in, int hidden,
+                              int emb_out, int edge_dim, int math)
+{
+    (void)edge_list; (void)out_degree_table;
+    GNNB_REQUIRE(hidden > 0 && edge_dim > 0, "bad hidden / edge feature size");
+    const bool strict = math == GNNB_MATH_STRICT;
+    Stage st;
+    ConvCommon c;
+    GNNB_TRY(stage_conv(st, num_nodes, num_edges, x_in, x_out, neighbor_table_offsets,
+                        neighbor_table, in_degree_table, emb_in, emb_out, &c));
+    const float *ef;
+    const int32_t *eidx;
+    GNNB_TRY(st.in(edge_feature_table, (size_t)num_edges * edge_dim, &ef));
+    GNNB_TRY(st.in(edge_index_table, (size_t)num_edges, &eidx));
+    const float *Wet, *W0t, *W1t, *be, *b0, *b1;
+    int lde, ld0, ld1;
+    GNNB_TRY(pack_weight(st, edge_proj_weight, emb_in, edge_dim, &Wet, &lde));
+    GNNB_TRY(pack_weight(st, mlp_0_weight, hidden, emb_in, &W0t, &ld0));
+    GNNB_TRY(pack_weight(st, mlp_1_weight, emb_out, hidden, &W1t, &ld1));
+    GNNB_TRY(st.in(edge_proj_bias, (size_t)emb_in, &be));
+    GNNB_TRY(st.in(mlp_0_bias, (size_t)hidden, &b0));
+    GNNB_TRY(st.in(mlp_1_bias, (size_t)emb_out, &b1));
+    float *proj, *agg, *hid;
+    const int lda = round_up(emb_in, 4), ldh = round_up(hidden, 4);
+    GNNB_TRY(st.scratch((size_t)std::max(num_edges, 1) * lda, &proj));
+    GNNB_TRY(st.scratch((size_t)num_nodes * lda, &agg));
+    GNNB_TRY(st.scratch((size_t)num_nodes * ldh, &hid));
+    if (num_edges > 0) {
+        GemmArgs ge = simple_gemm(ef, edge_dim, edge_dim, Wet, lde, be, proj, lda, num_edges, emb_in,
+                                  GNNB_ACT_IDENTITY);
+        GNNB_TRY(launch_gemm(ge, strict, 0, nullptr));
+    }
+    GineAggArgs a{};
+    a.x = c.x; a.ldx = emb_in; a.F = emb_in; a.proj = proj; a.ldp = lda; a.out = agg; a.ldo = lda;
+    a.offsets = c.off; a.nbr = c.nbr; a.edge_index = eidx; a.in_deg = c.ind; a.n = num_nodes;
+    a.eps = gin_eps;
+    GNNB_TRY(launch_gine_agg(a, 0, nullptr));
+    GemmArgs g0 = simple_gemm(agg, lda, emb_in, W0t, ld0, b0, hid, ldh, num_nodes, hidden,
+                              GNNB_ACT_RELU);
+    GNNB_TRY(launch_gemm(g0, strict, 0, nullptr));
+    GemmArgs g1 = simple_gemm(hid, ldh, hidden, W1t, ld1, b1, c.y, emb_out, num_nodes, emb_out,
+                              GNNB_ACT_IDENTITY);
+    GNNB_TRY(launch_gemm(g1, strict, 0, nullptr));
+    return st.finish();
+}
+
+// lib:2350-2499 lg_conv (LightGCN propagation, no weights) and lib:2501-2634 simple_conv (plain
+// neighbor sum): the aggregation kernel alone.
+static int agg_only_conv(int mode, int num_nodes, int num_edges, const float *x_in, float *x_out,
+                         const int32_t *offsets, const int32_t *nbr, const int32_t *in_deg, int emb,
+                         int math)
+{
+    Stage st;
+    ConvCommon c;
+    GNNB_TRY(stage_conv(st, num_nodes, num_edges, x_in, x_out, offsets, nbr, in_deg, emb, emb, &c));
+    AggArgs a{};
+    a.mode = mode; a.x = c.x; a.ldx = emb; a.F = emb; a.out = c.y; a.ldo = emb;
+    a.offsets = c.off; a.nbr = c.nbr; a.in_deg = c.ind; a.n = num_nodes;
+    GNNB_TRY(launch_agg(a, math == GNNB_MATH_STRICT, 0, nullptr));
+    return st.finish();
+}
+
+extern "C" int gnnb_lg_conv(int num_nodes, int num_edges, const float *x_in, float *x_out,
+                            const int32_t *edge_list, const int32_t *neighbor_table_offsets,
+                            const int32_t *neighbor_table, const int32_t *in_degree_table,
+                            const int32_t *out_degree_table, int emb, int math)
+{
+    (void)edge_list; (void)out_degree_table;
+    return agg_only_conv(AGG_LG, num_nodes, num_edges, x_in, x_out, neighbor_table_offsets,
+                         neighbor_table, in_degree_table, emb, math);
+}
+
+extern "C" int gnnb_simple_conv(int num_nodes, int num_edges, const float *x_in, float *x_out,
+                                const int32_t *edge_list, const int32_t *neighbor_table_offsets,
+                                const int32_t *neighbor_table, const int32_t *in_degree_table,
+                                const int32_t *out_degree_table, int emb, int math)
+{
+    (void)edge_list; (void)out_degree_table;
+    return agg_only_conv(AGG_SUM, num_nodes, num_edges, x_in, x_out, neighbor_table_offsets,
+                         neighbor_table, in_degree_table, emb, math);
 }
 
 extern "C" int gnnb_pna_conv(int num_nodes, int num_edges, const float *x_in, float *x_out,

@@ -153,6 +153,49 @@ def pna_conv(x, edge_list, neighbor_table_offsets, neighbor_table, in_degree_tab
     return y
 
 
+def gine_conv(x, edge_feature_table, edge_list, neighbor_table_offsets, neighbor_table,
+              edge_index_table, in_degree_table, out_degree_table, edge_proj_weight,
+              edge_proj_bias, mlp_0_weight, mlp_0_bias, mlp_1_weight, mlp_1_bias, gin_eps: float,
+              math: int = FAST):
+    """lib:1627-1742"""
+    we, be, w0, b0, w1, b1 = map(_f32, (edge_proj_weight, edge_proj_bias, mlp_0_weight, mlp_0_bias,
+                                        mlp_1_weight, mlp_1_bias))
+    hid, fi, fo, fe = int(w0.shape[0]), int(w0.shape[1]), int(w1.shape[0]), int(we.shape[1])
+    x, y, n, e, coo, off, nbr, ind, outd = _conv_prologue(
+        x, edge_list, neighbor_table_offsets, neighbor_table, in_degree_table, out_degree_table, fo)
+    ef, eidx = _f32(edge_feature_table), _i32(edge_index_table)
+    _lib.check(_lib.load().gnnb_gine_conv(n, e, _ptr(x), _ptr(y), _ptr(ef), _ptr(coo), _ptr(off),
+                                          _ptr(nbr), _ptr(eidx), _ptr(ind), _ptr(outd), _ptr(we),
+                                          _ptr(be), _ptr(w0), _ptr(b0), _ptr(w1), _ptr(b1),
+                                          float(gin_eps), fi, hid, fo, fe, math))
+    return y
+
+
+def _agg_only(name, x, edge_list, neighbor_table_offsets, neighbor_table, in_degree_table,
+              out_degree_table, math):
+    x = _f32(x)
+    f = int(x.shape[1])
+    x, y, n, e, coo, off, nbr, ind, outd = _conv_prologue(
+        x, edge_list, neighbor_table_offsets, neighbor_table, in_degree_table, out_degree_table, f)
+    _lib.check(getattr(_lib.load(), name)(n, e, _ptr(x), _ptr(y), _ptr(coo), _ptr(off), _ptr(nbr),
+                                          _ptr(ind), _ptr(outd), f, math))
+    return y
+
+
+def lg_conv(x, edge_list, neighbor_table_offsets, neighbor_table, in_degree_table,
+            out_degree_table, math: int = FAST):
+    """lib:2398-2499"""
+    return _agg_only("gnnb_lg_conv", x, edge_list, neighbor_table_offsets, neighbor_table,
+                     in_degree_table, out_degree_table, math)
+
+
+def simple_conv(x, edge_list, neighbor_table_offsets, neighbor_table, in_degree_table,
+                out_degree_table, math: int = FAST):
+    """lib:2564-2634"""
+    return _agg_only("gnnb_simple_conv", x, edge_list, neighbor_table_offsets, neighbor_table,
+                     in_degree_table, out_degree_table, math)
+
+
 def _pool(kind: str, x):
     x = _f32(x)
     n, f = int(x.shape[0]), int(x.shape[1])

@@ -172,6 +172,27 @@ int gnnb_sage_conv(int num_nodes, int num_edges, const float *x_in, float *x_out
                    const int32_t *out_degree_table, const float *neighbor_lin_weight,
                    const float *neighbor_lin_bias, const float *self_lin_weight, int emb_in,
                    int emb_out, int math);
+/* lib:1627-1742 gine_conv: edge features enter through edge_index_table (lib:1126-1166);
+ * edge_feature_table [num_edges][edge_dim] in COO (edge id) order, edge_proj_weight
+ * [emb_in][edge_dim]; then the GIN MLP (hidden, emb_out). */
+int gnnb_gine_conv(int num_nodes, int num_edges, const float *x_in, float *x_out,
+                   const float *edge_feature_table, const int32_t *edge_list,
+                   const int32_t *neighbor_table_offsets, const int32_t *neighbor_table,
+                   const int32_t *edge_index_table, const int32_t *in_degree_table,
+                   const int32_t *out_degree_table, const float *edge_proj_weight,
+                   const float *edge_proj_bias, const float *mlp_0_weight, const float *mlp_0_bias,
+                   const float *mlp_1_weight, const float *mlp_1_bias, float gin_eps, int emb_in,
+                   int hidden, int emb_out, int edge_dim, int math);
+/* lib:2398-2499 lg_conv: y_v = sum_u x_u / sqrt(deg_in(v) deg_in(u)) (no weights, emb_out = emb_in) */
+int gnnb_lg_conv(int num_nodes, int num_edges, const float *x_in, float *x_out,
+                 const int32_t *edge_list, const int32_t *neighbor_table_offsets,
+                 const int32_t *neighbor_table, const int32_t *in_degree_table,
+                 const int32_t *out_degree_table, int emb, int math);
+/* lib:2564-2634 simple_conv: y_v = sum_u x_u */
+int gnnb_simple_conv(int num_nodes, int num_edges, const float *x_in, float *x_out,
+                     const int32_t *edge_list, const int32_t *neighbor_table_offsets,
+                     const int32_t *neighbor_table, const int32_t *in_degree_table,
+                     const int32_t *out_degree_table, int emb, int math);
 /* lib:1891-2157 (transform 2F->F, apply 13F->emb_out, final emb_out->emb_out) */
 int gnnb_pna_conv(int num_nodes, int num_edges, const float *x_in, float *x_out,
                   const int32_t *edge_list, const int32_t *neighbor_table_offsets,

@@ -191,6 +191,50 @@ def test_convs_edge_cases_from_reference_templates(L, orc):
     _conv_all(L, orc, x, coo, n, 2, 8)
 
 
+# ------------------------------------------------------------------------------- gine / lg / simple
+def test_gine_lg_simple_reference_fixture_vs_pyg_golden(L, lib_tb):
+    """the reference's own tests of the three remaining convs (test.cpp:1287-1455, 1728-1919)"""
+    t = lib_tb
+    ef = t.f32("tb_input_edge_features", t.e, 16)
+    y = L.gine_conv(t.x, ef, t.coo, t.offsets, t.nbr, t.eidx, t.in_deg, t.out_deg,
+                    t.f32("tb_gine_edge_proj_weights", 8, 16), t.f32("tb_gine_edge_proj_bias"),
+                    t.f32("tb_gine_mlp_0_weights", 8, 8), t.f32("tb_gine_mlp_0_bias"),
+                    t.f32("tb_gine_mlp_1_weights", 8, 8), t.f32("tb_gine_mlp_1_bias"),
+                    float(t.f32("tb_gine_eps")[0]))
+    assert np.abs(y - t.f32("tb_gine_output", t.n, 8)).max() < 1e-5
+    y = L.lg_conv(t.x, t.coo, t.offsets, t.nbr, t.in_deg, t.out_deg)
+    assert np.abs(y - t.f32("tb_lgconv_output", t.n, 8)).max() < 1e-5
+    y = L.simple_conv(t.x, t.coo, t.offsets, t.nbr, t.in_deg, t.out_deg)
+    assert np.abs(y - t.f32("tb_simple_output", t.n, 8)).max() < 1e-5
+
+
+@pytest.mark.parametrize("n,e,fi,fo,fe", [(1, 0, 8, 8, 4), (2, 3, 8, 16, 16), (100, 534, 8, 8, 16),
+                                          (700, 3000, 128, 128, 32), (300, 2000, 30, 20, 7),
+                                          (5000, 60000, 64, 64, 16)])
+def test_gine_lg_simple_random(L, orc, n, e, fi, fo, fe):
+    rng = np.random.default_rng(n + 3 * e + fi)
+    coo = rand_graph(rng, n, e)
+    if e > 10000:
+        coo[: e // 8, 1] = 5      # a heavy destination row
+    x = rng.uniform(-1, 1, (n, fi)).astype(np.float32)
+    ef = rng.uniform(-1, 1, (e, fe)).astype(np.float32)
+    ind, outd = orc.degree_tables(coo, n)
+    off, nbr, eidx = orc.neighbor_tables(coo, ind, with_edge_index=True)
+    W = lambda *s: rng.uniform(-0.3, 0.3, s).astype(np.float32)  # noqa: E731
+    w = [W(fi, fe), W(fi), W(fo, fi), W(fo), W(fo, fo), W(fo)]
+    ref = orc.gine_conv(x, ef, off, nbr, eidx, ind, *w, 0.2)
+    got = L.gine_conv(x, ef, coo, off, nbr, eidx, ind, outd, *w, 0.2)
+    assert rel_err(got, ref) < TOL
+    assert np.array_equal(L.gine_conv(x, ef, coo, off, nbr, eidx, ind, outd, *w, 0.2, math=L.STRICT), ref)
+    for fn, ofn in ((L.lg_conv, orc.lg_conv), (L.simple_conv, orc.simple_conv)):
+        ref = ofn(x, off, nbr, ind)
+        got = fn(x, coo, off, nbr, ind, outd)
+        with np.errstate(invalid="ignore"):
+            assert np.array_equal(np.isnan(got), np.isnan(ref))
+        assert rel_err(np.nan_to_num(got), np.nan_to_num(ref)) < TOL
+        assert np.array_equal(fn(x, coo, off, nbr, ind, outd, math=L.STRICT), ref, equal_nan=True)
+
+
 @pytest.mark.parametrize("n,e,fi,fo", [(1, 0, 9, 64), (2, 1, 11, 128), (40, 90, 64, 64),
                                        (700, 3000, 128, 128), (300, 900, 80, 80), (50, 200, 5, 12),
                                        (3000, 50000, 32, 16)])
