@@ -9,7 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libgnnb_b200.so"
-SOURCES = ["model.cu", "layers.cu", "tables.cu", "agg.cu", "gemm.cu", "pool.cu", "fused.cu", "fused_tc.cu", "tc_test.cu"]
+SOURCES = ["model.cu", "layers.cu", "tables.cu", "agg.cu", "gemm.cu", "gemm_tc.cu", "pool.cu", "fused.cu", "fused_tc.cu", "tc_test.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

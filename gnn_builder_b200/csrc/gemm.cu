@@ -273,6 +273,7 @@ int launch_gemm(const GemmArgs &g, bool strict, cudaStream_t s, int *launches)
         if (launches) ++*launches;
         return GNNB_OK;
     }
+    if (gemm_tc_supported(g)) return launch_gemm_tc(g, s, launches);
     const int mb = (g.M + BM - 1) / BM;
     if (g.N > 64) {
         dim3 grid(mb, (g.N + 127) / 128);

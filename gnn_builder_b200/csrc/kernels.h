@@ -94,6 +94,8 @@ int launch_pna_agg(const PnaAggArgs &a, cudaStream_t s, int *launches);
 struct GemmArgs {
     const float *A1; int lda1; int K1; const float *W1t; int ldw1;
     const float *A2; int lda2; int K2; const float *W2t; int ldw2;
+    const float *img1, *img2;   // optional tensor-core weight images of W1 / W2 (gemm_tc.cu); when
+                                // present (and FAST math) the GEMM runs on tcgen05, else on the FMA pipe
     int second_separate;        // STRICT only: A2.W2t is a separate bias-free sum added last (SAGE)
     const float *bias;          // [N] or null
     const float *skip; int ldskip;  // added before the activation, or null
@@ -102,6 +104,11 @@ struct GemmArgs {
     int M; int N;
 };
 int launch_gemm(const GemmArgs &g, bool strict, cudaStream_t s, int *launches);
+// gemm_tc.cu: tcgen05 (3xTF32) version of the same contract, for large M
+size_t gemm_tc_image_floats(int K, int N);
+int gemm_tc_build_image(const float *Wt, int ldw, int K, int N, float *img, cudaStream_t s);
+bool gemm_tc_supported(const GemmArgs &g);
+int launch_gemm_tc(const GemmArgs &g, cudaStream_t s, int *launches);
 // Wt[k][n] (ld = ldw) from W[n][k] (reference layout); pads columns n..ldw with zeros
 int launch_transpose_weight(const float *W, float *Wt, int out_size, int in_size, int ldw,
                             cudaStream_t s, int *launches);

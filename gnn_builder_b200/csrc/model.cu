@@ -225,7 +225,7 @@ extern "C" int gnnb_model_destroy(gnnb_model_t *m)
     fused_release(m);
     fused_tc_release(m);
     m->prof.release();
-    DeviceBuf *bufs[] = {&m->weights, &m->st_x, &m->st_coo, &m->st_nptr, &m->st_eptr, &m->st_out,
+    DeviceBuf *bufs[] = {&m->weights, &m->weight_images, &m->st_x, &m->st_coo, &m->st_nptr, &m->st_eptr, &m->st_out,
                          &m->in_deg, &m->out_deg, &m->offsets, &m->nbr, &m->dinv, &m->feat[0],
                          &m->feat[1], &m->agg, &m->hid, &m->wide, &m->pooled, &m->hbuf[0],
                          &m->hbuf[1], &m->pool_tmp, &m->ptr_tmp, &m->tws.keys_in, &m->tws.keys_out,
@@ -361,6 +361,24 @@ extern "C" int gnnb_model_finalize(gnnb_model_t *m)
         lp.c = resolve(L.c, base); lp.d = resolve(L.d, base);
         m->layers.push_back(lp);
     }
+    {   // tensor-core weight images for the layerwise GEMMs (one allocation, built on the device)
+        std::vector<PackedLinear *> all;
+        for (PackedLinear &l : m->head) all.push_back(&l);
+        for (LayerPack &lp : m->layers)
+            for (PackedLinear *l : {&lp.a, &lp.b, &lp.c, &lp.d})
+                if (l->Wt != nullptr && l->in > 0 && l->out > 0) all.push_back(l);
+        size_t total = 0;
+        for (PackedLinear *l : all) total += gemm_tc_image_floats(l->in, l->out);
+        GNNB_TRY(m->weight_images.ensure(std::max<size_t>(total, 1) * sizeof(float)));
+        size_t off = 0;
+        for (PackedLinear *l : all) {
+            float *img = m->weight_images.as<float>() + off;
+            GNNB_TRY(gemm_tc_build_image(l->Wt, l->ldw, l->in, l->out, img, m->stream));
+            l->img = img;
+            off += gemm_tc_image_floats(l->in, l->out);
+        }
+        GNNB_CUDA(cudaStreamSynchronize(m->stream));
+    }
     fused_release(m);
     fused_tc_release(m);
     GNNB_TRY(fused_prepare(m));
@@ -424,7 +442,7 @@ static GemmArgs gemm_args(const float *A, int lda, const PackedLinear &L, float 
                           int act, const float *skip = nullptr, int ldskip = 0)
 {
     GemmArgs g{};
-    g.A1 = A; g.lda1 = lda; g.K1 = L.in; g.W1t = L.Wt; g.ldw1 = L.ldw;
+    g.A1 = A; g.lda1 = lda; g.K1 = L.in; g.W1t = L.Wt; g.ldw1 = L.ldw; g.img1 = L.img;
     g.A2 = nullptr; g.lda2 = 0; g.K2 = 0; g.W2t = nullptr; g.ldw2 = 4;
     g.second_separate = 0;
     g.bias = L.bias; g.skip = skip; g.ldskip = ldskip; g.act = act;
@@ -519,7 +537,7 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
             a.mode = AGG_MEAN;
             { ProfScope ps(m->prof, PROF_AGG, s); GNNB_TRY(launch_agg(a, strict, s, launches)); }
             GemmArgs g = gemm_args(a.out, a.ldo, L.a, dst, ld_out, T, d.gnn_act, skip, cur_ld);
-            g.A2 = cur; g.lda2 = cur_ld; g.K2 = fi; g.W2t = L.b.Wt; g.ldw2 = L.b.ldw;
+            g.A2 = cur; g.lda2 = cur_ld; g.K2 = fi; g.W2t = L.b.Wt; g.ldw2 = L.b.ldw; g.img2 = L.b.img;
             g.second_separate = 1;  // lib:2316-2332
             { ProfScope ps(m->prof, PROF_GEMM, s); GNNB_TRY(launch_gemm(g, strict, s, launches)); }
             break;
@@ -536,7 +554,7 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
             float *hid = m->hid.as<float>();
             GemmArgs g1 = gemm_args(cur, cur_ld, L.b, hid, ld_out, T, GNNB_ACT_IDENTITY);
             g1.bias = L.c.bias;
-            g1.A2 = cat12; g1.lda2 = 12 * fi; g1.K2 = 12 * fi; g1.W2t = L.c.Wt; g1.ldw2 = L.c.ldw;
+            g1.A2 = cat12; g1.lda2 = 12 * fi; g1.K2 = 12 * fi; g1.W2t = L.c.Wt; g1.ldw2 = L.c.ldw; g1.img2 = L.c.img;
             { ProfScope ps(m->prof, PROF_GEMM, s); GNNB_TRY(launch_gemm(g1, false, s, launches)); }   // lib:2149
             GemmArgs g2 = gemm_args(hid, ld_out, L.d, dst, ld_out, T, d.gnn_act, skip, cur_ld);
             { ProfScope ps(m->prof, PROF_GEMM, s); GNNB_TRY(launch_gemm(g2, false, s, launches)); }   // lib:2150

@@ -20,6 +20,7 @@ struct ParamSlot {
 struct PackedLinear {
     const float *Wt = nullptr;
     const float *bias = nullptr;
+    const float *img = nullptr;   // tensor-core weight image (gemm_tc.cu), built at finalize
     int in = 0, out = 0, ldw = 0;
 };
 
@@ -84,6 +85,7 @@ struct gnnb_model {
 
     std::vector<gnnb::ParamSlot> params;
     gnnb::DeviceBuf weights;  // all packed weights, one allocation
+    gnnb::DeviceBuf weight_images;  // tensor-core images of the same linears (layerwise tcgen05 GEMM)
     std::vector<gnnb::LayerPack> layers;
     std::vector<gnnb::PackedLinear> head;
     gnnb::FusedPlan *fused = nullptr;
