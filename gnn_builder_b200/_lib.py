@@ -48,6 +48,7 @@ EXPORTS = [
     "gnnb_gine_conv", "gnnb_lg_conv", "gnnb_simple_conv",
     "gnnb_global_add_pool", "gnnb_global_mean_pool", "gnnb_global_max_pool",
     "gnnb_partition_tables", "gnnb_degree_inv_sqrt", "gnnb_gcn_conv_partition",
+    "gnnb_pool_partial",
     "gnnb_debug_tc_gemm", "gnnb_debug_tc_agg_gemm", "gnnb_debug_tc_mma_rate",
 ]
 
@@ -114,6 +115,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.gnnb_debug_tc_mma_rate.argtypes = [ci, ci, ci, vp]
     lib.gnnb_partition_tables.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]
     lib.gnnb_degree_inv_sqrt.argtypes = [vp, vp, ci, vp]
+    lib.gnnb_pool_partial.argtypes = [vp, C.c_int64, ci, vp, vp]
     lib.gnnb_gcn_conv_partition.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci,
                                             ci, ci, vp]
     _lib = lib

@@ -14,7 +14,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-] + (["-DGNNB_TC_SUBTIMING"] if os.environ.get("GNNB_TC_SUBTIMING") else [])
+] + (["-DGNNB_TC_SUBTIMING"] if os.environ.get("GNNB_TC_SUBTIMING") else []) \
+  + os.environ.get("GNNB_NVCC_EXTRA", "").split()
 
 
 def nvcc() -> str:

@@ -53,9 +53,14 @@ void build_weight_image(const float *W, int N, int n_valid, int K, int ld, int c
 namespace {
 
 constexpr int TM = 128;
-constexpr int NTHREADS = 256;            // worker threads (8 warps; warp 0 also issues the MMAs)
+#ifndef GNNB_TC_WORKERS
+#define GNNB_TC_WORKERS 256
+#endif
+constexpr int NTHREADS = GNNB_TC_WORKERS;   // worker threads (8 or 16 warps; warp 0 also issues the MMAs)
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int CTA_THREADS = NTHREADS + 32;   // + the weight-producer warp
+constexpr int CSTRIDE = 32 * (NWARPS / 4);   // column stride between the 32-column blocks of one warp
+constexpr int NCHALF = NTHREADS / TM;        // staging: threads per row
 constexpr int MAX_LAYERS = 8;
 constexpr int MAX_HEAD = 6;
 constexpr int HEAD_G = 128;      // pooled graphs per head call (one 128-row MMA tile)
@@ -354,7 +359,7 @@ __device__ __forceinline__ void row_pass(uint32_t tmem_src, int ncols, F &&f)
     const int warp = threadIdx.x >> 5;
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
 #pragma unroll 1
-    for (int c0 = (warp >> 2) * 32; c0 < ncols; c0 += 64) {
+    for (int c0 = (warp >> 2) * 32; c0 < ncols; c0 += CSTRIDE) {
         uint32_t r[32];
         SUBT(0, tc::tmem_ld32_nowait(tmem_src + lane_base + (uint32_t)c0, r); tc::tmem_ld_wait());
         SUBT(1, f(c0, lane_base, r));
@@ -407,7 +412,7 @@ __device__ __forceinline__ void cvt_self(uint32_t tmem_base, const unsigned char
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = 32 * (warp & 3) + lane;
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-    for (int c0 = (warp >> 2) * 32; c0 < kp; c0 += 64) {
+    for (int c0 = (warp >> 2) * 32; c0 < kp; c0 += CSTRIDE) {
         float v[32];
 #pragma unroll
         for (int j8 = 0; j8 < 4; j8++) {
@@ -561,7 +566,7 @@ __device__ __forceinline__ void epilogue_global(uint32_t tmem_base, int N, const
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     const int npad = (N + 31) & ~31;
     float *grow = row < n_rows ? gout + (size_t)gids[row] * ldg : nullptr;
-    for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += 64) {
+    for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += CSTRIDE) {
         float v[32];
         tc::tmem_ld32(tmem_base + TM_D + lane_base + (uint32_t)c0, v);
         if (grow == nullptr) continue;
@@ -572,7 +577,7 @@ __device__ __forceinline__ void epilogue_global(uint32_t tmem_base, int N, const
 }
 
 // barrier over the 256 worker threads (the producer warp never joins it)
-__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(NTHREADS) : "memory"); }
 
 #define GNNB_WAIT_DONE()                                                            \
     do {                                                                            \
@@ -605,7 +610,7 @@ __device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, uint32_t
             if (j == 0) {  // A chunk: pending[:, 128c : 128c + K) -> (hi, lo), zero padded
                 const int kp = L.KA * tc::ATOM_K;
                 const float *src = pending + (size_t)row * PLD + c * 128;
-                for (int c0 = (warp >> 2) * 32; c0 < kp; c0 += 64) {
+                for (int c0 = (warp >> 2) * 32; c0 < kp; c0 += CSTRIDE) {
                     float v[32];
 #pragma unroll
                     for (int j4 = 0; j4 < 8; j4++) {
@@ -758,7 +763,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
                 const float *src = p.x + (size_t)(cur_row0 + r_own) * F;
 #pragma unroll
                 for (int q = 0; q < 2; q++) {
-                    const int c = (c_half + 2 * q) * 8;
+                    const int c = (c_half + NCHALF * q) * 8;
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                         xv[q][j] = (r_own < rows && c + j < F) ? __ldg(src + c + j) : 0.0f;
@@ -819,7 +824,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
                 const float *src = p.x + (size_t)(cur_row0 + r_own) * F;
 #pragma unroll
                 for (int q = 0; q < 2; q++) {
-                    const int c = (c_half + 2 * q) * 8;
+                    const int c = (c_half + NCHALF * q) * 8;
                     if (c < kp0) {
                         float o[8];
 #pragma unroll
@@ -830,7 +835,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
                         store_row8(XP, r_own, c, o);
                     }
                 }
-                for (int c = (c_half + 4) * 8; c < kp0; c += 16) {   // in_dim > 32
+                for (int c = (c_half + 2 * NCHALF) * 8; c < kp0; c += 8 * NCHALF) {   // in_dim > 32 (16 NCHALF)
                     float o[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++) {

@@ -4,6 +4,7 @@
 // the reference; each call stages host buffers, runs the same kernels the model path uses on
 // the default stream, and returns when the results are back.
 #include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "kernels.h"
@@ -56,6 +57,14 @@ class Stage {
         *dev = static_cast<T *>(d);
         return GNNB_OK;
     }
+    // tensor-core weight images built by pack_weight, looked up by the packed-weight pointer
+    void add_image(const float *Wt, const float *img) { images_.push_back({Wt, img}); }
+    const float *image_of(const float *Wt) const
+    {
+        for (const auto &p : images_)
+            if (p.first == Wt) return p.second;
+        return nullptr;
+    }
     int finish()
     {
         GNNB_CUDA(cudaDeviceSynchronize());
@@ -67,6 +76,7 @@ class Stage {
     struct Back { void *host; void *dev; size_t bytes; };
     std::vector<void *> owned_;
     std::vector<Back> back_;
+    std::vector<std::pair<const float *, const float *>> images_;
 };
 
 struct TempWs {
@@ -89,7 +99,19 @@ int pack_weight(Stage &st, const float *W, int out, int in, const float **Wt, in
     GNNB_TRY(st.scratch((size_t)in * *ldw, &t));
     GNNB_TRY(launch_transpose_weight(dW, t, out, in, *ldw, 0, nullptr));
     *Wt = t;
+    float *img;   // the same weight as a tensor-core image (used by the GEMM when M is large)
+    GNNB_TRY(st.scratch(gemm_tc_image_floats(in, out), &img));
+    GNNB_TRY(gemm_tc_build_image(t, *ldw, in, out, img, 0));
+    st.add_image(t, img);
     return GNNB_OK;
+}
+
+// launch_gemm with the tensor-core images of the staged weights attached
+int stage_gemm(const Stage &st, GemmArgs g, bool strict)
+{
+    g.img1 = st.image_of(g.W1t);
+    g.img2 = g.W2t != nullptr ? st.image_of(g.W2t) : nullptr;
+    return launch_gemm(g, strict, 0, nullptr);
 }
 
 GemmArgs simple_gemm(const float *A, int lda, int K, const float *Wt, int ldw, const float *bias,
@@ -201,7 +223,7 @@ extern "C" int gnnb_linear(const float *x, float *y, const float *weight, const 
     GNNB_TRY(pack_weight(st, weight, out_size, in_size, &Wt, &ldw));
     GemmArgs g = simple_gemm(dx, in_size, in_size, Wt, ldw, db, dy, out_size, rows, out_size,
                              GNNB_ACT_IDENTITY);
-    GNNB_TRY(launch_gemm(g, math == GNNB_MATH_STRICT, 0, nullptr));
+    GNNB_TRY(stage_gemm(st, g, math == GNNB_MATH_STRICT));
     return st.finish();
 }
 
@@ -246,7 +268,7 @@ extern "C" int gnnb_gcn_conv(int num_nodes, int num_edges, const float *x_in, fl
     GNNB_TRY(launch_agg(a, strict, 0, nullptr));
     GemmArgs g = simple_gemm(agg, lda, emb_in, Wt, ldw, db, c.y, emb_out, num_nodes, emb_out,
                              GNNB_ACT_IDENTITY);
-    GNNB_TRY(launch_gemm(g, strict, 0, nullptr));
+    GNNB_TRY(stage_gemm(st, g, strict));
     return st.finish();
 }
 
@@ -281,10 +303,10 @@ extern "C" int gnnb_gin_conv(int num_nodes, int num_edges, const float *x_in, fl
     GNNB_TRY(launch_agg(a, strict, 0, nullptr));
     GemmArgs g0 = simple_gemm(agg, lda, emb_in, W0t, ld0, b0, hid, ldh, num_nodes, hidden,
                               GNNB_ACT_RELU);
-    GNNB_TRY(launch_gemm(g0, strict, 0, nullptr));
+    GNNB_TRY(stage_gemm(st, g0, strict));
     GemmArgs g1 = simple_gemm(hid, ldh, hidden, W1t, ld1, b1, c.y, emb_out, num_nodes, emb_out,
                               GNNB_ACT_IDENTITY);
-    GNNB_TRY(launch_gemm(g1, strict, 0, nullptr));
+    GNNB_TRY(stage_gemm(st, g1, strict));
     return st.finish();
 }
 
@@ -317,7 +339,7 @@ extern "C" int gnnb_sage_conv(int num_nodes, int num_edges, const float *x_in, f
                              GNNB_ACT_IDENTITY);
     g.A2 = c.x; g.lda2 = emb_in; g.K2 = emb_in; g.W2t = Wrt; g.ldw2 = ldr;
     g.second_separate = 1;
-    GNNB_TRY(launch_gemm(g, strict, 0, nullptr));
+    GNNB_TRY(stage_gemm(st, g, strict));
     return st.finish();
 }
 
@@ -360,7 +382,7 @@ extern "C" int gnnb_gine_conv(int num_nodes, int num_edges, const float *x_in, f
     if (num_edges > 0) {
         GemmArgs ge = simple_gemm(ef, edge_dim, edge_dim, Wet, lde, be, proj, lda, num_edges, emb_in,
                                   GNNB_ACT_IDENTITY);
-        GNNB_TRY(launch_gemm(ge, strict, 0, nullptr));
+        GNNB_TRY(stage_gemm(st, ge, strict));
     }
     GineAggArgs a{};
     a.x = c.x; a.ldx = emb_in; a.F = emb_in; a.proj = proj; a.ldp = lda; a.out = agg; a.ldo = lda;
@@ -369,10 +391,10 @@ extern "C" int gnnb_gine_conv(int num_nodes, int num_edges, const float *x_in, f
     GNNB_TRY(launch_gine_agg(a, 0, nullptr));
     GemmArgs g0 = simple_gemm(agg, lda, emb_in, W0t, ld0, b0, hid, ldh, num_nodes, hidden,
                               GNNB_ACT_RELU);
-    GNNB_TRY(launch_gemm(g0, strict, 0, nullptr));
+    GNNB_TRY(stage_gemm(st, g0, strict));
     GemmArgs g1 = simple_gemm(hid, ldh, hidden, W1t, ld1, b1, c.y, emb_out, num_nodes, emb_out,
                               GNNB_ACT_IDENTITY);
-    GNNB_TRY(launch_gemm(g1, strict, 0, nullptr));
+    GNNB_TRY(stage_gemm(st, g1, strict));
     return st.finish();
 }
 
@@ -463,7 +485,7 @@ extern "C" int gnnb_pna_conv(int num_nodes, int num_edges, const float *x_in, fl
     GNNB_TRY(st.scratch((size_t)n * 12 * F + 4, &cat12));
     GNNB_TRY(st.scratch((size_t)n * ld_o, &hid));
     GemmArgs g0 = simple_gemm(c.x, F, F, d_wab, ld_ab, d_bab, ab, 2 * F, n, 2 * F, GNNB_ACT_IDENTITY);
-    GNNB_TRY(launch_gemm(g0, false, 0, nullptr));
+    GNNB_TRY(stage_gemm(st, g0, false));
     PnaAggArgs pa{};
     pa.ab = ab; pa.F = F; pa.cat12 = cat12; pa.offsets = c.off; pa.nbr = c.nbr; pa.in_deg = c.ind;
     pa.n = n; pa.delta = pna_avg_degree_log;
@@ -471,10 +493,10 @@ extern "C" int gnnb_pna_conv(int num_nodes, int num_edges, const float *x_in, fl
     GemmArgs g1 = simple_gemm(c.x, F, F, d_wself, ld_o, d_bpost, hid, ld_o, n, emb_out,
                               GNNB_ACT_IDENTITY);
     g1.A2 = cat12; g1.lda2 = 12 * F; g1.K2 = 12 * F; g1.W2t = d_wagg; g1.ldw2 = ld_o;
-    GNNB_TRY(launch_gemm(g1, false, 0, nullptr));
+    GNNB_TRY(stage_gemm(st, g1, false));
     GemmArgs g2 = simple_gemm(hid, ld_o, emb_out, Wlint, ldlin, d_blin, c.y, emb_out, n, emb_out,
                               GNNB_ACT_IDENTITY);
-    GNNB_TRY(launch_gemm(g2, false, 0, nullptr));
+    GNNB_TRY(stage_gemm(st, g2, false));
     return st.finish();
 }
 
@@ -505,7 +527,8 @@ extern "C" int gnnb_global_max_pool(int num_nodes, int num_edges, const float *x
 namespace {
 struct PartitionCache {
     TableWorkspace ws;
-    DeviceBuf wt, agg;
+    DeviceBuf wt, img, agg, pool_tmp, pool_ptr;
+    int64_t pool_n = -1;
     const int32_t *heavy_key = nullptr;
     int heavy_n = 0, n_heavy = 0, slices = 0;
 };
@@ -552,6 +575,9 @@ extern "C" int gnnb_gcn_conv_partition(int n_local, int row_begin, int n_total, 
     GNNB_TRY(g_part.wt.ensure(sizeof(float) * (size_t)emb_in * ldw));
     GNNB_TRY(g_part.agg.ensure(sizeof(float) * (size_t)n_local * lda));
     GNNB_TRY(launch_transpose_weight(weight, g_part.wt.as<float>(), emb_out, emb_in, ldw, s, nullptr));
+    // tensor-core image of the same weight (two tiny kernels per call; the GEMM then runs on tcgen05)
+    GNNB_TRY(g_part.img.ensure(sizeof(float) * gemm_tc_image_floats(emb_in, emb_out)));
+    GNNB_TRY(gemm_tc_build_image(g_part.wt.as<float>(), ldw, emb_in, emb_out, g_part.img.as<float>(), s));
     if (g_part.heavy_key != in_degree_local || g_part.heavy_n != n_local) {
         GNNB_TRY(find_heavy_rows(in_degree_local, n_local, kHeavyThreshold, g_part.ws,
                                  &g_part.n_heavy, s, nullptr));
@@ -570,6 +596,28 @@ extern "C" int gnnb_gcn_conv_partition(int n_local, int row_begin, int n_total, 
     GemmArgs g = simple_gemm(a.out, lda, emb_in, g_part.wt.as<float>(), ldw, bias, y_local, emb_out,
                              n_local, emb_out, act);
     g.skip = skip_local; g.ldskip = emb_out;
+    g.img1 = g_part.img.as<float>();
     GNNB_TRY(launch_gemm(g, false, s, nullptr));
     return GNNB_OK;
+}
+
+// Column-wise sum and max over the n rows of x[n][F] (device pointers, asynchronous on `stream`):
+// the per-rank partial of global_add/mean/max_pool (lib:2709-2803) for a row-partitioned graph;
+// out[0..F) = sums, out[F..2F) = maxima (0 for n = 0).  The ranks combine them with all_reduce.
+extern "C" int gnnb_pool_partial(const float *x, int64_t n, int F, float *out, void *stream)
+{
+    GNNB_REQUIRE(n >= 0 && F > 0 && out != nullptr, "bad arguments");
+    GNNB_REQUIRE(n == 0 || (is_device_pointer(x) && is_device_pointer(out)),
+                 "gnnb_pool_partial takes device pointers");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (g_part.pool_n != n) {
+        GNNB_TRY(g_part.pool_ptr.ensure(2 * sizeof(int64_t)));
+        const int64_t h[2] = {0, n};
+        GNNB_CUDA(cudaMemcpyAsync(g_part.pool_ptr.ptr, h, sizeof(h), cudaMemcpyHostToDevice, s));
+        GNNB_CUDA(cudaStreamSynchronize(s));   // h is a stack variable
+        g_part.pool_n = n;
+    }
+    const int pools[2] = {GNNB_POOL_ADD, GNNB_POOL_MAX};
+    return launch_pool(x, F, F, g_part.pool_ptr.as<int64_t>(), 0, 1, n, pools, 2, out, g_part.pool_tmp, s,
+                       nullptr);
 }

@@ -66,18 +66,39 @@ __global__ void __launch_bounds__(128) pool_kernel(const PoolArgs a)
     }
 }
 
-__global__ void __launch_bounds__(128) pool_combine_kernel(const PoolArgs a)
+// Partials of one graph are combined by a CTA of 8 groups x 128 feature lanes: group q walks the
+// splits q, q + 8, ... (independent loads, short serial chain), the 8 group results are then added
+// in group order through shared memory, so the result is deterministic.
+constexpr int COMBINE_GROUPS = 8;
+__global__ void __launch_bounds__(128 * COMBINE_GROUPS) pool_combine_kernel(const PoolArgs a)
 {
+    __shared__ float s_sum[COMBINE_GROUPS][128], s_max[COMBINE_GROUPS][128];
+    const int fl = threadIdx.x & 127, grp = threadIdx.x >> 7;
     for (int g = blockIdx.x; g < a.n_graphs; g += gridDim.x) {
         const int64_t n = __ldg(a.node_ptr + g + 1) - __ldg(a.node_ptr + g);
-        for (int f = threadIdx.x; f < a.F; f += blockDim.x) {
+        for (int f0 = 0; f0 < a.F; f0 += 128) {
+            const int f = f0 + fl;
             float sum = 0.0f, mx = -INFINITY;
-            for (int s = 0; s < a.splits; s++) {
-                const float *p = a.partial + ((size_t)g * a.splits + s) * 2 * a.F;
-                sum += p[f];
-                mx = fmaxf(mx, p[a.F + f]);
+            if (f < a.F) {
+                for (int sp = grp; sp < a.splits; sp += COMBINE_GROUPS) {
+                    const float *p = a.partial + ((size_t)g * a.splits + sp) * 2 * a.F;
+                    sum += p[f];
+                    mx = fmaxf(mx, p[a.F + f]);
+                }
             }
-            write_pools(a, g, f, sum, mx, n);
+            s_sum[grp][fl] = sum;
+            s_max[grp][fl] = mx;
+            __syncthreads();
+            if (grp == 0 && f < a.F) {
+                float ts = 0.0f, tm = -INFINITY;
+#pragma unroll
+                for (int q = 0; q < COMBINE_GROUPS; q++) {
+                    ts += s_sum[q][fl];
+                    tm = fmaxf(tm, s_max[q][fl]);
+                }
+                write_pools(a, g, f, ts, tm, n);
+            }
+            __syncthreads();
         }
     }
 }
@@ -125,7 +146,7 @@ int launch_pool(const float *x, int ldx, int F, const int64_t *node_ptr, int64_t
     GNNB_CUDA(cudaGetLastError());
     if (launches) ++*launches;
     if (splits > 1) {
-        pool_combine_kernel<<<gx, 128, 0, s>>>(a);
+        pool_combine_kernel<<<gx, 128 * COMBINE_GROUPS, 0, s>>>(a);
         GNNB_CUDA(cudaGetLastError());
         if (launches) ++*launches;
     }

@@ -141,7 +141,11 @@ class CudaBackend:
         return y
 
     def pool_partial(self, x_local):
-        return x_local.sum(0), x_local.max(0).values if x_local.shape[0] else x_local.sum(0)
+        n, f = int(x_local.shape[0]), int(x_local.shape[1])
+        out = self.empty((2, f))
+        self._lib.check(self.lib.gnnb_pool_partial(self._p(x_local.contiguous()), n, f, self._p(out),
+                                                   self._stream()))
+        return out[0], out[1]
 
     def head(self, pooled, linears, mlp_act, out_act):
         from . import layers

@@ -224,6 +224,11 @@ int gnnb_gcn_conv_partition(int n_local, int row_begin, int n_total, int num_edg
                             const float *dinv_full, const float *weight, const float *bias,
                             const float *skip_local, int emb_in, int emb_out, int act, void *stream);
 
+/* Per-rank partial of the global pools for a row-partitioned graph: out[0..F) = column sums,
+ * out[F..2F) = column maxima of x[n][F] (lib:2709-2803; device pointers, asynchronous on stream).
+ * The ranks combine them with all_reduce(sum) / all_reduce(max). */
+int gnnb_pool_partial(const float *x, int64_t n, int F, float *out, void *stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------- */
 /* One-CTA tensor-core GEMM C[128][N] = A[128][K] . W[N][K]^T (tcgen05, 3xTF32) built from the
  * same primitives as the fused kernel's node transform; host buffers; K <= 128, N % 16 == 0. */

@@ -72,7 +72,11 @@ def test_tables_device_pointers(L, orc):
 
 # ------------------------------------------------------------------------------- linear / act
 @pytest.mark.parametrize("rows,fi,fo", [(1, 10, 20), (7, 9, 64), (300, 128, 128), (129, 384, 64),
-                                        (64, 64, 19), (33, 1040, 80), (5, 3, 1)])
+                                        (64, 64, 19), (33, 1040, 80), (5, 3, 1),
+                                        # >= 512 rows: the tcgen05 (3xTF32) GEMM of gemm_tc.cu
+                                        (512, 128, 128), (5000, 128, 128), (4099, 1040, 80),
+                                        (3001, 11, 160), (7777, 80, 19), (1000, 33, 8),
+                                        (20000, 384, 64), (600, 200, 192)])
 def test_linear(L, orc, rows, fi, fo):
     rng = np.random.default_rng(rows * fi + fo)
     x = rng.uniform(-1, 1, (rows, fi)).astype(np.float32)
