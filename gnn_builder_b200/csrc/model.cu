@@ -691,47 +691,69 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
     const gnnb_model_desc &d = m->d;
     cudaStream_t s = m->stream;
     const bool dev = is_device_pointer(node_ptr);
-    // host copies of the offsets (needed for validation, path choice and chunking)
-    std::vector<int64_t> hn((size_t)n_graphs + 1), he((size_t)n_graphs + 1);
+    // the offsets on the host (validation, path choice, chunking): host arrays are used in place
+    std::vector<int64_t> hn_copy, he_copy;
+    const int64_t *hn = node_ptr, *he = edge_ptr;
     if (dev) {
-        GNNB_CUDA(cudaMemcpy(hn.data(), node_ptr, hn.size() * 8, cudaMemcpyDeviceToHost));
-        GNNB_CUDA(cudaMemcpy(he.data(), edge_ptr, he.size() * 8, cudaMemcpyDeviceToHost));
-    } else {
-        std::memcpy(hn.data(), node_ptr, hn.size() * 8);
-        std::memcpy(he.data(), edge_ptr, he.size() * 8);
-    }
-    int64_t max_n = 0, max_e = 0;
-    for (int g = 0; g < n_graphs; g++) {
-        const int64_t n = hn[g + 1] - hn[g], e = he[g + 1] - he[g];
-        GNNB_REQUIRE(n >= 0 && e >= 0, "node_ptr/edge_ptr must be non-decreasing");
-        max_n = std::max(max_n, n);
-        max_e = std::max(max_e, e);
+        hn_copy.resize((size_t)n_graphs + 1);
+        he_copy.resize((size_t)n_graphs + 1);
+        GNNB_CUDA(cudaMemcpy(hn_copy.data(), node_ptr, hn_copy.size() * 8, cudaMemcpyDeviceToHost));
+        GNNB_CUDA(cudaMemcpy(he_copy.data(), edge_ptr, he_copy.size() * 8, cudaMemcpyDeviceToHost));
+        hn = hn_copy.data();
+        he = he_copy.data();
     }
     GNNB_REQUIRE(hn[0] == 0 && he[0] == 0, "node_ptr[0] and edge_ptr[0] must be 0");
-    if (d.max_nodes > 0) GNNB_REQUIRE(max_n <= d.max_nodes, "graph exceeds max_nodes");
-    if (d.max_edges > 0) GNNB_REQUIRE(max_e <= d.max_edges, "graph exceeds max_edges");
-    GNNB_REQUIRE(max_n < (1ll << 31) && max_e < (1ll << 31), "graph too large");
     const int64_t T = hn[n_graphs], E = he[n_graphs];
+    GNNB_REQUIRE(T >= 0 && E >= 0 && T < (1ll << 40) && E < (1ll << 40), "bad node_ptr/edge_ptr totals");
     GNNB_REQUIRE(T == 0 || x != nullptr, "x is null");
     GNNB_REQUIRE(E == 0 || edge_list != nullptr, "edge_list is null");
+    // validation of graphs [a, b): offsets non-decreasing, capacities respected; updates the maxima
+    int64_t max_n = 0, max_e = 0;
+    auto scan = [&](int a, int b) -> int {
+        for (int g = a; g < b; g++) {
+            const int64_t n = hn[g + 1] - hn[g], e = he[g + 1] - he[g];
+            GNNB_REQUIRE(n >= 0 && e >= 0, "node_ptr/edge_ptr must be non-decreasing");
+            max_n = std::max(max_n, n);
+            max_e = std::max(max_e, e);
+        }
+        if (d.max_nodes > 0) GNNB_REQUIRE(max_n <= d.max_nodes, "graph exceeds max_nodes");
+        if (d.max_edges > 0) GNNB_REQUIRE(max_e <= d.max_edges, "graph exceeds max_edges");
+        GNNB_REQUIRE(max_n < (1ll << 31) && max_e < (1ll << 31), "graph too large");
+        return GNNB_OK;
+    };
 
     // ---- host buffers + tensor-core fused kernel: chunked ingest pipeline.  The batch is cut into
-    // chunks of graphs; chunk k+1 is copied in (h2d stream) while chunk k computes (compute stream)
-    // and chunk k-1's outputs are copied out (d2h stream), through double-buffered chunk staging.
-    // End to end the step then costs max(PCIe, kernel) instead of their sum.
+    // chunks of graphs; chunk k+1 is validated and copied in (h2d stream) while chunk k computes
+    // (compute stream) and chunk k-1's outputs are copied out (d2h stream), through double-buffered
+    // chunk staging.  End to end the step then costs max(PCIe, kernel) instead of their sum, and the
+    // host-side scan of the offsets hides behind the GPU as well.  The choice is optimistic (it
+    // assumes every graph fits a tile); a chunk that does not, a capacity overflow or non-finite
+    // activations send the whole batch to the regular path below.
+    bool scanned_all = false;
     if (!dev) {
         int path0, kernel0;
-        GNNB_TRY(choose_path(m, (int)max_n, (int)max_e, &path0, &kernel0));
+        GNNB_TRY(choose_path(m, 1, 1, &path0, &kernel0));
         if (path0 == GNNB_PATH_FUSED && kernel0 == 3 && getenv("GNNB_NO_INGEST_PIPELINE") == nullptr) {
-            int chunk_graphs = 32768;
+            // chunk boundaries: a short ramp (4k, 8k, 16k, 32k graphs) so that the first copy-in is
+            // brief, then large chunks (fewer launches, smaller per-launch tails)
+            int chunk_graphs = 65536;
             if (const char *e = getenv("GNNB_INGEST_CHUNK_GRAPHS")) chunk_graphs = std::max(1024, atoi(e));
-            const int n_chunks = (n_graphs + chunk_graphs - 1) / chunk_graphs;
-            int64_t max_cn = 1, max_ce = 1;
-            for (int k = 0; k < n_chunks; k++) {
-                const int a = k * chunk_graphs, b = std::min(n_graphs, a + chunk_graphs);
-                max_cn = std::max(max_cn, hn[b] - hn[a]);
-                max_ce = std::max(max_ce, he[b] - he[a]);
+            std::vector<int> cb{0};
+            for (int sz = 4096; cb.back() < n_graphs;) {
+                cb.push_back(std::min(n_graphs, cb.back() + std::min(sz, chunk_graphs)));
+                if (sz < chunk_graphs) sz *= 2;
             }
+            const int n_chunks = (int)cb.size() - 1;
+            int64_t max_cn = 1, max_ce = 1;
+            bool sane = true;
+            for (int k = 0; k < n_chunks; k++) {
+                const int a = cb[k], b = cb[k + 1];
+                const int64_t cn = hn[b] - hn[a], ce = he[b] - he[a];
+                sane = sane && cn >= 0 && ce >= 0 && cn <= T && ce <= E;
+                max_cn = std::max(max_cn, cn);
+                max_ce = std::max(max_ce, ce);
+            }
+            GNNB_REQUIRE(sane, "node_ptr/edge_ptr must be non-decreasing");
             for (int i = 0; i < 2; i++) {
                 GNNB_TRY(m->ch_x[i].ensure(sizeof(float) * (size_t)max_cn * d.in_dim));
                 GNNB_TRY(m->ch_coo[i].ensure(sizeof(int32_t) * 2 * (size_t)max_ce));
@@ -743,61 +765,84 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
             m->last_launches = 0;
             m->last_path = GNNB_PATH_FUSED;
             m->last_kernel = 3;
+            int rc = GNNB_OK;
+            bool too_big = false;
             {
                 ProfScope ps(m->prof, PROF_FUSED, s);
-                for (int k = 0; k < n_chunks; k++) {
-                    const int a = k * chunk_graphs, b = std::min(n_graphs, a + chunk_graphs), bi = k & 1;
+                for (int k = 0; k < n_chunks && rc == GNNB_OK; k++) {
+                    const int a = cb[k], b = cb[k + 1], bi = k & 1;
+                    rc = scan(a, b);
+                    if (rc != GNNB_OK) break;
+                    if (!fused_tc_supports(m, (int)max_n, (int)max_e)) { too_big = true; break; }
                     const int64_t cn = hn[b] - hn[a], ce = he[b] - he[a];
-                    if (k >= 2) GNNB_CUDA(cudaStreamWaitEvent(m->h2d_stream, m->ev_done[bi], 0));
-                    if (cn > 0)
-                        GNNB_CUDA(cudaMemcpyAsync(m->ch_x[bi].ptr, x + (size_t)hn[a] * d.in_dim,
-                                                  sizeof(float) * (size_t)cn * d.in_dim,
+                    auto issue = [&]() -> int {
+                        if (k >= 2) GNNB_CUDA(cudaStreamWaitEvent(m->h2d_stream, m->ev_done[bi], 0));
+                        if (cn > 0)
+                            GNNB_CUDA(cudaMemcpyAsync(m->ch_x[bi].ptr, x + (size_t)hn[a] * d.in_dim,
+                                                      sizeof(float) * (size_t)cn * d.in_dim,
+                                                      cudaMemcpyHostToDevice, m->h2d_stream));
+                        if (ce > 0)
+                            GNNB_CUDA(cudaMemcpyAsync(m->ch_coo[bi].ptr, edge_list + 2 * (size_t)he[a],
+                                                      sizeof(int32_t) * 2 * (size_t)ce, cudaMemcpyHostToDevice,
+                                                      m->h2d_stream));
+                        GNNB_CUDA(cudaMemcpyAsync(m->ch_nptr[bi].ptr, node_ptr + a, 8 * (size_t)(b - a + 1),
                                                   cudaMemcpyHostToDevice, m->h2d_stream));
-                    if (ce > 0)
-                        GNNB_CUDA(cudaMemcpyAsync(m->ch_coo[bi].ptr, edge_list + 2 * (size_t)he[a],
-                                                  sizeof(int32_t) * 2 * (size_t)ce, cudaMemcpyHostToDevice,
-                                                  m->h2d_stream));
-                    GNNB_CUDA(cudaMemcpyAsync(m->ch_nptr[bi].ptr, node_ptr + a, 8 * (size_t)(b - a + 1),
-                                              cudaMemcpyHostToDevice, m->h2d_stream));
-                    GNNB_CUDA(cudaMemcpyAsync(m->ch_eptr[bi].ptr, edge_ptr + a, 8 * (size_t)(b - a + 1),
-                                              cudaMemcpyHostToDevice, m->h2d_stream));
-                    GNNB_CUDA(cudaEventRecord(m->ev_h2d[bi], m->h2d_stream));
-                    GNNB_CUDA(cudaStreamWaitEvent(s, m->ev_h2d[bi], 0));
-                    // the offsets stay absolute (relative to the whole batch): rebase the data pointers
-                    const float *xb = m->ch_x[bi].as<float>() - (size_t)hn[a] * d.in_dim;
-                    const int32_t *cb = m->ch_coo[bi].as<int32_t>() - 2 * (size_t)he[a];
-                    GNNB_TRY(fused_tc_run(m, xb, cb, m->ch_nptr[bi].as<int64_t>(), m->ch_eptr[bi].as<int64_t>(),
-                                          b - a, cn, (int)max_n, dout_all + (size_t)a * d.mlp_out, s,
-                                          &m->last_launches, k == 0));
-                    GNNB_CUDA(cudaEventRecord(m->ev_done[bi], s));
-                    GNNB_CUDA(cudaStreamWaitEvent(m->d2h_stream, m->ev_done[bi], 0));
-                    GNNB_CUDA(cudaMemcpyAsync(out + (size_t)a * d.mlp_out, dout_all + (size_t)a * d.mlp_out,
-                                              sizeof(float) * (size_t)(b - a) * d.mlp_out,
-                                              cudaMemcpyDeviceToHost, m->d2h_stream));
+                        GNNB_CUDA(cudaMemcpyAsync(m->ch_eptr[bi].ptr, edge_ptr + a, 8 * (size_t)(b - a + 1),
+                                                  cudaMemcpyHostToDevice, m->h2d_stream));
+                        GNNB_CUDA(cudaEventRecord(m->ev_h2d[bi], m->h2d_stream));
+                        GNNB_CUDA(cudaStreamWaitEvent(s, m->ev_h2d[bi], 0));
+                        // the offsets stay absolute (relative to the whole batch): rebase the data pointers
+                        const float *xb = m->ch_x[bi].as<float>() - (size_t)hn[a] * d.in_dim;
+                        const int32_t *cb = m->ch_coo[bi].as<int32_t>() - 2 * (size_t)he[a];
+                        GNNB_TRY(fused_tc_run(m, xb, cb, m->ch_nptr[bi].as<int64_t>(),
+                                              m->ch_eptr[bi].as<int64_t>(), b - a, cn, (int)max_n,
+                                              dout_all + (size_t)a * d.mlp_out, s, &m->last_launches, k == 0));
+                        GNNB_CUDA(cudaEventRecord(m->ev_done[bi], s));
+                        GNNB_CUDA(cudaStreamWaitEvent(m->d2h_stream, m->ev_done[bi], 0));
+                        GNNB_CUDA(cudaMemcpyAsync(out + (size_t)a * d.mlp_out, dout_all + (size_t)a * d.mlp_out,
+                                                  sizeof(float) * (size_t)(b - a) * d.mlp_out,
+                                                  cudaMemcpyDeviceToHost, m->d2h_stream));
+                        return GNNB_OK;
+                    };
+                    rc = issue();
                 }
             }
-            GNNB_CUDA(cudaStreamSynchronize(s));
-            GNNB_CUDA(cudaStreamSynchronize(m->d2h_stream));
+            // drain whatever was issued before looking at the outcome
+            cudaStreamSynchronize(m->h2d_stream);
+            cudaStreamSynchronize(s);
+            cudaStreamSynchronize(m->d2h_stream);
+            if (rc != GNNB_OK) return rc;
             int status = 0;
-            GNNB_TRY(fused_any_status(m, &status));
-            if (status == 2) {
-                set_error("edge_list holds a node index outside its graph");
-                return GNNB_ERR_INVALID;
+            if (!too_big) {
+                scanned_all = true;
+                GNNB_TRY(fused_any_status(m, &status));
+                if (status == 2) {
+                    set_error("edge_list holds a node index outside its graph");
+                    return GNNB_ERR_INVALID;
+                }
+                if (status == 0) return GNNB_OK;
             }
-            if (status == 0) return GNNB_OK;
             if (m->path == GNNB_PATH_FUSED) {
-                set_error(status == 1 ? "fused path requested but a tile exceeded its capacity"
-                                      : "fused path requested but the batch produced non-finite "
-                                        "activations (graphs of a tile would contaminate each other)");
+                set_error(too_big ? "fused path requested but a graph is larger than a CTA tile"
+                          : status == 1 ? "fused path requested but a tile exceeded its capacity"
+                                        : "fused path requested but the batch produced non-finite "
+                                          "activations (graphs of a tile would contaminate each other)");
                 return GNNB_ERR_INVALID;
             }
-            // capacity overflow or non-finite activations: fall through to the whole-batch upload
-            // below and redo everything on the layerwise path
-            m->path = GNNB_PATH_LAYERWISE;
-            const int rc = gnnb_model_run_batch(m, x, edge_list, node_ptr, edge_ptr, n_graphs, out);
-            m->path = GNNB_PATH_AUTO;
-            return rc;
+            if (!too_big) {
+                // capacity overflow or non-finite activations: redo the batch on the layerwise path
+                m->path = GNNB_PATH_LAYERWISE;
+                const int rc2 = gnnb_model_run_batch(m, x, edge_list, node_ptr, edge_ptr, n_graphs, out);
+                m->path = GNNB_PATH_AUTO;
+                return rc2;
+            }
+            // a graph larger than a tile: the regular path below chooses the kernel from the full scan
         }
+    }
+    if (!scanned_all) {
+        max_n = 0;
+        max_e = 0;
+        GNNB_TRY(scan(0, n_graphs));
     }
 
     const float *dx = x;
@@ -807,8 +852,8 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
     if (!dev) {
         GNNB_TRY(m->st_x.ensure(sizeof(float) * (size_t)std::max<int64_t>(T, 1) * d.in_dim));
         GNNB_TRY(m->st_coo.ensure(sizeof(int32_t) * 2 * (size_t)std::max<int64_t>(E, 1)));
-        GNNB_TRY(m->st_nptr.ensure(8 * hn.size()));
-        GNNB_TRY(m->st_eptr.ensure(8 * he.size()));
+        GNNB_TRY(m->st_nptr.ensure(8 * ((size_t)n_graphs + 1)));
+        GNNB_TRY(m->st_eptr.ensure(8 * ((size_t)n_graphs + 1)));
         GNNB_TRY(m->st_out.ensure(sizeof(float) * (size_t)n_graphs * d.mlp_out));
         if (T > 0)
             GNNB_CUDA(cudaMemcpyAsync(m->st_x.ptr, x, sizeof(float) * (size_t)T * d.in_dim,
@@ -816,8 +861,8 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
         if (E > 0)
             GNNB_CUDA(cudaMemcpyAsync(m->st_coo.ptr, edge_list, sizeof(int32_t) * 2 * (size_t)E,
                                       cudaMemcpyHostToDevice, s));
-        GNNB_CUDA(cudaMemcpyAsync(m->st_nptr.ptr, node_ptr, 8 * hn.size(), cudaMemcpyHostToDevice, s));
-        GNNB_CUDA(cudaMemcpyAsync(m->st_eptr.ptr, edge_ptr, 8 * he.size(), cudaMemcpyHostToDevice, s));
+        GNNB_CUDA(cudaMemcpyAsync(m->st_nptr.ptr, node_ptr, 8 * ((size_t)n_graphs + 1), cudaMemcpyHostToDevice, s));
+        GNNB_CUDA(cudaMemcpyAsync(m->st_eptr.ptr, edge_ptr, 8 * ((size_t)n_graphs + 1), cudaMemcpyHostToDevice, s));
         dx = m->st_x.as<float>();
         dcoo = m->st_coo.as<int32_t>();
         dnp = m->st_nptr.as<int64_t>();
