@@ -56,9 +56,9 @@ constexpr int TM = 128;
 #ifndef GNNB_TC_WORKERS
 #define GNNB_TC_WORKERS 256
 #endif
-constexpr int NTHREADS = GNNB_TC_WORKERS;   // worker threads (8 or 16 warps; warp 0 also issues the MMAs)
+constexpr int NTHREADS = GNNB_TC_WORKERS;   // worker threads (8 or 16 warps)
 constexpr int NWARPS = NTHREADS / 32;
-constexpr int CTA_THREADS = NTHREADS + 32;   // + the weight-producer warp
+constexpr int CTA_THREADS = NTHREADS + 64;   // + the weight-producer warp + the MMA-issuing warp
 constexpr int CSTRIDE = 32 * (NWARPS / 4);   // column stride between the 32-column blocks of one warp
 constexpr int NCHALF = NTHREADS / TM;        // staging: threads per row
 constexpr int MAX_LAYERS = 8;
@@ -105,7 +105,7 @@ struct TcParams {
 };
 
 struct Misc {
-    uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_done;
+    uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_done, bar_ready;
     uint32_t tmem_slot;
     int pend_n;
     int nonfinite;
@@ -585,19 +585,26 @@ __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;\n"
         done_cnt++;                                                                 \
         tc::tc_fence_after();                                                       \
     } while (0)
-#define GNNB_PUBLISH_TMEM()                                                         \
+// Hand-off to the issuing warp: every worker arrives on bar_ready once its part of the operands
+// (tensor-memory A rows, or shared-memory planes / ADJ after fence.proxy.async) is written; the
+// issuer waits for all 256 arrivals, issues the next MMA phase and commits to bar_done, on which
+// the workers are already polling.  No CTA barrier on the MMA path.
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+#define GNNB_HANDOFF()                                                              \
     do {                                                                            \
         tc::tc_fence_before();                                                      \
-        SUBT(3, worker_sync());                                                     \
+        mbar_arrive(&ms.bar_ready);                                                 \
     } while (0)
 
 // MLP head (cpp:454-530) for up to 128 pending graphs: the pooled vectors [128][head_in] go from the
 // per-CTA pending buffer (L2) to tensor memory in 128-wide K chunks that accumulate into the same
 // accumulator; later head layers take their A operand from the previous epilogue like GIN's hidden
 // layer.  All worker threads call this.
-__device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, uint32_t ring, int warp_u,
-                                           uint32_t &cons, uint32_t tmem_base, const float *pending,
-                                           int n_rows, uint32_t &done_cnt)
+__device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, uint32_t tmem_base,
+                                           const float *pending, int n_rows, uint32_t &done_cnt)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = 32 * (warp & 3) + lane;
@@ -623,9 +630,8 @@ __device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, uint32_t
                                   tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
                 }
                 tc::tmem_st_wait();
-                GNNB_PUBLISH_TMEM();
+                GNNB_HANDOFF();      // (for j > 0 the previous layer's epilogue handed A off)
             }
-            if (warp_u == 0) gemm_issue(ms, ring, cons, tmem_base, L, c > 0);
             GNNB_WAIT_DONE();
         }
         const TLinear &L0 = p.hl[j][0];
@@ -634,9 +640,21 @@ __device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, uint32_t
                             p.head_n[j]);
         } else {
             epilogue_tmem(tmem_base, L0.N, L0.bias, p.mlp_act);
+            GNNB_HANDOFF();
         }
-        GNNB_PUBLISH_TMEM();
     }
+}
+
+// the head's GEMMs in execution order (issuing warp)
+__device__ __forceinline__ void head_issue(const TcParams &p, Misc &ms, uint32_t ring, uint32_t &cons,
+                                           uint32_t tmem_base, uint32_t &ready_cnt)
+{
+    for (int j = 0; j < p.mlp_num_linear; j++)
+        for (int c = 0; c < p.hchunks[j]; c++) {
+            tc::mbar_wait(&ms.bar_ready, ready_cnt & 1);
+            ready_cnt++;
+            gemm_issue(ms, ring, cons, tmem_base, p.hl[j][c], c > 0);
+        }
 }
 
 __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_constant__ TcParams p)
@@ -664,6 +682,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             tc::mbar_init(&ms.bar_empty[i], 1);
         }
         tc::mbar_init(&ms.bar_done, 1);
+        tc::mbar_init(&ms.bar_ready, NTHREADS);
         tc::mbar_fence_init();
         ms.pend_n = 0;
         ms.nonfinite = 0;
@@ -713,6 +732,38 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             for (int j = 0; j < p.mlp_num_linear; j++)
                 for (int c = 0; c < p.hchunks[j]; c++)
                     produce_linear(ms, ring_addr, prod, p.hl[j][c], copy_off, leader);
+    } else if (warp_u == NWARPS + 1) {
+        // ------------------------------------------------------------ MMA-issuing warp
+        // mirrors the workers' sequence of MMA phases (per tile: aggregation and transforms of
+        // every layer, then the head when 128 pooled graphs are waiting); each phase starts when
+        // all workers have arrived on bar_ready and ends with a commit to bar_done.
+        uint32_t ready_cnt = 0;
+        int pend = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int tg0 = __ldg(p.tile_bounds + tile), tg1 = __ldg(p.tile_bounds + tile + 1);
+            const int tng = tg1 - tg0;
+            const int64_t trows = __ldg(p.node_ptr + tg1) - __ldg(p.node_ptr + tg0);
+            if (tng <= 0 || trows > TM || tng > TM) continue;
+            for (int l = 0; l < p.num_layers; l++) {
+                tc::mbar_wait(&ms.bar_ready, ready_cnt & 1);
+                ready_cnt++;
+                agg_issue(ms, tmem_base + TM_D, adj_addr, xp_addr, (p.fi[l] + 31) & ~31, (int)trows);
+                tc::mbar_wait(&ms.bar_ready, ready_cnt & 1);
+                ready_cnt++;
+                gemm_issue(ms, ring_addr, cons, tmem_base, p.l0[l], false);
+                if (p.conv_type != GNNB_CONV_GCN) {
+                    tc::mbar_wait(&ms.bar_ready, ready_cnt & 1);
+                    ready_cnt++;
+                    gemm_issue(ms, ring_addr, cons, tmem_base, p.l1[l], p.conv_type == GNNB_CONV_SAGE);
+                }
+            }
+            pend += tng;
+            if (pend >= HEAD_G) {
+                head_issue(p, ms, ring_addr, cons, tmem_base, ready_cnt);
+                pend -= HEAD_G;
+            }
+        }
+        if (pend > 0) head_issue(p, ms, ring_addr, cons, tmem_base, ready_cnt);
     } else {
     // ---------------------------------------------------------------- worker warps
     float *pending = p.pending + (size_t)blockIdx.x * HEAD_G * PLD;
@@ -846,7 +897,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
                 }
             }
             tc::fence_async_smem();
-            GNNB_PUBLISH_TMEM();
+            GNNB_HANDOFF();      // ADJ + planes are ready: layer 0's aggregation may start
             GNNB_PHASE(1)
         }
         // second half of the next tile's geometry (the bounds have arrived by now), and a hint to
@@ -865,7 +916,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
 
         const int my_deg = ms.deg[32 * (warp & 3) + lane];   // row owned in the thread-per-row phases
         const float my_dinv = 1.0f / sqrtf(1.0f + (float)my_deg);
-        const int rows_u = __shfl_sync(0xffffffffu, rows, 0);
 
         // -------------------------------------------------------------------- conv layers
         for (int l = 0; l < p.num_layers; l++) {
@@ -873,30 +923,26 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             const int kp = (fi + 31) & ~31;
             const bool last_layer = l == p.num_layers - 1;
             const bool do_skip = p.skip && l != 0 && !last_layer;  // cpp:269-279
-            if (warp_u == 0) agg_issue(ms, tmem_base + TM_D, adj_addr, xp_addr, kp, rows_u);
-            GNNB_WAIT_DONE();
+            GNNB_WAIT_DONE();    // aggregation (issued by the issuing warp)
             GNNB_PHASE(2)
             if (conv == GNNB_CONV_GCN) cvt_agg<0>(tmem_base, XP, kp, my_dinv, true, 1.0f, 0.0f);
             else if (conv == GNNB_CONV_SAGE) cvt_agg<1>(tmem_base, XP, kp, 1.0f, my_deg > 0, (float)my_deg, 0.0f);
             else if (p.gin_eps != 0.0f) cvt_agg<2>(tmem_base, XP, kp, 1.0f, true, 1.0f, p.gin_eps);
             else cvt_agg<0>(tmem_base, XP, kp, 1.0f, true, 1.0f, 0.0f);
-            GNNB_PUBLISH_TMEM();
+            GNNB_HANDOFF();
             GNNB_PHASE(3)
-            if (warp_u == 0) gemm_issue(ms, ring_addr, cons, tmem_base, p.l0[l], false);
             GNNB_WAIT_DONE();
             GNNB_PHASE(7)
             if (conv == GNNB_CONV_GIN) {
                 epilogue_tmem(tmem_base, p.l0[l].N, p.l0[l].bias, GNNB_ACT_RELU);
-                GNNB_PUBLISH_TMEM();
+                GNNB_HANDOFF();
                 GNNB_PHASE(3)
-                if (warp_u == 0) gemm_issue(ms, ring_addr, cons, tmem_base, p.l1[l], false);
                 GNNB_WAIT_DONE();
                 GNNB_PHASE(7)
             } else if (conv == GNNB_CONV_SAGE) {
                 cvt_self(tmem_base, XP, kp);
-                GNNB_PUBLISH_TMEM();
+                GNNB_HANDOFF();
                 GNNB_PHASE(3)
-                if (warp_u == 0) gemm_issue(ms, ring_addr, cons, tmem_base, p.l1[l], true);
                 GNNB_WAIT_DONE();
                 GNNB_PHASE(7)
             }
@@ -909,8 +955,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
                     bad_values |= epilogue_planes(tmem_base, XP, Lb.N, Lb.bias, p.gnn_act, do_skip, gcn,
                                                   sqrtf(1.0f + (float)my_deg), my_dinv);
             }
-            tc::fence_async_smem();
-            GNNB_PUBLISH_TMEM();
+            if (last_layer) {
+                worker_sync();           // pooling reads the other threads' rows
+            } else {
+                tc::fence_async_smem();
+                GNNB_HANDOFF();          // the planes are ready: the next layer's aggregation may start
+            }
             GNNB_PHASE(3)
         }
 
@@ -923,12 +973,24 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
                 float *dst = pending + (size_t)(base_n + gi) * PLD;
                 for (int cc = lane * 4; cc < emb; cc += 128) {   // emb % 16 == 0
                     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), mx = sum;
-                    for (int r = r0; r < r1; r++) {
-                        const float4 v = *reinterpret_cast<const float4 *>(XP + out_chunk_offset(r, cc));
-                        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-                        const bool first = r == r0;                       // lib:748-759
-                        mx.x = (first || v.x > mx.x) ? v.x : mx.x; mx.y = (first || v.y > mx.y) ? v.y : mx.y;
-                        mx.z = (first || v.z > mx.z) ? v.z : mx.z; mx.w = (first || v.w > mx.w) ? v.w : mx.w;
+                    // rows in order (the reference's sum order, lib:2709-2739), loads of four rows
+                    // in flight at a time
+                    for (int r = r0; r < r1; r += 4) {
+                        float4 v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            v[q] = *reinterpret_cast<const float4 *>(XP + out_chunk_offset(min(r + q, r1 - 1), cc));
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            if (r + q < r1) {
+                                sum.x += v[q].x; sum.y += v[q].y; sum.z += v[q].z; sum.w += v[q].w;
+                                const bool first = r + q == r0;                       // lib:748-759
+                                mx.x = (first || v[q].x > mx.x) ? v[q].x : mx.x;
+                                mx.y = (first || v[q].y > mx.y) ? v[q].y : mx.y;
+                                mx.z = (first || v[q].z > mx.z) ? v[q].z : mx.z;
+                                mx.w = (first || v[q].w > mx.w) ? v[q].w : mx.w;
+                            }
+                        }
                     }
                     const float inv_on = (r1 > r0) ? 1.0f : 0.0f, cntf = (float)max(r1 - r0, 1);
                     for (int q = 0; q < p.num_pools; q++) {
@@ -948,7 +1010,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             gdone += cnt;
             GNNB_PHASE(4)
             if (base_n + cnt == HEAD_G) {
-                head_flush(p, ms, ring_addr, warp_u, cons, tmem_base, pending, HEAD_G, done_cnt);
+                head_flush(p, ms, tmem_base, pending, HEAD_G, done_cnt);
                 if (tid == 0) ms.pend_n = 0;
                 GNNB_PHASE(5)
             }
@@ -959,7 +1021,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
     worker_sync();
     {
         const int left = ms.pend_n;
-        if (left > 0) head_flush(p, ms, ring_addr, warp_u, cons, tmem_base, pending, left, done_cnt);
+        if (left > 0) head_flush(p, ms, tmem_base, pending, left, done_cnt);
     }
     GNNB_PHASE(5)
 #undef GNNB_PHASE
