@@ -926,7 +926,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             GNNB_WAIT_DONE();    // aggregation (issued by the issuing warp)
             GNNB_PHASE(2)
             if (conv == GNNB_CONV_GCN) cvt_agg<0>(tmem_base, XP, kp, my_dinv, true, 1.0f, 0.0f);
-            else if (conv == GNNB_CONV_SAGE) cvt_agg<1>(tmem_base, XP, kp, 1.0f, my_deg > 0, (float)my_deg, 0.0f);
+            else if (conv == GNNB_CONV_SAGE)   // mean = sum * (1 / deg): one division per row, not per element
+                cvt_agg<0>(tmem_base, XP, kp, my_deg > 0 ? 1.0f / (float)my_deg : 0.0f, true, 1.0f, 0.0f);
             else if (p.gin_eps != 0.0f) cvt_agg<2>(tmem_base, XP, kp, 1.0f, true, 1.0f, p.gin_eps);
             else cvt_agg<0>(tmem_base, XP, kp, 1.0f, true, 1.0f, 0.0f);
             GNNB_HANDOFF();
