@@ -385,9 +385,15 @@ __global__ void __launch_bounds__(256) pna_agg_kernel(const PnaAggArgs a)
                     o[8 + j].v[i] = __fmul_rn(att, q[j]);
                 }
             }
-            float *dst = a.cat12 + (size_t)v * 12 * F + c;
+            if (a.compact) {
+                float *dst = a.cat12 + (size_t)v * 4 * F + c;
 #pragma unroll
-            for (int j = 0; j < 12; j++) o[j].store(dst + (size_t)j * F);
+                for (int j = 0; j < 4; j++) o[j].store(dst + (size_t)j * F);
+            } else {
+                float *dst = a.cat12 + (size_t)v * 12 * F + c;
+#pragma unroll
+                for (int j = 0; j < 12; j++) o[j].store(dst + (size_t)j * F);
+            }
         }
     }
 }

@@ -274,6 +274,7 @@ int launch_gemm(const GemmArgs &g, bool strict, cudaStream_t s, int *launches)
         return GNNB_OK;
     }
     if (gemm_tc_supported(g)) return launch_gemm_tc(g, s, launches);
+    GNNB_REQUIRE(g.expand_deg == nullptr, "gemm: expand mode needs the tensor-core path");
     const int mb = (g.M + BM - 1) / BM;
     if (g.N > 64) {
         dim3 grid(mb, (g.N + 127) / 128);

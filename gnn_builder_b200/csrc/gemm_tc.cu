@@ -37,8 +37,9 @@ constexpr int NTHREADS = NWORK + 64;       // + producer warp + issuer warp
 constexpr int ASTAGES = 6;                 // raw A atoms in flight (shared memory)
 constexpr int A_STAGE_BYTES = TM * tc::ROW_BYTES;   // 16 KB
 constexpr int WSLOTS = 4;
-constexpr int TSTAGES = 2;                 // A operand stages in tensor memory
-constexpr uint32_t TM_A = 384;             // A stages: [384, 512): stage s hi at +64 s, lo at +64 s + 32
+constexpr int MAX_TSTAGES = 4;             // A operand stages in tensor memory: 4 when the two
+                                           // accumulators leave 256 columns free, else 2; stage s
+                                           // lives at [512 - 64 (s + 1), +64): hi 32 columns, lo 32
 
 struct TcGemmParams {
     const float *A[2];
@@ -48,11 +49,18 @@ struct TcGemmParams {
     int ldskip, act;
     float *C;
     int ldc, M, N, Npad, n_tiles;
+    int tstages;       // 2 or 4
+    // expand mode: operand 1 holds statistics [M][K[1]] standing for [A | amp_v A | att_v A]:
+    // every physical atom of operand 1 is handed to the MMAs three times (scaled by 1, amp, att)
+    // against the weight atoms ka, KA[1] + ka, 2 KA[1] + ka.  rep1 = 3 then, else 1.
+    int rep1;
+    const int32_t *expand_deg;
+    float expand_delta;
 };
 
 struct Bars {
     uint64_t w_full[WSLOTS], w_empty[WSLOTS];
-    uint64_t a_full[TSTAGES], a_free[TSTAGES];
+    uint64_t a_full[MAX_TSTAGES], a_free[MAX_TSTAGES];
     uint64_t d_full[2];
     uint32_t tmem_slot;
 };
@@ -134,7 +142,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     if (warp_u == 0) tc::tmem_alloc(&bars.tmem_slot, 512);
     if (tid == 0) {
         for (int i = 0; i < WSLOTS; i++) { tc::mbar_init(&bars.w_full[i], 1); tc::mbar_init(&bars.w_empty[i], 1); }
-        for (int i = 0; i < TSTAGES; i++) { tc::mbar_init(&bars.a_full[i], NWORK); tc::mbar_init(&bars.a_free[i], 1); }
+        for (int i = 0; i < MAX_TSTAGES; i++) { tc::mbar_init(&bars.a_full[i], NWORK); tc::mbar_init(&bars.a_free[i], 1); }
         tc::mbar_init(&bars.d_full[0], 1);
         tc::mbar_init(&bars.d_full[1], 1);
         tc::mbar_fence_init();
@@ -143,7 +151,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, bars.tmem_slot, 0);
-    const int atoms_per_tile = p.KA[0] + p.KA[1];
+    const int atoms_per_tile = p.KA[0] + p.KA[1];            // physical atoms (shared-memory ring)
+    const int vatoms_per_tile = p.KA[0] + p.rep1 * p.KA[1];   // hand-offs to the MMAs
     const int stride = gridDim.x;
 
     if (warp_u == 8) {
@@ -153,16 +162,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += stride)
             for (int op = 0; op < 2; op++) {
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(p.img[op]);
-                for (int u = 0; u < 2 * p.KA[op]; u++) {   // [atom 0 hi, atom 0 lo, atom 1 hi, ...]
-                    const uint32_t s = prod & (WSLOTS - 1), use = prod / WSLOTS;
-                    if (use > 0) tc::mbar_wait(&bars.w_empty[s], (use - 1) & 1);
-                    if (leader) {
-                        tc::mbar_expect_tx(&bars.w_full[s], slot_stride);
-                        tc::bulk_g2s_addr(w_ring + s * slot_stride, src + (size_t)u * slot_stride, slot_stride,
-                                          &bars.w_full[s]);
-                    }
-                    prod++;
-                }
+                const int rep = op == 1 ? p.rep1 : 1;
+                for (int pa = 0; pa < p.KA[op]; pa++)
+                    for (int r = 0; r < rep; r++)
+                        for (int part = 0; part < 2; part++) {   // weight atom r KA + pa: hi, then lo
+                            const size_t u = (size_t)(r * p.KA[op] + pa) * 2 + part;
+                            const uint32_t s = prod & (WSLOTS - 1), use = prod / WSLOTS;
+                            if (use > 0) tc::mbar_wait(&bars.w_empty[s], (use - 1) & 1);
+                            if (leader) {
+                                tc::mbar_expect_tx(&bars.w_full[s], slot_stride);
+                                tc::bulk_g2s_addr(w_ring + s * slot_stride, src + u * slot_stride, slot_stride,
+                                                  &bars.w_full[s]);
+                            }
+                            prod++;
+                        }
             }
     } else if (warp_u == 9) {
         // ------------------------------------------------------------ MMA issuer
@@ -172,10 +185,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         int t_local = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += stride, t_local++) {
             const uint32_t tmem_d = tmem + (uint32_t)(t_local & 1) * (uint32_t)p.Npad;
-            for (int a = 0; a < atoms_per_tile; a++) {
-                const uint32_t st = acons & (TSTAGES - 1);
-                tc::mbar_wait(&bars.a_full[st], (acons / TSTAGES) & 1);
-                const uint32_t ahi = tmem + TM_A + st * 64u, alo = ahi + 32u;
+            for (int a = 0; a < vatoms_per_tile; a++) {
+                const uint32_t st = acons & (uint32_t)(p.tstages - 1);
+                tc::mbar_wait(&bars.a_full[st], (acons / (uint32_t)p.tstages) & 1);
+                const uint32_t ahi = tmem + 512u - 64u * (st + 1u), alo = ahi + 32u;
                 {   // hi weights: A_hi.B_hi + A_lo.B_hi
                     const uint32_t s = cons & (WSLOTS - 1);
                     tc::mbar_wait(&bars.w_full[s], (cons / WSLOTS) & 1);
@@ -287,9 +300,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             issue_atom(p, pf, a_ring + (uint32_t)(i % ASTAGES) * A_STAGE_BYTES, tid);
             pf.next(p, stride);
         }
-        uint32_t g = 0;          // atoms consumed so far (global stream position)
+        uint32_t g = 0;          // physical atoms consumed so far (position in the shared-memory ring)
+        uint32_t vg = 0;         // hand-offs to the MMAs so far (tensor-memory stage / barrier phase)
         int t_local = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += stride, t_local++) {
+            float amp = 1.0f, att = 1.0f;   // PNA degree scalers of this thread's row (lib:1973-1984)
+            if (p.rep1 == 3) {
+                const int64_t grow = (int64_t)tile * TM + row;
+                const int dg = grow < p.M ? __ldg(p.expand_deg + grow) : 1;
+                const float lg1 = logf((float)((dg < 1 ? 1 : dg) + 1));
+                amp = __fdiv_rn(lg1, p.expand_delta);
+                att = __fdiv_rn(p.expand_delta, lg1);
+            }
             for (int a = 0; a < atoms_per_tile; a++, g++) {
                 cp_async_wait<ASTAGES - 2>();       // this thread's copies of atom g have landed
                 worker_sync();                      // everyone's have, and atom g-1 has been read by all
@@ -297,27 +319,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                 pf.next(p, stride);
                 // own row, columns [16 half, +16) of the atom -> hi / lo -> tensor memory stage
                 const unsigned char *stg = base + (size_t)(g % ASTAGES) * A_STAGE_BYTES + (size_t)row * tc::ROW_BYTES;
-                float h[16], l[16];
+                float vv[16];
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const int chunk = half * 4 + q;
                     const float4 v = *reinterpret_cast<const float4 *>(stg + ((chunk ^ (row & 7)) << 4));
-                    const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        h[4 * q + j] = tc::tf32_hi(vv[j]);
-                        l[4 * q + j] = vv[j] - h[4 * q + j];
-                    }
+                    vv[4 * q] = v.x; vv[4 * q + 1] = v.y; vv[4 * q + 2] = v.z; vv[4 * q + 3] = v.w;
                 }
-                const uint32_t st = g & (TSTAGES - 1), use = g / TSTAGES;
-                if (use > 0) tc::mbar_wait(&bars.a_free[st], (use - 1) & 1);   // MMAs of atom g-2 done
-                tc::tc_fence_after();
-                const uint32_t dst = tmem + TM_A + st * 64u + lane_base + (uint32_t)(half * 16);
-                tc::tmem_st16(dst, h);
-                tc::tmem_st16(dst + 32u, l);
-                tc::tmem_st_wait();
-                tc::tc_fence_before();
-                mbar_arrive(&bars.a_full[st]);
+                const int reps = a >= p.KA[0] ? p.rep1 : 1;
+                for (int r = 0; r < reps; r++, vg++) {
+                    const float sc = r == 0 ? 1.0f : (r == 1 ? amp : att);
+                    float h[16], l[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const float t = vv[j] * sc;
+                        h[j] = tc::tf32_hi(t);
+                        l[j] = t - h[j];
+                    }
+                    const uint32_t st = vg & (uint32_t)(p.tstages - 1), use = vg / (uint32_t)p.tstages;
+                    if (use > 0) tc::mbar_wait(&bars.a_free[st], (use - 1) & 1);   // MMAs two hand-offs back are done
+                    tc::tc_fence_after();
+                    const uint32_t dst = tmem + 512u - 64u * (st + 1u) + lane_base + (uint32_t)(half * 16);
+                    tc::tmem_st16(dst, h);
+                    tc::tmem_st16(dst + 32u, l);
+                    tc::tmem_st_wait();
+                    tc::tc_fence_before();
+                    mbar_arrive(&bars.a_full[st]);
+                }
                 // the previous tile's accumulator is complete by now: write it out while this
                 // tile's MMAs run
                 if (a == 0 && t_local > 0) epilogue(tile - stride, t_local - 1);
@@ -378,7 +406,8 @@ bool gemm_tc_supported(const GemmArgs &g)
     const int Npad = (g.N + 15) / 16 * 16;
     // two accumulators + the A stages must fit the 512 columns; tiny problems are not worth a
     // persistent launch
-    return g.N >= 8 && 2 * Npad <= (int)TM_A && g.M >= 4 * TM && g.K1 >= 1;
+    if (g.expand_deg != nullptr && (g.A2 == nullptr || g.K2 % (3 * tc::ATOM_K) != 0)) return false;
+    return g.N >= 8 && 2 * Npad <= 384 && g.M >= 4 * TM && g.K1 >= 1;
 }
 
 int launch_gemm_tc(const GemmArgs &g, cudaStream_t s, int *launches)
@@ -393,6 +422,13 @@ int launch_gemm_tc(const GemmArgs &g, cudaStream_t s, int *launches)
     p.bias = g.bias; p.skip = g.skip; p.ldskip = g.ldskip; p.act = g.act;
     p.C = g.C; p.ldc = g.ldc; p.M = g.M; p.N = g.N; p.Npad = (g.N + 15) / 16 * 16;
     p.n_tiles = (g.M + TM - 1) / TM;
+    // 4 stages (possible when 2 Npad <= 256) measured no faster than 2: the hand-off is not the limiter
+    p.tstages = (getenv("GNNB_TC_GEMM_STAGES4") != nullptr && 2 * p.Npad <= 256) ? 4 : 2;
+    p.rep1 = 1;
+    if (g.expand_deg != nullptr && g.A2 != nullptr) {   // A2 = [M][K2/3] statistics, expanded x3
+        p.K[1] = g.K2 / 3; p.KA[1] = p.K[1] / tc::ATOM_K; p.rep1 = 3;
+        p.expand_deg = g.expand_deg; p.expand_delta = g.expand_delta;
+    }
     const size_t smem = 1024 + (size_t)ASTAGES * A_STAGE_BYTES + (size_t)WSLOTS * p.Npad * tc::ROW_BYTES +
                         256 /* Bars */ + 8 * 4096 /* per-warp output staging */;
     static_assert(sizeof(Bars) <= 256, "Bars must fit its slot");

@@ -85,6 +85,8 @@ struct PnaAggArgs {
     const int32_t *offsets, *nbr, *in_deg;
     int n;
     float delta;
+    int compact;           // 1: write only the [n][4F] statistics (max,min,mean,std); the two degree
+                           // scalers are applied by the consumer (gemm_tc.cu expands them on the fly)
 };
 int launch_pna_agg(const PnaAggArgs &a, cudaStream_t s, int *launches);
 
@@ -96,6 +98,9 @@ struct GemmArgs {
     const float *A2; int lda2; int K2; const float *W2t; int ldw2;
     const float *img1, *img2;   // optional tensor-core weight images of W1 / W2 (gemm_tc.cu); when
                                 // present (and FAST math) the GEMM runs on tcgen05, else on the FMA pipe
+    // PNA "expand" mode (tensor-core path only): A2 holds the [M][K2/3] statistics and stands for
+    // [A2 | amp_v A2 | att_v A2] (lib:1857-1875), amp_v = log(max(deg_v,1)+1)/delta, att_v = 1/amp_v
+    const int32_t *expand_deg; float expand_delta;
     int second_separate;        // STRICT only: A2.W2t is a separate bias-free sum added last (SAGE)
     const float *bias;          // [N] or null
     const float *skip; int ldskip;  // added before the activation, or null

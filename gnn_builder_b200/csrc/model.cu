@@ -547,14 +547,19 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
             float *cat12 = ab + (size_t)Tn * 2 * ldf;         // [T][12fi]
             GemmArgs g0 = gemm_args(cur, cur_ld, L.a, ab, 2 * fi, T, GNNB_ACT_IDENTITY);
             { ProfScope ps(m->prof, PROF_GEMM, s); GNNB_TRY(launch_gemm(g0, false, s, launches)); }
-            PnaAggArgs pa{};
-            pa.ab = ab; pa.F = fi; pa.cat12 = cat12; pa.offsets = offsets; pa.nbr = nbr;
-            pa.in_deg = in_deg; pa.n = T; pa.delta = d.pna_delta;
-            { ProfScope ps(m->prof, PROF_AGG, s); GNNB_TRY(launch_pna_agg(pa, s, launches)); }
             float *hid = m->hid.as<float>();
             GemmArgs g1 = gemm_args(cur, cur_ld, L.b, hid, ld_out, T, GNNB_ACT_IDENTITY);
             g1.bias = L.c.bias;
-            g1.A2 = cat12; g1.lda2 = 12 * fi; g1.K2 = 12 * fi; g1.W2t = L.c.Wt; g1.ldw2 = L.c.ldw; g1.img2 = L.c.img;
+            g1.A2 = cat12; g1.K2 = 12 * fi; g1.W2t = L.c.Wt; g1.ldw2 = L.c.ldw; g1.img2 = L.c.img;
+            // tensor-core path: only the [T][4F] statistics are materialised; the GEMM expands them
+            // to [stats | amp stats | att stats] while it feeds the MMAs (3x less HBM traffic)
+            g1.lda2 = 4 * fi; g1.expand_deg = in_deg; g1.expand_delta = d.pna_delta;
+            const bool expand = gemm_tc_supported(g1);
+            if (!expand) { g1.lda2 = 12 * fi; g1.expand_deg = nullptr; }
+            PnaAggArgs pa{};
+            pa.ab = ab; pa.F = fi; pa.cat12 = cat12; pa.offsets = offsets; pa.nbr = nbr;
+            pa.in_deg = in_deg; pa.n = T; pa.delta = d.pna_delta; pa.compact = expand ? 1 : 0;
+            { ProfScope ps(m->prof, PROF_AGG, s); GNNB_TRY(launch_pna_agg(pa, s, launches)); }
             { ProfScope ps(m->prof, PROF_GEMM, s); GNNB_TRY(launch_gemm(g1, false, s, launches)); }   // lib:2149
             GemmArgs g2 = gemm_args(hid, ld_out, L.d, dst, ld_out, T, d.gnn_act, skip, cur_ld);
             { ProfScope ps(m->prof, PROF_GEMM, s); GNNB_TRY(launch_gemm(g2, false, s, launches)); }   // lib:2150
