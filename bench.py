@@ -42,6 +42,31 @@ def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
+def bind_to_gpu_numa(device_index: int):
+    """Pin this process to the CPU cores next to its GPU (sysfs local_cpulist of the PCI device),
+    so that the pinned host buffers it allocates -- and the copies out of them -- stay on the
+    GPU's own NUMA node when several ranks share the host.  Best effort: silently skipped when
+    the topology cannot be read."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        path = Path(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist")
+        cpus = set()
+        for part in path.read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return 0
+
+
 def algorithmic_flops_per_batch(w, batch) -> float:
     """SURVEY 8(d) formulas, evaluated on the actual batch."""
     n, e, g = batch.total_nodes, batch.total_edges, batch.n_graphs
@@ -489,6 +514,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else 0
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -660,7 +686,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(w, args, G), path=path_used,
-                           nodes_per_gpu=T, edges_per_gpu=E),
+                           nodes_per_gpu=T, edges_per_gpu=E,
+                           **({"host_binding": f"each rank pinned to its GPU's NUMA-local cores "
+                                               f"({numa_cpus} on rank 0)"} if numa_cpus else {})),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
