@@ -73,7 +73,12 @@ constexpr int RING_BYTES = NSLOT * SLOT_STRIDE;
 constexpr int CNT_BYTES = TM * TM;
 constexpr int MAX_NODES_PER_GRAPH = TM;   // a graph must fit one tile
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TM_D = 0, TM_AHI = 128, TM_ALO = 256;
+constexpr uint32_t TM_D0 = 0, TM_AHI = 128, TM_ALO = 256, TM_D1 = 384;
+static_assert(NWARPS == 8, "the two-step row passes assume 8 worker warps (two 32-column blocks per warp)");
+// The accumulator is double buffered: MMA phase i writes D[i & 1] (an accumulating phase stays on
+// the buffer of the phase it adds to), so the row pass that reads phase i's result can overlap the
+// first MMAs of phase i + 1.
+__device__ __forceinline__ uint32_t dcol_of(uint32_t dw) { return dw ? TM_D1 : TM_D0; }
 
 struct TLinear {
     const float *img;   // weight image: per K atom [hi N x 128 B | lo N x 128 B]
@@ -105,7 +110,11 @@ struct TcParams {
 };
 
 struct Misc {
-    uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_done, bar_ready;
+    uint64_t bar_full[NSLOT], bar_empty[NSLOT];
+    // MMA <-> row-pass hand-off, per 64-column half h: ready[h] = the workers have written columns
+    // [64 h, 64 h + 64) of the next MMA operand (one arrival per worker warp); done[h] = the MMAs
+    // producing columns [64 h, +64) of the accumulator have completed (tcgen05.commit).
+    uint64_t bar_done[2], bar_ready[2];
     uint32_t tmem_slot;
     int pend_n;
     int nonfinite;
@@ -247,16 +256,25 @@ __device__ __forceinline__ void produce_linear(Misc &ms, uint32_t ring, uint32_t
     }
 }
 // D[128][N] (+)= A(hi,lo in tensor memory)[128][KA*32] . W^T, 3xTF32: first the hi weight atoms
-// (A_hi.B_hi and A_lo.B_hi), then the lo atoms (A_hi.B_lo).  All lanes of warp 0.
+// (A_hi.B_hi and A_lo.B_hi), then the lo atoms (A_hi.B_lo).  All lanes of the issuing warp.
+// The A operand arrives in two halves: the hi atoms that only touch columns [0, 64) are issued as
+// soon as ready[0] completes, i.e. while the workers are still converting columns [64, 128).
 __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &cons, uint32_t tmem_base,
-                                           const TLinear &L, bool accumulate)
+                                           uint32_t dcol, const TLinear &L, bool accumulate,
+                                           uint32_t &ready_cnt)
 {
     const bool leader = tc::elect_one();
     const int KA = L.KA;
+    const int KA0 = KA < 2 ? KA : 2;   // atoms inside the first 64 columns
     const uint32_t idesc = tc::make_idesc_tf32(TM, L.N);
-    const uint32_t tmem_d = tmem_base + TM_D, ahi = tmem_base + TM_AHI, alo = tmem_base + TM_ALO;
+    const uint32_t tmem_d = tmem_base + dcol, ahi = tmem_base + TM_AHI, alo = tmem_base + TM_ALO;
+    tc::mbar_wait(&ms.bar_ready[0], ready_cnt & 1);
     tc::tc_fence_after();
     for (int ka = 0; ka < KA; ka++) {   // hi atoms
+        if (ka == KA0) {
+            tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1);
+            tc::tc_fence_after();
+        }
         const uint32_t s = cons & (NSLOT - 1);
         tc::mbar_wait(&ms.bar_full[s], (cons / NSLOT) & 1);
         tc::tc_fence_after();
@@ -275,6 +293,11 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &co
         }
         cons++;
     }
+    if (KA <= KA0) {
+        tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1);
+        tc::tc_fence_after();
+    }
+    ready_cnt++;
     for (int ka = 0; ka < KA; ka++) {   // lo atoms
         const uint32_t s = cons & (NSLOT - 1);
         tc::mbar_wait(&ms.bar_full[s], (cons / NSLOT) & 1);
@@ -289,31 +312,46 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &co
         }
         cons++;
     }
-    if (leader) tc::mma_commit(&ms.bar_done);
+    if (leader) {
+        tc::mma_commit(&ms.bar_done[0]);
+        tc::mma_commit(&ms.bar_done[1]);
+    }
 }
 
 // AGG[128][n_cols] = ADJ . (Xh + Xm + Xl), K = source nodes (16 per MMA, only the k-steps that
-// cover the tile's rows).  Warp-uniform, like gemm_issue.
+// cover the tile's rows).  Warp-uniform, like gemm_issue.  Issued per 64-column half of the
+// features (one 64-feature block of the planes each): half 0 starts when the workers have written
+// plane columns [0, 64) and is handed back (done[0]) while half 1 is still running.
 __device__ __forceinline__ void agg_issue(Misc &ms, uint32_t tmem_d, uint32_t adj, uint32_t xp,
-                                          int n_cols, int rows)
+                                          int n_cols, int rows, uint32_t &ready_cnt)
 {
     const bool leader = tc::elect_one();
-    const uint32_t idesc = tc::make_idesc_bf16(TM, n_cols, 1);
     const int nks = rows > 0 ? (rows + 15) >> 4 : 1;   // (an all-empty tile still defines D)
-    tc::tc_fence_after();
     // ADJ: k-step ks lives in K atom ks >> 2 at byte 32 (ks & 3); planes: 16 nodes = 2048 bytes
     const uint64_t a0 = tc::make_desc(adj), a1 = tc::make_desc(adj + tc::PLANE_BLOCK_BYTES);
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        tc::mbar_wait(&ms.bar_ready[h], ready_cnt & 1);
+        tc::tc_fence_after();
+        const int nh = min(n_cols - 64 * h, 64);
+        if (nh > 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(TM, nh, 1);
 #pragma unroll
-    for (int pl = 0; pl < 3; pl++) {
-        const uint64_t b0 = tc::make_desc_mn(xp + (uint32_t)pl * tc::PLANE_BYTES, tc::PLANE_BLOCK_BYTES, 1024u);
+            for (int pl = 0; pl < 3; pl++) {
+                const uint64_t b0 = tc::make_desc_mn(xp + (uint32_t)pl * tc::PLANE_BYTES +
+                                                         (uint32_t)h * tc::PLANE_BLOCK_BYTES,
+                                                     tc::PLANE_BLOCK_BYTES, 1024u);
 #pragma unroll
-        for (int ks = 0; ks < 8; ks++) {
-            if (ks < nks && leader)
-                tc::mma_bf16(tmem_d, (ks < 4 ? a0 : a1) + (uint64_t)(2 * (ks & 3)), b0 + (uint64_t)(128 * ks),
-                             idesc, (pl == 0 && ks == 0) ? 0u : 1u);
+                for (int ks = 0; ks < 8; ks++) {
+                    if (ks < nks && leader)
+                        tc::mma_bf16(tmem_d + 64u * (uint32_t)h, (ks < 4 ? a0 : a1) + (uint64_t)(2 * (ks & 3)),
+                                     b0 + (uint64_t)(128 * ks), idesc, (pl == 0 && ks == 0) ? 0u : 1u);
+                }
+            }
         }
+        if (leader) tc::mma_commit(&ms.bar_done[h]);
     }
-    if (leader) tc::mma_commit(&ms.bar_done);
+    ready_cnt++;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -345,25 +383,71 @@ __device__ __forceinline__ void split_store32(uint32_t ahi, uint32_t alo, const 
     tc::tmem_st32(alo, l);
 }
 
-// One pass over the accumulator columns this warp owns ([32 h, +32) and [32 h + 64, +32), h = warp
-// >> 2, limited to ncols): f(c0, lane_base, v) runs per 32-column block.
+// Hand-off to the issuing warp, one arrival per worker warp and per 64-column half: every lane has
+// made its part of the operands visible (tcgen05.wait::st, or fence.proxy.async for shared memory),
+// the warp converges and lane 0 arrives.  256 single-thread arrivals on one mbarrier word used to
+// serialise for several hundred cycles per phase.
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void handoff_half(Misc &ms, int h)
+{
+    tc::tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&ms.bar_ready[h]);
+}
+__device__ __forceinline__ void handoff_both(Misc &ms)
+{
+    tc::tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        mbar_arrive(&ms.bar_ready[0]);
+        mbar_arrive(&ms.bar_ready[1]);
+    }
+}
+// wait for both halves of the current MMA phase (every worker polls: no CTA barrier)
+__device__ __forceinline__ void wait_done_both(Misc &ms, uint32_t &done_cnt)
+{
+    tc::mbar_wait(&ms.bar_done[0], done_cnt & 1);
+    tc::mbar_wait(&ms.bar_done[1], done_cnt & 1);
+    done_cnt++;
+    tc::tc_fence_after();
+}
+
+// One pass over the accumulator of the current MMA phase, in two steps of one 32-column block per
+// warp: step h covers columns [64 h, 64 h + 64) (warps 0-3 the first 32 of them, warps 4-7 the
+// second 32), limited to ncols.  Step h waits for done[h] (the MMAs of that accumulator half),
+// runs f(c0, lane_base, v) on the block and, when the pass produces the next MMA operand
+// (HK = 1: in tensor memory, HK = 2: in shared memory), hands that half off on ready[h] -- so the
+// next phase's first MMAs run while step 1 is still converting, and (aggregation) step 0 runs
+// while the second half of the accumulator is still being computed.
 #ifdef GNNB_TC_SUBTIMING
 __device__ unsigned long long g_sub[8];
 #define SUBT(i, expr) do { const long long t0_ = clock64(); expr; if (threadIdx.x == 0) atomicAdd(&g_sub[i], (unsigned long long)(clock64() - t0_)); } while (0)
 #else
 #define SUBT(i, expr) do { expr; } while (0)
 #endif
-template <class F>
-__device__ __forceinline__ void row_pass(uint32_t tmem_src, int ncols, F &&f)
+template <int HK, class F>
+__device__ __forceinline__ void row_pass(Misc &ms, uint32_t &done_cnt, uint32_t tmem_src, int ncols, F &&f)
 {
     const int warp = threadIdx.x >> 5;
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
 #pragma unroll 1
-    for (int c0 = (warp >> 2) * 32; c0 < ncols; c0 += CSTRIDE) {
-        uint32_t r[32];
-        SUBT(0, tc::tmem_ld32_nowait(tmem_src + lane_base + (uint32_t)c0, r); tc::tmem_ld_wait());
-        SUBT(1, f(c0, lane_base, r));
+    for (int h = 0; h < 2; h++) {
+        SUBT(3, tc::mbar_wait(&ms.bar_done[h], done_cnt & 1));
+        tc::tc_fence_after();
+        const int c0 = (warp >> 2) * 32 + 64 * h;
+        if (c0 < ncols) {
+            uint32_t r[32];
+            SUBT(0, tc::tmem_ld32_nowait(tmem_src + lane_base + (uint32_t)c0, r); tc::tmem_ld_wait());
+            SUBT(1, f(c0, lane_base, r));
+        }
+        if (HK == 1) SUBT(2, tc::tmem_st_wait());
+        if (HK == 2) tc::fence_async_smem();
+        if (HK != 0) handoff_half(ms, h);
     }
+    done_cnt++;
 }
 template <int ACT>   // 0 identity, 1 relu, 2 anything else (one out-of-line call)
 __device__ __forceinline__ float act_fast(int act, float x)
@@ -373,15 +457,14 @@ __device__ __forceinline__ float act_fast(int act, float x)
     return act_apply_general(act, x);
 }
 
-// aggregation accumulator -> A operand.  MODE 0: v * scale (GCN dinv_v; 1 for plain sums), MODE 1:
-// v / divisor when on, else 0 (SAGE mean, lib:2180-2207), MODE 2: v + self_coef * x_v (GIN eps).
-// Columns [0, kp).
+// aggregation accumulator -> A operand.  MODE 0: v * scale (GCN dinv_v; SAGE 1 / deg, lib:2180-2207;
+// 1 for plain sums), MODE 2: v + self_coef * x_v (GIN eps).  Columns [0, kp).
 template <int MODE>
-__device__ __forceinline__ void cvt_agg(uint32_t tmem_base, const unsigned char *XP, int kp,
-                                        float scale, bool on, float divisor, float self_coef)
+__device__ __forceinline__ void cvt_agg(Misc &ms, uint32_t &done_cnt, uint32_t tmem_base, uint32_t dcol,
+                                        const unsigned char *XP, int kp, float scale, float self_coef)
 {
     const int row = 32 * ((threadIdx.x >> 5) & 3) + (threadIdx.x & 31);
-    row_pass(tmem_base + TM_D, kp, [&](int c0, uint32_t lane_base, const uint32_t (&r)[32]) {
+    row_pass<1>(ms, done_cnt, tmem_base + dcol, kp, [&](int c0, uint32_t lane_base, const uint32_t (&r)[32]) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
@@ -393,9 +476,6 @@ __device__ __forceinline__ void cvt_agg(uint32_t tmem_base, const unsigned char 
 #pragma unroll
                 for (int j = 0; j < 8; j++) v[8 * j8 + j] = fmaf(self_coef, xs[j], v[8 * j8 + j]);
             }
-        } else if (MODE == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = on ? v[j] / divisor : 0.0f;
         } else {
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] *= scale;
@@ -403,37 +483,42 @@ __device__ __forceinline__ void cvt_agg(uint32_t tmem_base, const unsigned char 
         split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
                       tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
     });
-    SUBT(2, tc::tmem_st_wait());
 }
 
-// own row of the planes -> A operand (SAGE root term), columns [0, kp)
-__device__ __forceinline__ void cvt_self(uint32_t tmem_base, const unsigned char *XP, int kp)
+// own row of the planes -> A operand (SAGE root term), columns [0, kp).  The caller has waited for
+// the GEMM that was reading the A operand.
+__device__ __forceinline__ void cvt_self(Misc &ms, uint32_t tmem_base, const unsigned char *XP, int kp)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = 32 * (warp & 3) + lane;
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-    for (int c0 = (warp >> 2) * 32; c0 < kp; c0 += CSTRIDE) {
-        float v[32];
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        const int c0 = (warp >> 2) * 32 + 64 * h;
+        if (c0 < kp) {
+            float v[32];
 #pragma unroll
-        for (int j8 = 0; j8 < 4; j8++) {
-            float xs[8];
-            load_row8(XP, row, c0 + 8 * j8, xs);
+            for (int j8 = 0; j8 < 4; j8++) {
+                float xs[8];
+                load_row8(XP, row, c0 + 8 * j8, xs);
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[8 * j8 + j] = xs[j];
+                for (int j = 0; j < 8; j++) v[8 * j8 + j] = xs[j];
+            }
+            split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
+                          tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
         }
-        split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
-                      tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
+        tc::tmem_st_wait();
+        handoff_half(ms, h);
     }
-    tc::tmem_st_wait();
 }
 
 // accumulator -> (+bias, activation) -> A operand (GIN hidden layer, head hidden layers).
 // Columns [N, round_up(N, 32)) are zero filled.
 template <int ACT>
-__device__ __forceinline__ void epilogue_tmem_t(uint32_t tmem_base, int N, const float *__restrict__ bias,
-                                                int act)
+__device__ __forceinline__ void epilogue_tmem_t(Misc &ms, uint32_t &done_cnt, uint32_t tmem_base,
+                                                uint32_t dcol, int N, const float *__restrict__ bias, int act)
 {
-    row_pass(tmem_base + TM_D, (N + 31) & ~31, [&](int c0, uint32_t lane_base, const uint32_t (&r)[32]) {
+    row_pass<1>(ms, done_cnt, tmem_base + dcol, (N + 31) & ~31, [&](int c0, uint32_t lane_base, const uint32_t (&r)[32]) {
         float v[32];
 #pragma unroll
         for (int j4 = 0; j4 < 8; j4++) {
@@ -448,14 +533,13 @@ __device__ __forceinline__ void epilogue_tmem_t(uint32_t tmem_base, int N, const
         split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
                       tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
     });
-    tc::tmem_st_wait();
 }
-__device__ __forceinline__ void epilogue_tmem(uint32_t tmem_base, int N, const float *__restrict__ bias,
-                                              int act)
+__device__ __forceinline__ void epilogue_tmem(Misc &ms, uint32_t &done_cnt, uint32_t tmem_base, uint32_t dcol,
+                                              int N, const float *__restrict__ bias, int act)
 {
-    if (act == GNNB_ACT_RELU) epilogue_tmem_t<1>(tmem_base, N, bias, act);
-    else if (act == GNNB_ACT_IDENTITY) epilogue_tmem_t<0>(tmem_base, N, bias, act);
-    else epilogue_tmem_t<2>(tmem_base, N, bias, act);
+    if (act == GNNB_ACT_RELU) epilogue_tmem_t<1>(ms, done_cnt, tmem_base, dcol, N, bias, act);
+    else if (act == GNNB_ACT_IDENTITY) epilogue_tmem_t<0>(ms, done_cnt, tmem_base, dcol, N, bias, act);
+    else epilogue_tmem_t<2>(ms, done_cnt, tmem_base, dcol, N, bias, act);
 }
 
 // accumulator -> (+bias, +skip, activation, * out_scale) -> bf16 planes (the next layer's input).
@@ -463,13 +547,14 @@ __device__ __forceinline__ void epilogue_tmem(uint32_t tmem_base, int N, const f
 // a non-finite value was written (chk accumulates t * 0, which is NaN exactly then).  Columns
 // [N, round_up(N, 32)) are zero filled.
 template <int ACT, bool SKIP, bool SCALE>
-__device__ __forceinline__ int epilogue_planes_t(uint32_t tmem_base, unsigned char *XP, int N,
+__device__ __forceinline__ int epilogue_planes_t(Misc &ms, uint32_t &done_cnt, uint32_t tmem_d,
+                                                 unsigned char *XP, int N,
                                                  const float *__restrict__ bias, int act,
                                                  float skip_unscale, float out_scale)
 {
     const int row = 32 * ((threadIdx.x >> 5) & 3) + (threadIdx.x & 31);
     float chk = 0.0f;
-    row_pass(tmem_base + TM_D, (N + 31) & ~31, [&](int c0, uint32_t, const uint32_t (&r)[32]) {
+    row_pass<2>(ms, done_cnt, tmem_d, (N + 31) & ~31, [&](int c0, uint32_t, const uint32_t (&r)[32]) {
 #pragma unroll
         for (int j8 = 0; j8 < 4; j8++) {
             const int c = c0 + 8 * j8;
@@ -500,22 +585,21 @@ __device__ __forceinline__ int epilogue_planes_t(uint32_t tmem_base, unsigned ch
 }
 // SCALE (GCN only): skip_unscale undoes the dinv factor stored in the planes, out_scale applies the
 // next layer's.  The common cases (ReLU / identity, with and without skip) get lean instantiations.
-__device__ __forceinline__ int epilogue_planes(uint32_t tmem_base, unsigned char *XP, int N,
+__device__ __forceinline__ int epilogue_planes(Misc &ms, uint32_t &done_cnt, uint32_t tmem_d,
+                                               unsigned char *XP, int N,
                                                const float *__restrict__ bias, int act, bool skip,
                                                bool scale, float skip_unscale, float out_scale)
 {
+#define GNNB_EP(A, S, C, u, o) epilogue_planes_t<A, S, C>(ms, done_cnt, tmem_d, XP, N, bias, act, u, o)
     if (scale) {
         if (act == GNNB_ACT_RELU)
-            return skip ? epilogue_planes_t<1, true, true>(tmem_base, XP, N, bias, act, skip_unscale, out_scale)
-                        : epilogue_planes_t<1, false, true>(tmem_base, XP, N, bias, act, skip_unscale, out_scale);
-        return skip ? epilogue_planes_t<2, true, true>(tmem_base, XP, N, bias, act, skip_unscale, out_scale)
-                    : epilogue_planes_t<2, false, true>(tmem_base, XP, N, bias, act, skip_unscale, out_scale);
+            return skip ? GNNB_EP(1, true, true, skip_unscale, out_scale) : GNNB_EP(1, false, true, skip_unscale, out_scale);
+        return skip ? GNNB_EP(2, true, true, skip_unscale, out_scale) : GNNB_EP(2, false, true, skip_unscale, out_scale);
     }
     if (act == GNNB_ACT_RELU)
-        return skip ? epilogue_planes_t<1, true, false>(tmem_base, XP, N, bias, act, 1.0f, 1.0f)
-                    : epilogue_planes_t<1, false, false>(tmem_base, XP, N, bias, act, 1.0f, 1.0f);
-    return skip ? epilogue_planes_t<2, true, false>(tmem_base, XP, N, bias, act, 1.0f, 1.0f)
-                : epilogue_planes_t<2, false, false>(tmem_base, XP, N, bias, act, 1.0f, 1.0f);
+        return skip ? GNNB_EP(1, true, false, 1.0f, 1.0f) : GNNB_EP(1, false, false, 1.0f, 1.0f);
+    return skip ? GNNB_EP(2, true, false, 1.0f, 1.0f) : GNNB_EP(2, false, false, 1.0f, 1.0f);
+#undef GNNB_EP
 }
 
 // Last conv layer: accumulator -> (+bias, +skip, activation) -> plain fp32 rows in the (now dead)
@@ -527,11 +611,12 @@ __device__ __forceinline__ uint32_t out_chunk_offset(int row, int c4)   // c4 % 
     return (uint32_t)row * 512u + (uint32_t)(((c4 >> 2) ^ (row & 7)) << 4);
 }
 template <int ACT>
-__device__ __forceinline__ void epilogue_rows_t(uint32_t tmem_base, unsigned char *XP, int N,
+__device__ __forceinline__ void epilogue_rows_t(Misc &ms, uint32_t &done_cnt, uint32_t tmem_d,
+                                                unsigned char *XP, int N,
                                                 const float *__restrict__ bias, int act)
 {
     const int row = 32 * ((threadIdx.x >> 5) & 3) + (threadIdx.x & 31);
-    row_pass(tmem_base + TM_D, (N + 31) & ~31, [&](int c0, uint32_t, const uint32_t (&r)[32]) {
+    row_pass<0>(ms, done_cnt, tmem_d, (N + 31) & ~31, [&](int c0, uint32_t, const uint32_t (&r)[32]) {
 #pragma unroll
         for (int j4 = 0; j4 < 8; j4++) {
             const int c = c0 + 4 * j4;
@@ -548,16 +633,17 @@ __device__ __forceinline__ void epilogue_rows_t(uint32_t tmem_base, unsigned cha
     });
 }
 // (the last layer never has a skip connection, cpp:269-279, and GCN leaves it unscaled)
-__device__ __forceinline__ void epilogue_rows(uint32_t tmem_base, unsigned char *XP, int N,
+__device__ __forceinline__ void epilogue_rows(Misc &ms, uint32_t &done_cnt, uint32_t tmem_d,
+                                              unsigned char *XP, int N,
                                               const float *__restrict__ bias, int act)
 {
-    if (act == GNNB_ACT_RELU) epilogue_rows_t<1>(tmem_base, XP, N, bias, act);
-    else if (act == GNNB_ACT_IDENTITY) epilogue_rows_t<0>(tmem_base, XP, N, bias, act);
-    else epilogue_rows_t<2>(tmem_base, XP, N, bias, act);
+    if (act == GNNB_ACT_RELU) epilogue_rows_t<1>(ms, done_cnt, tmem_d, XP, N, bias, act);
+    else if (act == GNNB_ACT_IDENTITY) epilogue_rows_t<0>(ms, done_cnt, tmem_d, XP, N, bias, act);
+    else epilogue_rows_t<2>(ms, done_cnt, tmem_d, XP, N, bias, act);
 }
 
 // head output: columns [0, n_true) of rows [0, n_rows) -> gout[gids[row]][col]
-__device__ __forceinline__ void epilogue_global(uint32_t tmem_base, int N, const float *__restrict__ bias,
+__device__ __forceinline__ void epilogue_global(uint32_t tmem_d, int N, const float *__restrict__ bias,
                                                 int act, float *gout, const int *gids, int n_rows,
                                                 int ldg, int n_true)
 {
@@ -568,7 +654,7 @@ __device__ __forceinline__ void epilogue_global(uint32_t tmem_base, int N, const
     float *grow = row < n_rows ? gout + (size_t)gids[row] * ldg : nullptr;
     for (int c0 = (warp >> 2) * 32; c0 < npad; c0 += CSTRIDE) {
         float v[32];
-        tc::tmem_ld32(tmem_base + TM_D + lane_base + (uint32_t)c0, v);
+        tc::tmem_ld32(tmem_d + lane_base + (uint32_t)c0, v);
         if (grow == nullptr) continue;
 #pragma unroll
         for (int j = 0; j < 32; j++)
@@ -579,32 +665,14 @@ __device__ __forceinline__ void epilogue_global(uint32_t tmem_base, int N, const
 // barrier over the 256 worker threads (the producer warp never joins it)
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(NTHREADS) : "memory"); }
 
-#define GNNB_WAIT_DONE()                                                            \
-    do {                                                                            \
-        tc::mbar_wait(&ms.bar_done, done_cnt & 1);   /* every worker polls: no barrier */ \
-        done_cnt++;                                                                 \
-        tc::tc_fence_after();                                                       \
-    } while (0)
-// Hand-off to the issuing warp: every worker arrives on bar_ready once its part of the operands
-// (tensor-memory A rows, or shared-memory planes / ADJ after fence.proxy.async) is written; the
-// issuer waits for all 256 arrivals, issues the next MMA phase and commits to bar_done, on which
-// the workers are already polling.  No CTA barrier on the MMA path.
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(tc::smem_u32(bar)) : "memory");
-}
-#define GNNB_HANDOFF()                                                              \
-    do {                                                                            \
-        tc::tc_fence_before();                                                      \
-        mbar_arrive(&ms.bar_ready);                                                 \
-    } while (0)
-
 // MLP head (cpp:454-530) for up to 128 pending graphs: the pooled vectors [128][head_in] go from the
 // per-CTA pending buffer (L2) to tensor memory in 128-wide K chunks that accumulate into the same
 // accumulator; later head layers take their A operand from the previous epilogue like GIN's hidden
-// layer.  All worker threads call this.
+// layer.  All worker threads call this.  dw: index of the accumulator buffer of the latest
+// non-accumulating MMA phase (toggled whenever the workers start one).
 __device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, uint32_t tmem_base,
-                                           const float *pending, int n_rows, uint32_t &done_cnt)
+                                           const float *pending, int n_rows, uint32_t &done_cnt,
+                                           uint32_t &dw)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = 32 * (warp & 3) + lane;
@@ -612,48 +680,55 @@ __device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, uint32_t
     const int head_in = p.emb * p.num_pools;
     for (int j = 0; j < p.mlp_num_linear; j++) {
         const bool last = j == p.mlp_num_linear - 1;
-        for (int c = 0; c < p.hchunks[j]; c++) {
+        const int nch = p.hchunks[j];
+        for (int c = 0; c < nch; c++) {
             const TLinear &L = p.hl[j][c];
             if (j == 0) {  // A chunk: pending[:, 128c : 128c + K) -> (hi, lo), zero padded
                 const int kp = L.KA * tc::ATOM_K;
                 const float *src = pending + (size_t)row * PLD + c * 128;
-                for (int c0 = (warp >> 2) * 32; c0 < kp; c0 += CSTRIDE) {
-                    float v[32];
+#pragma unroll 1
+                for (int h = 0; h < 2; h++) {
+                    const int c0 = (warp >> 2) * 32 + 64 * h;
+                    if (c0 < kp) {
+                        float v[32];
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; j4++) {
-                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row < n_rows && c * 128 + c0 + j4 * 4 < head_in)   // head_in % 4 == 0
-                            t = __ldcg(reinterpret_cast<const float4 *>(src + c0 + j4 * 4));
-                        v[j4 * 4] = t.x; v[j4 * 4 + 1] = t.y; v[j4 * 4 + 2] = t.z; v[j4 * 4 + 3] = t.w;
+                        for (int j4 = 0; j4 < 8; j4++) {
+                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (row < n_rows && c * 128 + c0 + j4 * 4 < head_in)   // head_in % 4 == 0
+                                t = __ldcg(reinterpret_cast<const float4 *>(src + c0 + j4 * 4));
+                            v[j4 * 4] = t.x; v[j4 * 4 + 1] = t.y; v[j4 * 4 + 2] = t.z; v[j4 * 4 + 3] = t.w;
+                        }
+                        split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
+                                      tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
                     }
-                    split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
-                                  tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
+                    tc::tmem_st_wait();
+                    handoff_half(ms, h);     // (for j > 0 the previous layer's epilogue handed A off)
                 }
-                tc::tmem_st_wait();
-                GNNB_HANDOFF();      // (for j > 0 the previous layer's epilogue handed A off)
+                if (c == 0) dw ^= 1u;        // chunk 0 starts a new accumulator, the others add to it
             }
-            GNNB_WAIT_DONE();
+            // the next chunk overwrites the A operand: wait for the MMAs that read it
+            if (c < nch - 1) wait_done_both(ms, done_cnt);
         }
         const TLinear &L0 = p.hl[j][0];
         if (last) {
-            epilogue_global(tmem_base, L0.N, L0.bias, p.out_act, p.out, ms.pend_gid, n_rows, p.mlp_out,
-                            p.head_n[j]);
+            wait_done_both(ms, done_cnt);
+            epilogue_global(tmem_base + dcol_of(dw), L0.N, L0.bias, p.out_act, p.out, ms.pend_gid, n_rows,
+                            p.mlp_out, p.head_n[j]);
         } else {
-            epilogue_tmem(tmem_base, L0.N, L0.bias, p.mlp_act);
-            GNNB_HANDOFF();
+            epilogue_tmem(ms, done_cnt, tmem_base, dcol_of(dw), L0.N, L0.bias, p.mlp_act);
+            dw ^= 1u;                        // ... which started the next head layer's GEMM
         }
     }
 }
 
 // the head's GEMMs in execution order (issuing warp)
 __device__ __forceinline__ void head_issue(const TcParams &p, Misc &ms, uint32_t ring, uint32_t &cons,
-                                           uint32_t tmem_base, uint32_t &ready_cnt)
+                                           uint32_t tmem_base, uint32_t &ready_cnt, uint32_t &dw)
 {
     for (int j = 0; j < p.mlp_num_linear; j++)
         for (int c = 0; c < p.hchunks[j]; c++) {
-            tc::mbar_wait(&ms.bar_ready, ready_cnt & 1);
-            ready_cnt++;
-            gemm_issue(ms, ring, cons, tmem_base, p.hl[j][c], c > 0);
+            if (c == 0) dw ^= 1u;
+            gemm_issue(ms, ring, cons, tmem_base, dcol_of(dw), p.hl[j][c], c > 0, ready_cnt);
         }
 }
 
@@ -681,8 +756,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             tc::mbar_init(&ms.bar_full[i], 1);
             tc::mbar_init(&ms.bar_empty[i], 1);
         }
-        tc::mbar_init(&ms.bar_done, 1);
-        tc::mbar_init(&ms.bar_ready, NTHREADS);
+        for (int h = 0; h < 2; h++) {
+            tc::mbar_init(&ms.bar_done[h], 1);
+            tc::mbar_init(&ms.bar_ready[h], NWARPS);   // one arrival per worker warp
+        }
         tc::mbar_fence_init();
         ms.pend_n = 0;
         ms.nonfinite = 0;
@@ -698,7 +775,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
     const uint32_t adj_addr = __shfl_sync(0xffffffffu, tc::smem_u32(ADJ), 0);
     const uint32_t xp_addr = adj_addr + tc::PLANE_BYTES;
     const uint32_t ring_addr = adj_addr + 4 * tc::PLANE_BYTES;
-    uint32_t done_cnt = 0, cons = 0;
+    uint32_t done_cnt = 0, cons = 0, dw = 0;   // dw: accumulator buffer of the latest new MMA phase
     const int n_tiles = __shfl_sync(0xffffffffu, __ldg(p.n_tiles_ptr), 0);
 
     if (warp_u == NWARPS) {
@@ -735,9 +812,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
     } else if (warp_u == NWARPS + 1) {
         // ------------------------------------------------------------ MMA-issuing warp
         // mirrors the workers' sequence of MMA phases (per tile: aggregation and transforms of
-        // every layer, then the head when 128 pooled graphs are waiting); each phase starts when
-        // all workers have arrived on bar_ready and ends with a commit to bar_done.
-        uint32_t ready_cnt = 0;
+        // every layer, then the head when 128 pooled graphs are waiting); each phase consumes one
+        // completion of ready[0] and ready[1] and commits once to done[0] and done[1].
+        uint32_t ready_cnt = 0, dw = 0;
         int pend = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int tg0 = __ldg(p.tile_bounds + tile), tg1 = __ldg(p.tile_bounds + tile + 1);
@@ -745,25 +822,24 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             const int64_t trows = __ldg(p.node_ptr + tg1) - __ldg(p.node_ptr + tg0);
             if (tng <= 0 || trows > TM || tng > TM) continue;
             for (int l = 0; l < p.num_layers; l++) {
-                tc::mbar_wait(&ms.bar_ready, ready_cnt & 1);
-                ready_cnt++;
-                agg_issue(ms, tmem_base + TM_D, adj_addr, xp_addr, (p.fi[l] + 31) & ~31, (int)trows);
-                tc::mbar_wait(&ms.bar_ready, ready_cnt & 1);
-                ready_cnt++;
-                gemm_issue(ms, ring_addr, cons, tmem_base, p.l0[l], false);
+                dw ^= 1u;
+                agg_issue(ms, tmem_base + dcol_of(dw), adj_addr, xp_addr, (p.fi[l] + 31) & ~31, (int)trows,
+                          ready_cnt);
+                dw ^= 1u;
+                gemm_issue(ms, ring_addr, cons, tmem_base, dcol_of(dw), p.l0[l], false, ready_cnt);
                 if (p.conv_type != GNNB_CONV_GCN) {
-                    tc::mbar_wait(&ms.bar_ready, ready_cnt & 1);
-                    ready_cnt++;
-                    gemm_issue(ms, ring_addr, cons, tmem_base, p.l1[l], p.conv_type == GNNB_CONV_SAGE);
+                    const bool acc = p.conv_type == GNNB_CONV_SAGE;
+                    if (!acc) dw ^= 1u;
+                    gemm_issue(ms, ring_addr, cons, tmem_base, dcol_of(dw), p.l1[l], acc, ready_cnt);
                 }
             }
             pend += tng;
             if (pend >= HEAD_G) {
-                head_issue(p, ms, ring_addr, cons, tmem_base, ready_cnt);
+                head_issue(p, ms, ring_addr, cons, tmem_base, ready_cnt, dw);
                 pend -= HEAD_G;
             }
         }
-        if (pend > 0) head_issue(p, ms, ring_addr, cons, tmem_base, ready_cnt);
+        if (pend > 0) head_issue(p, ms, ring_addr, cons, tmem_base, ready_cnt, dw);
     } else {
     // ---------------------------------------------------------------- worker warps
     float *pending = p.pending + (size_t)blockIdx.x * HEAD_G * PLD;
@@ -897,7 +973,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
                 }
             }
             tc::fence_async_smem();
-            GNNB_HANDOFF();      // ADJ + planes are ready: layer 0's aggregation may start
+            handoff_both(ms);    // ADJ + planes are ready: layer 0's aggregation may start
+            dw ^= 1u;
             GNNB_PHASE(1)
         }
         // second half of the next tile's geometry (the bounds have arrived by now), and a hint to
@@ -923,46 +1000,37 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             const int kp = (fi + 31) & ~31;
             const bool last_layer = l == p.num_layers - 1;
             const bool do_skip = p.skip && l != 0 && !last_layer;  // cpp:269-279
-            GNNB_WAIT_DONE();    // aggregation (issued by the issuing warp)
-            GNNB_PHASE(2)
-            if (conv == GNNB_CONV_GCN) cvt_agg<0>(tmem_base, XP, kp, my_dinv, true, 1.0f, 0.0f);
+            // aggregation accumulator -> A operand (each half as soon as its MMAs are done), which
+            // starts the first transform
+            if (conv == GNNB_CONV_GCN) cvt_agg<0>(ms, done_cnt, tmem_base, dcol_of(dw), XP, kp, my_dinv, 0.0f);
             else if (conv == GNNB_CONV_SAGE)   // mean = sum * (1 / deg): one division per row, not per element
-                cvt_agg<0>(tmem_base, XP, kp, my_deg > 0 ? 1.0f / (float)my_deg : 0.0f, true, 1.0f, 0.0f);
-            else if (p.gin_eps != 0.0f) cvt_agg<2>(tmem_base, XP, kp, 1.0f, true, 1.0f, p.gin_eps);
-            else cvt_agg<0>(tmem_base, XP, kp, 1.0f, true, 1.0f, 0.0f);
-            GNNB_HANDOFF();
-            GNNB_PHASE(3)
-            GNNB_WAIT_DONE();
-            GNNB_PHASE(7)
+                cvt_agg<0>(ms, done_cnt, tmem_base, dcol_of(dw), XP, kp, my_deg > 0 ? 1.0f / (float)my_deg : 0.0f, 0.0f);
+            else if (p.gin_eps != 0.0f) cvt_agg<2>(ms, done_cnt, tmem_base, dcol_of(dw), XP, kp, 1.0f, p.gin_eps);
+            else cvt_agg<0>(ms, done_cnt, tmem_base, dcol_of(dw), XP, kp, 1.0f, 0.0f);
+            dw ^= 1u;
+            GNNB_PHASE(2)
             if (conv == GNNB_CONV_GIN) {
-                epilogue_tmem(tmem_base, p.l0[l].N, p.l0[l].bias, GNNB_ACT_RELU);
-                GNNB_HANDOFF();
+                epilogue_tmem(ms, done_cnt, tmem_base, dcol_of(dw), p.l0[l].N, p.l0[l].bias, GNNB_ACT_RELU);
+                dw ^= 1u;
                 GNNB_PHASE(3)
-                GNNB_WAIT_DONE();
-                GNNB_PHASE(7)
             } else if (conv == GNNB_CONV_SAGE) {
-                cvt_self(tmem_base, XP, kp);
-                GNNB_HANDOFF();
+                wait_done_both(ms, done_cnt);     // the first transform has finished reading A
+                cvt_self(ms, tmem_base, XP, kp);  // the root transform accumulates on the same buffer
                 GNNB_PHASE(3)
-                GNNB_WAIT_DONE();
-                GNNB_PHASE(7)
             }
             {
                 const TLinear &Lb = conv == GNNB_CONV_GIN ? p.l1[l] : p.l0[l];
                 const bool gcn = conv == GNNB_CONV_GCN;
-                if (last_layer)   // only pooling reads it: plain fp32 rows
-                    epilogue_rows(tmem_base, XP, Lb.N, Lb.bias, p.gnn_act);
-                else
-                    bad_values |= epilogue_planes(tmem_base, XP, Lb.N, Lb.bias, p.gnn_act, do_skip, gcn,
-                                                  sqrtf(1.0f + (float)my_deg), my_dinv);
+                if (last_layer) {   // only pooling reads it: plain fp32 rows
+                    epilogue_rows(ms, done_cnt, tmem_base + dcol_of(dw), XP, Lb.N, Lb.bias, p.gnn_act);
+                    worker_sync();           // pooling reads the other threads' rows
+                } else {            // the planes of the next layer; each half starts its aggregation
+                    bad_values |= epilogue_planes(ms, done_cnt, tmem_base + dcol_of(dw), XP, Lb.N, Lb.bias,
+                                                  p.gnn_act, do_skip, gcn, sqrtf(1.0f + (float)my_deg), my_dinv);
+                    dw ^= 1u;
+                }
             }
-            if (last_layer) {
-                worker_sync();           // pooling reads the other threads' rows
-            } else {
-                tc::fence_async_smem();
-                GNNB_HANDOFF();          // the planes are ready: the next layer's aggregation may start
-            }
-            GNNB_PHASE(3)
+            GNNB_PHASE(7)
         }
 
         // -------------------------------------------------------------------- pooling -> pending
@@ -1011,7 +1079,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             gdone += cnt;
             GNNB_PHASE(4)
             if (base_n + cnt == HEAD_G) {
-                head_flush(p, ms, tmem_base, pending, HEAD_G, done_cnt);
+                head_flush(p, ms, tmem_base, pending, HEAD_G, done_cnt, dw);
                 if (tid == 0) ms.pend_n = 0;
                 GNNB_PHASE(5)
             }
@@ -1022,7 +1090,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
     worker_sync();
     {
         const int left = ms.pend_n;
-        if (left > 0) head_flush(p, ms, tmem_base, pending, left, done_cnt);
+        if (left > 0) head_flush(p, ms, tmem_base, pending, left, done_cnt, dw);
     }
     GNNB_PHASE(5)
 #undef GNNB_PHASE
@@ -1241,8 +1309,9 @@ int fused_tc_status(gnnb_model *m, int *status)
         unsigned long long t[16];
         GNNB_CUDA(cudaMemcpy(t, plan->timing.ptr, sizeof(t), cudaMemcpyDeviceToHost));
         GNNB_CUDA(cudaMemset(plan->timing.ptr, 0, sizeof(t)));
-        const char *names[8] = {"stage", "adj+planes", "agg-mma", "convert/epilogue", "pool", "head",
-                                "-", "transform-mma"};
+        // (the row passes include their waits for the MMAs of the phase they read)
+        const char *names[8] = {"stage", "adj+planes", "agg->A pass", "hidden/self pass", "pool", "head",
+                                "-", "output pass"};
         unsigned long long tot = 0;
         for (int i = 0; i < 8; i++) tot += t[i];
         fprintf(stderr, "[gnnb fused-tc phases]");
@@ -1255,7 +1324,7 @@ int fused_tc_status(gnnb_model *m, int *status)
         cudaMemcpyFromSymbol(sub, g_sub, sizeof(sub));
         unsigned long long zero[8] = {0};
         cudaMemcpyToSymbol(g_sub, zero, sizeof(zero));
-        fprintf(stderr, "[gnnb fused-tc sub] tmem-ld %.1f%% row-work %.1f%% st-wait(cvt) %.1f%% publish-barrier %.1f%%\n",
+        fprintf(stderr, "[gnnb fused-tc sub] tmem-ld %.1f%% row-work %.1f%% st-wait %.1f%% mma-done-wait %.1f%%\n",
                 100.0 * sub[0] / tot, 100.0 * sub[1] / tot, 100.0 * sub[2] / tot, 100.0 * sub[3] / tot);
 #endif
     }
