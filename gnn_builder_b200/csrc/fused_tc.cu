@@ -74,7 +74,15 @@ constexpr int CNT_BYTES = TM * TM;
 constexpr int MAX_NODES_PER_GRAPH = TM;   // a graph must fit one tile
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_D0 = 0, TM_AHI = 128, TM_ALO = 256, TM_D1 = 384;
-static_assert(NWARPS == 8, "the two-step row passes assume 8 worker warps (two 32-column blocks per warp)");
+static_assert(NWARPS == 8 || NWARPS == 16, "row passes: 8 worker warps (two 32-column blocks each) or 16 (one each)");
+constexpr int PASS_STEPS = 2;                // one step per 64-column half
+constexpr int STEP_COLS = 256 / NWARPS;      // columns of its rows a warp converts per step (32 or 16)
+#ifndef GNNB_TC_CHUNK
+#define GNNB_TC_CHUNK (GNNB_TC_WORKERS == 512 ? 16 : 32)
+#endif
+constexpr int CH = GNNB_TC_CHUNK;            // accumulator columns a thread holds at a time (16 keeps 16 warps under 96 registers)
+static_assert((CH == 16 || CH == 32) && CH <= STEP_COLS, "row passes work on 16- or 32-column chunks");
+constexpr int READY_ARRIVALS = NWARPS;       // every worker warp arrives once per 64-column half
 // The accumulator is double buffered: MMA phase i writes D[i & 1] (an accumulating phase stays on
 // the buffer of the phase it adds to), so the row pass that reads phase i's result can overlap the
 // first MMAs of phase i + 1.
@@ -235,6 +243,10 @@ __global__ void __launch_bounds__(256) tc_pack_compact_kernel(const int32_t *__r
 // instructions themselves are predicated on the elected lane.  Issued from a divergent
 // `if (tid == 0)` region the same loop costs ~110 cycles per MMA (a register -> uniform-register
 // waterfall per instruction), 1.7x the MMA itself (tools/mma_rate.py).
+// Unit order of one linear: the hi atoms 0 .. KA-1, then the lo atoms.  (Measured: moving the lo
+// atoms of the first two K atoms forward, so that half of the GEMM could start on the first half of
+// the A operand, is 3 % slower -- with a 4-slot ring the second group's units could then only be
+// requested once the first group's MMAs had completed.)
 __device__ __forceinline__ void produce_linear(Misc &ms, uint32_t ring, uint32_t &prod,
                                                const TLinear &L, size_t copy_off, bool leader)
 {
@@ -374,13 +386,14 @@ __device__ __forceinline__ void store_row8(unsigned char *XP, int row, int c, co
     *reinterpret_cast<uint4 *>(XP + tc::PLANE_BYTES + off) = m;
     *reinterpret_cast<uint4 *>(XP + 2 * tc::PLANE_BYTES + off) = l;
 }
-__device__ __forceinline__ void split_store32(uint32_t ahi, uint32_t alo, const float (&v)[32])
+template <int W>
+__device__ __forceinline__ void split_store(uint32_t ahi, uint32_t alo, const float (&v)[W])
 {
-    float h[32], l[32];
+    float h[W], l[W];
 #pragma unroll
-    for (int j = 0; j < 32; j++) { h[j] = tc::tf32_hi(v[j]); l[j] = v[j] - h[j]; }
-    tc::tmem_st32(ahi, h);
-    tc::tmem_st32(alo, l);
+    for (int j = 0; j < W; j++) { h[j] = tc::tf32_hi(v[j]); l[j] = v[j] - h[j]; }
+    tc::tmem_st(ahi, h);
+    tc::tmem_st(alo, l);
 }
 
 // Hand-off to the issuing warp, one arrival per worker warp and per 64-column half: every lane has
@@ -415,9 +428,9 @@ __device__ __forceinline__ void wait_done_both(Misc &ms, uint32_t &done_cnt)
     tc::tc_fence_after();
 }
 
-// One pass over the accumulator of the current MMA phase, in two steps of one 32-column block per
-// warp: step h covers columns [64 h, 64 h + 64) (warps 0-3 the first 32 of them, warps 4-7 the
-// second 32), limited to ncols.  Step h waits for done[h] (the MMAs of that accumulator half),
+// One pass over the accumulator of the current MMA phase, in two steps: step h covers columns
+// [64 h, 64 h + 64), STEP_COLS of them per warp (8 worker warps: warps 0-3 the first 32 columns of
+// their rows, warps 4-7 the second 32), limited to ncols.  Step h waits for done[h] (the MMAs of that accumulator half),
 // runs f(c0, lane_base, v) on the block and, when the pass produces the next MMA operand
 // (HK = 1: in tensor memory, HK = 2: in shared memory), hands that half off on ready[h] -- so the
 // next phase's first MMAs run while step 1 is still converting, and (aggregation) step 0 runs
@@ -434,14 +447,17 @@ __device__ __forceinline__ void row_pass(Misc &ms, uint32_t &done_cnt, uint32_t 
     const int warp = threadIdx.x >> 5;
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
 #pragma unroll 1
-    for (int h = 0; h < 2; h++) {
+    for (int st = 0; st < PASS_STEPS; st++) {
+        const int h = st, c0 = 64 * st + STEP_COLS * (warp >> 2);
         SUBT(3, tc::mbar_wait(&ms.bar_done[h], done_cnt & 1));
         tc::tc_fence_after();
-        const int c0 = (warp >> 2) * 32 + 64 * h;
         if (c0 < ncols) {
-            uint32_t r[32];
-            SUBT(0, tc::tmem_ld32_nowait(tmem_src + lane_base + (uint32_t)c0, r); tc::tmem_ld_wait());
-            SUBT(1, f(c0, lane_base, r));
+#pragma unroll 1
+            for (int cc = c0; cc < c0 + STEP_COLS; cc += CH) {
+                uint32_t r[CH];
+                SUBT(0, tc::tmem_ld_nowait(tmem_src + lane_base + (uint32_t)cc, r); tc::tmem_ld_wait());
+                SUBT(1, f(cc, lane_base, r));
+            }
         }
         if (HK == 1) SUBT(2, tc::tmem_st_wait());
         if (HK == 2) tc::fence_async_smem();
@@ -457,31 +473,31 @@ __device__ __forceinline__ float act_fast(int act, float x)
     return act_apply_general(act, x);
 }
 
-// aggregation accumulator -> A operand.  MODE 0: v * scale (GCN dinv_v; SAGE 1 / deg, lib:2180-2207;
-// 1 for plain sums), MODE 2: v + self_coef * x_v (GIN eps).  Columns [0, kp).
+// aggregation accumulator -> A operand.  MODE 0: v * scale (GCN dinv_v; SAGE 1 / deg, lib:2180-2207),
+// MODE 1: v as it is (GIN with eps = 0), MODE 2: v + self_coef * x_v (GIN eps).  Columns [0, kp).
 template <int MODE>
 __device__ __forceinline__ void cvt_agg(Misc &ms, uint32_t &done_cnt, uint32_t tmem_base, uint32_t dcol,
                                         const unsigned char *XP, int kp, float scale, float self_coef)
 {
     const int row = 32 * ((threadIdx.x >> 5) & 3) + (threadIdx.x & 31);
-    row_pass<1>(ms, done_cnt, tmem_base + dcol, kp, [&](int c0, uint32_t lane_base, const uint32_t (&r)[32]) {
-        float v[32];
+    row_pass<1>(ms, done_cnt, tmem_base + dcol, kp, [&](int c0, uint32_t lane_base, const uint32_t (&r)[CH]) {
+        float v[CH];
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < CH; j++) v[j] = __uint_as_float(r[j]);
         if (MODE == 2) {
 #pragma unroll
-            for (int j8 = 0; j8 < 4; j8++) {
+            for (int j8 = 0; j8 < CH / 8; j8++) {
                 float xs[8];
                 load_row8(XP, row, c0 + 8 * j8, xs);
 #pragma unroll
                 for (int j = 0; j < 8; j++) v[8 * j8 + j] = fmaf(self_coef, xs[j], v[8 * j8 + j]);
             }
-        } else {
+        } else if (MODE == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] *= scale;
+            for (int j = 0; j < CH; j++) v[j] *= scale;
         }
-        split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
-                      tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
+        split_store(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
+                    tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
     });
 }
 
@@ -493,19 +509,22 @@ __device__ __forceinline__ void cvt_self(Misc &ms, uint32_t tmem_base, const uns
     const int row = 32 * (warp & 3) + lane;
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
 #pragma unroll 1
-    for (int h = 0; h < 2; h++) {
-        const int c0 = (warp >> 2) * 32 + 64 * h;
+    for (int st = 0; st < PASS_STEPS; st++) {
+        const int h = st, c0 = 64 * st + STEP_COLS * (warp >> 2);
         if (c0 < kp) {
-            float v[32];
+#pragma unroll 1
+            for (int cc = c0; cc < c0 + STEP_COLS; cc += CH) {
+                float v[CH];
 #pragma unroll
-            for (int j8 = 0; j8 < 4; j8++) {
-                float xs[8];
-                load_row8(XP, row, c0 + 8 * j8, xs);
+                for (int j8 = 0; j8 < CH / 8; j8++) {
+                    float xs[8];
+                    load_row8(XP, row, cc + 8 * j8, xs);
 #pragma unroll
-                for (int j = 0; j < 8; j++) v[8 * j8 + j] = xs[j];
+                    for (int j = 0; j < 8; j++) v[8 * j8 + j] = xs[j];
+                }
+                split_store(tmem_base + TM_AHI + lane_base + (uint32_t)cc,
+                            tmem_base + TM_ALO + lane_base + (uint32_t)cc, v);
             }
-            split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
-                          tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
         }
         tc::tmem_st_wait();
         handoff_half(ms, h);
@@ -518,10 +537,10 @@ template <int ACT>
 __device__ __forceinline__ void epilogue_tmem_t(Misc &ms, uint32_t &done_cnt, uint32_t tmem_base,
                                                 uint32_t dcol, int N, const float *__restrict__ bias, int act)
 {
-    row_pass<1>(ms, done_cnt, tmem_base + dcol, (N + 31) & ~31, [&](int c0, uint32_t lane_base, const uint32_t (&r)[32]) {
-        float v[32];
+    row_pass<1>(ms, done_cnt, tmem_base + dcol, (N + 31) & ~31, [&](int c0, uint32_t lane_base, const uint32_t (&r)[CH]) {
+        float v[CH];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; j4++) {
+        for (int j4 = 0; j4 < CH / 4; j4++) {
             const bool in_range = c0 + j4 * 4 < N;   // N % 4 == 0
             const float4 bs = in_range ? __ldg(reinterpret_cast<const float4 *>(bias + c0 + j4 * 4))
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -530,8 +549,8 @@ __device__ __forceinline__ void epilogue_tmem_t(Misc &ms, uint32_t &done_cnt, ui
             for (int j = 0; j < 4; j++)
                 v[j4 * 4 + j] = in_range ? act_fast<ACT>(act, __uint_as_float(r[j4 * 4 + j]) + bss[j]) : 0.0f;
         }
-        split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
-                      tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
+        split_store(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
+                    tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
     });
 }
 __device__ __forceinline__ void epilogue_tmem(Misc &ms, uint32_t &done_cnt, uint32_t tmem_base, uint32_t dcol,
@@ -554,9 +573,9 @@ __device__ __forceinline__ int epilogue_planes_t(Misc &ms, uint32_t &done_cnt, u
 {
     const int row = 32 * ((threadIdx.x >> 5) & 3) + (threadIdx.x & 31);
     float chk = 0.0f;
-    row_pass<2>(ms, done_cnt, tmem_d, (N + 31) & ~31, [&](int c0, uint32_t, const uint32_t (&r)[32]) {
+    row_pass<2>(ms, done_cnt, tmem_d, (N + 31) & ~31, [&](int c0, uint32_t, const uint32_t (&r)[CH]) {
 #pragma unroll
-        for (int j8 = 0; j8 < 4; j8++) {
+        for (int j8 = 0; j8 < CH / 8; j8++) {
             const int c = c0 + 8 * j8;
             float o[8];
             if (c < N) {   // N % 8 == 0
@@ -616,9 +635,9 @@ __device__ __forceinline__ void epilogue_rows_t(Misc &ms, uint32_t &done_cnt, ui
                                                 const float *__restrict__ bias, int act)
 {
     const int row = 32 * ((threadIdx.x >> 5) & 3) + (threadIdx.x & 31);
-    row_pass<0>(ms, done_cnt, tmem_d, (N + 31) & ~31, [&](int c0, uint32_t, const uint32_t (&r)[32]) {
+    row_pass<0>(ms, done_cnt, tmem_d, (N + 31) & ~31, [&](int c0, uint32_t, const uint32_t (&r)[CH]) {
 #pragma unroll
-        for (int j4 = 0; j4 < 8; j4++) {
+        for (int j4 = 0; j4 < CH / 4; j4++) {
             const int c = c0 + 4 * j4;
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c < N) {   // N % 4 == 0
@@ -687,19 +706,22 @@ __device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, uint32_t
                 const int kp = L.KA * tc::ATOM_K;
                 const float *src = pending + (size_t)row * PLD + c * 128;
 #pragma unroll 1
-                for (int h = 0; h < 2; h++) {
-                    const int c0 = (warp >> 2) * 32 + 64 * h;
+                for (int st = 0; st < PASS_STEPS; st++) {
+                    const int h = st, c0 = 64 * st + STEP_COLS * (warp >> 2);
                     if (c0 < kp) {
-                        float v[32];
+#pragma unroll 1
+                        for (int cc = c0; cc < c0 + STEP_COLS; cc += CH) {
+                            float v[CH];
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; j4++) {
-                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (row < n_rows && c * 128 + c0 + j4 * 4 < head_in)   // head_in % 4 == 0
-                                t = __ldcg(reinterpret_cast<const float4 *>(src + c0 + j4 * 4));
-                            v[j4 * 4] = t.x; v[j4 * 4 + 1] = t.y; v[j4 * 4 + 2] = t.z; v[j4 * 4 + 3] = t.w;
+                            for (int j4 = 0; j4 < CH / 4; j4++) {
+                                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (row < n_rows && c * 128 + cc + j4 * 4 < head_in)   // head_in % 4 == 0
+                                    t = __ldcg(reinterpret_cast<const float4 *>(src + cc + j4 * 4));
+                                v[j4 * 4] = t.x; v[j4 * 4 + 1] = t.y; v[j4 * 4 + 2] = t.z; v[j4 * 4 + 3] = t.w;
+                            }
+                            split_store(tmem_base + TM_AHI + lane_base + (uint32_t)cc,
+                                        tmem_base + TM_ALO + lane_base + (uint32_t)cc, v);
                         }
-                        split_store32(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
-                                      tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
                     }
                     tc::tmem_st_wait();
                     handoff_half(ms, h);     // (for j > 0 the previous layer's epilogue handed A off)
@@ -758,7 +780,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
         }
         for (int h = 0; h < 2; h++) {
             tc::mbar_init(&ms.bar_done[h], 1);
-            tc::mbar_init(&ms.bar_ready[h], NWARPS);   // one arrival per worker warp
+            tc::mbar_init(&ms.bar_ready[h], READY_ARRIVALS);   // one arrival per worker warp and half
         }
         tc::mbar_fence_init();
         ms.pend_n = 0;
@@ -1006,7 +1028,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             else if (conv == GNNB_CONV_SAGE)   // mean = sum * (1 / deg): one division per row, not per element
                 cvt_agg<0>(ms, done_cnt, tmem_base, dcol_of(dw), XP, kp, my_deg > 0 ? 1.0f / (float)my_deg : 0.0f, 0.0f);
             else if (p.gin_eps != 0.0f) cvt_agg<2>(ms, done_cnt, tmem_base, dcol_of(dw), XP, kp, 1.0f, p.gin_eps);
-            else cvt_agg<0>(ms, done_cnt, tmem_base, dcol_of(dw), XP, kp, 1.0f, 0.0f);
+            else cvt_agg<1>(ms, done_cnt, tmem_base, dcol_of(dw), XP, kp, 1.0f, 0.0f);
             dw ^= 1u;
             GNNB_PHASE(2)
             if (conv == GNNB_CONV_GIN) {
