@@ -164,8 +164,10 @@ __global__ void __launch_bounds__(256) agg_rows_kernel(const AggArgs a)
 // `heavy_slices` slices, one CTA per (row, slice); its 8 warps split the slice, reduce their
 // partial sums in shared memory in warp order and write partial[h][slice][F].  A second kernel
 // adds the slices in order and applies the self term / normalisation, so the result does not
-// depend on scheduling.  (A first version gave each heavy row to ONE CTA: a 100k-neighbor hub
-// then ran for ~5 ms on 8 warps while 147 SMs idled.)
+// depend on scheduling.  (Measured alternatives: giving each heavy row to ONE CTA ran a
+// 100k-neighbor hub for ~5 ms on 8 warps while 147 SMs idled; slicing only rows above 4096
+// neighbors and letting one CTA finish the others directly was 2 % slower on the C5 step, the
+// bucket boundary -- GNNB_HEAVY_THRESHOLD, 64 ... 1024 -- moves the step by < 1 %.)
 template <int VEC, int MODE>
 __global__ void __launch_bounds__(256) agg_heavy_kernel(const AggArgs a)
 {

@@ -1,5 +1,6 @@
 // Host-side launchers of the CUDA kernels (internal).
 #pragma once
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -36,6 +37,16 @@ int find_heavy_rows(const int32_t *in_deg, int n, int threshold, TableWorkspace 
                     int *n_heavy_host, cudaStream_t s, int *launches);
 // degree bucketing parameters + partial-sum scratch for the heavy-row kernels
 constexpr int kHeavyThreshold = 256;
+// (tuning hook: GNNB_HEAVY_THRESHOLD overrides the bucket boundary)
+inline int heavy_threshold()
+{
+    static const int v = [] {
+        const char *e = getenv("GNNB_HEAVY_THRESHOLD");
+        const int t = e ? atoi(e) : 0;
+        return t > 0 ? t : kHeavyThreshold;
+    }();
+    return v;
+}
 int heavy_setup(TableWorkspace &ws, int n_heavy, int F, int *slices);
 // dinv[i] = 1 / sqrt(1 + in_deg[i])
 int compute_dinv(const int32_t *in_deg, float *dinv, int n, cudaStream_t s, int *launches);

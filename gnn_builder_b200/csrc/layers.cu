@@ -579,7 +579,7 @@ extern "C" int gnnb_gcn_conv_partition(int n_local, int row_begin, int n_total, 
     GNNB_TRY(g_part.img.ensure(sizeof(float) * gemm_tc_image_floats(emb_in, emb_out)));
     GNNB_TRY(gemm_tc_build_image(g_part.wt.as<float>(), ldw, emb_in, emb_out, g_part.img.as<float>(), s));
     if (g_part.heavy_key != in_degree_local || g_part.heavy_n != n_local) {
-        GNNB_TRY(find_heavy_rows(in_degree_local, n_local, kHeavyThreshold, g_part.ws,
+        GNNB_TRY(find_heavy_rows(in_degree_local, n_local, heavy_threshold(), g_part.ws,
                                  &g_part.n_heavy, s, nullptr));
         GNNB_TRY(heavy_setup(g_part.ws, g_part.n_heavy, emb_in, &g_part.slices));
         g_part.heavy_key = in_degree_local;
@@ -590,7 +590,7 @@ extern "C" int gnnb_gcn_conv_partition(int n_local, int row_begin, int n_total, 
     a.ldo = lda; a.offsets = offsets_local; a.nbr = neighbor_table_global; a.in_deg = in_degree_local;
     a.dinv = dinv_full; a.n = n_local; a.row_base = row_begin;
     a.heavy_rows = g_part.ws.heavy_rows.as<int32_t>(); a.n_heavy = g_part.n_heavy;
-    a.heavy_threshold = kHeavyThreshold;
+    a.heavy_threshold = heavy_threshold();
     a.heavy_partial = g_part.ws.heavy_partial.as<float>(); a.heavy_slices = g_part.slices;
     GNNB_TRY(launch_agg(a, false, s, nullptr));
     GemmArgs g = simple_gemm(a.out, lda, emb_in, g_part.wt.as<float>(), ldw, bias, y_local, emb_out,

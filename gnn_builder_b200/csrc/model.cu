@@ -485,7 +485,7 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
     }
     // degree bucketing only matters for big graphs (molecular graphs have in-degree <= ~8)
     int n_heavy = 0, heavy_slices = 0;
-    const int heavy_threshold = kHeavyThreshold;
+    const int heavy_threshold = heavy_threshold();
     if (!strict && d.num_layers > 0 && d.conv_type != GNNB_CONV_PNA && n_graphs > 0 &&
         T64 / n_graphs > 50000) {
         GNNB_TRY(find_heavy_rows(in_deg, T, heavy_threshold, m->tws, &n_heavy, s, launches));

@@ -26,7 +26,8 @@ def setup():
     model = gnnb.build_model(w, seed=1)
     n = 40000
     x, coo = gnnb.make_powerlaw_graph(n, 16, w.in_dim, seed=5, max_degree=5000)
-    coo[:3000, 1] = 17  # one row far above the heavy-row threshold
+    coo[:3000, 1] = 17      # a heavy row that one CTA finishes by itself (256 < in-degree <= 4096)
+    coo[3000:9500, 1] = 23  # a hub whose neighbor list is sliced over several CTAs (> 4096)
     return gnnb, w, model, n, x, coo
 
 
