@@ -124,7 +124,6 @@ struct Misc {
     // producing columns [64 h, +64) of the accumulator have completed (tcgen05.commit).
     uint64_t bar_done[2], bar_ready[2];
     uint32_t tmem_slot;
-    int pend_n;
     int nonfinite;
     int pend_gid[HEAD_G];
     int deg[TM];
@@ -783,7 +782,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             tc::mbar_init(&ms.bar_ready[h], READY_ARRIVALS);   // one arrival per worker warp and half
         }
         tc::mbar_fence_init();
-        ms.pend_n = 0;
         ms.nonfinite = 0;
     }
     for (int i = tid; i < CNT_BYTES / 16; i += CTA_THREADS)
@@ -869,6 +867,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
     const int conv = p.conv_type;
     const bool self_loop = conv == GNNB_CONV_GCN || conv == GNNB_CONV_GIN;
     int bad_values = 0;
+    int pend_n = 0;   // pooled graphs waiting for the head (uniform over the workers)
 
     // geometry of the first tile; later tiles are prefetched one iteration ahead
     int g0 = 0, g1 = 0;
@@ -949,6 +948,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
                 const int d = idx >> 3, s0 = (idx & 7) * 16;
                 uint4 *cp = reinterpret_cast<uint4 *>(CNT) + idx;
                 const uint4 cw = *cp;
+                // most 16-source groups of the block-diagonal matrix are empty: zeros, no conversion
+                if ((cw.x | cw.y | cw.z | cw.w) == 0u &&
+                    !(self_loop && d < rows && (unsigned)(d - s0) < 16u)) {
+                    *reinterpret_cast<uint4 *>(ADJ + tc::adj_chunk_offset(d, s0)) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(ADJ + tc::adj_chunk_offset(d, s0 + 8)) = make_uint4(0u, 0u, 0u, 0u);
+                    continue;
+                }
                 *cp = make_uint4(0u, 0u, 0u, 0u);
                 const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
                 uint32_t o[8];
@@ -1057,7 +1063,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
 
         // -------------------------------------------------------------------- pooling -> pending
         for (int gdone = 0; gdone < ng;) {
-            const int base_n = ms.pend_n;  // uniform: written below only after a barrier
+            const int base_n = pend_n;     // (a register: every worker tracks the same count)
             const int cnt = min(HEAD_G - base_n, ng - gdone);
             for (int gi = warp; gi < cnt; gi += NWARPS) {
                 const int r0 = ms.grow[gdone + gi], r1 = ms.grow[gdone + gi + 1];
@@ -1096,24 +1102,23 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
                 }
                 if (lane == 0) ms.pend_gid[base_n + gi] = cur_g0 + gdone + gi;
             }
-            worker_sync();
-            if (tid == 0) ms.pend_n = base_n + cnt;
+            pend_n = base_n + cnt;
             gdone += cnt;
             GNNB_PHASE(4)
-            if (base_n + cnt == HEAD_G) {
+            if (pend_n == HEAD_G) {
+                worker_sync();       // the pooled vectors and graph ids of every warp are in place
                 head_flush(p, ms, tmem_base, pending, HEAD_G, done_cnt, dw);
-                if (tid == 0) ms.pend_n = 0;
+                pend_n = 0;
                 GNNB_PHASE(5)
+                // more graphs of this tile follow: their pooling overwrites the pending rows and ids
+                // the slowest threads may still be reading in the head's last epilogue
+                if (gdone < ng) worker_sync();
             }
-            worker_sync();
         }
     }
     // graphs still waiting for the head
     worker_sync();
-    {
-        const int left = ms.pend_n;
-        if (left > 0) head_flush(p, ms, tmem_base, pending, left, done_cnt, dw);
-    }
+    if (pend_n > 0) head_flush(p, ms, tmem_base, pending, pend_n, done_cnt, dw);
     GNNB_PHASE(5)
 #undef GNNB_PHASE
     if (bad_values) atomicExch(p.error_flag, 3);
