@@ -131,14 +131,6 @@ struct Misc {
     int gedge[TM + 2];
 };
 
-// linear ids: 2 * layer + {0: l0, 1: l1}; 64 + 4 * head_layer + chunk
-constexpr int LIN_HEAD = 64;
-__device__ __forceinline__ const TLinear &lin(const TcParams &p, int id)
-{
-    if (id >= LIN_HEAD) return p.hl[(id - LIN_HEAD) >> 2][(id - LIN_HEAD) & 3];
-    return (id & 1) ? p.l1[id >> 1] : p.l0[id >> 1];
-}
-
 // Tile packing on the device: consecutive graphs are packed greedily into tiles of <= 128 rows
 // (and <= 128 graphs).  The greedy walk is sequential, so the batch is cut into chunks of
 // PACK_CHUNK graphs that are packed independently (one CTA each: every thread finds, for "its"
