@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import json
 import os
+import subprocess
 import time
 from functools import cached_property
 from pathlib import Path
@@ -119,6 +120,117 @@ class Project:
                         param_names=self.model.layer_parameter_names_flat,
                         param_shapes=self.model.layer_parameter_shapes_flat)
         (self.model_dir / "model_desc.json").write_text(json.dumps(manifest, indent=1))
+        (self.model_dir / "model.cpp").write_text(self.render_top())
+
+    # ------------------------------------------------------------------ the C++ seam
+    def render_top(self) -> str:
+        """``model.cpp`` for the GPU backend: ``extern "C" void <name>_top(...)`` with EXACTLY the
+        reference's signature (model.h.jinja:67-79: feature table, edge list, output, num_of_nodes,
+        num_of_edges, copy_parameters_flag, then one ``<param>_fixed_in`` array per parameter in
+        ``layer_parameter_names_flat`` order) forwarding to the C-ABI model handle -- what a
+        maintainer renders instead of model.cpp.jinja:686-766.  The reference's own ``model.h``
+        and ``model_tb.cpp`` compile and link against it unchanged (float build)."""
+        d = self.model.describe()
+        names = self.model.layer_parameter_names_flat
+        shapes = self.model.layer_parameter_shapes_flat
+        f_in, out_dim = d["in_dim"], d["mlp_out"]
+        pools = list(d["pools"]) + [0] * (4 - len(d["pools"]))
+
+        def dims(shape):
+            return "".join(f"[{int(v)}]" for v in shape)
+
+        def first(name, shape):
+            return f"&{name}_fixed_in" + "[0]" * len(shape)
+
+        def numel(shape):
+            return int(np.prod(shape)) if len(shape) else 1
+
+        args = "".join(f",\n    float {n}_fixed_in{dims(sh)}" for n, sh in zip(names, shapes))
+        sets = "\n".join(
+            f'        gnnb_check(gnnb_model_set_param(g_model, "{n}", {first(n, sh)}, {numel(sh)}));'
+            for n, sh in zip(names, shapes))
+        return f"""// Generated by gnn_builder_b200.Project.gen_hw_model -- do not edit.
+// `{self.name}_top` with the reference's signature (gnnbuilder model.h.jinja:67-79), computed on
+// the GPU through the C-ABI of libgnnb_b200.so (include/gnnb_b200.h).  Replaces the rendered
+// model.cpp (model.cpp.jinja:686-766); model.h and model_tb.cpp of the reference stay as they are.
+#include <cstdio>
+#include <cstdlib>
+
+#ifdef GNNB_REFERENCE_MODEL_H   // built next to the reference's rendered model.h: the compiler checks
+#include "model.h"              // this definition against the reference's own declaration
+#endif
+#include "gnnb_b200.h"
+
+static gnnb_model_t *g_model = nullptr;   // replaces the file-scope weight arrays (cpp:7-22)
+
+static void gnnb_check(int rc)
+{{
+    if (rc != GNNB_OK) {{   // the reference's top is void: there is no status to return
+        std::fprintf(stderr, "{self.name}_top: %s\\n", gnnb_last_error());
+        std::abort();
+    }}
+}}
+
+extern "C" void {self.name}_top(
+    float node_feature_table_input[{self.max_nodes}][{f_in}],
+    int edge_list_input[{self.max_edges}][2],
+    float model_output[{out_dim}],
+    int num_of_nodes,
+    int num_of_edges,
+    int copy_parameters_flag{args})
+{{
+    if (copy_parameters_flag) {{   // cpp:724-730: parameters are (re)loaded when the flag is set
+        if (g_model == nullptr) {{
+            gnnb_model_desc d = {{}};
+            d.conv_type = {d["conv_type"]}; d.num_layers = {d["num_layers"]}; d.in_dim = {d["in_dim"]};
+            d.hidden_dim = {d["hidden_dim"]}; d.out_dim = {d["out_dim"]}; d.skip = {d["skip"]};
+            d.gnn_act = {d["gnn_act"]}; d.gin_eps = {float(d["gin_eps"])!r}f; d.pna_delta = {float(d["pna_delta"])!r}f;
+            d.num_pools = {len(d["pools"])};
+            d.pools[0] = {pools[0]}; d.pools[1] = {pools[1]}; d.pools[2] = {pools[2]}; d.pools[3] = {pools[3]};
+            d.mlp_num_linear = {d["mlp_num_linear"]}; d.mlp_hidden = {d["mlp_hidden"]}; d.mlp_out = {d["mlp_out"]};
+            d.mlp_act = {d["mlp_act"]}; d.out_act = {d["out_act"]};
+            d.max_nodes = {self.max_nodes}; d.max_edges = {self.max_edges};
+            gnnb_check(gnnb_model_create(&d, -1, &g_model));
+        }}
+{sets}
+        gnnb_check(gnnb_model_finalize(g_model));
+    }}
+    if (g_model == nullptr) {{
+        std::fprintf(stderr, "{self.name}_top: called before the parameters were loaded\\n");
+        std::abort();
+    }}
+    gnnb_check(gnnb_model_run_graph(g_model, &node_feature_table_input[0][0], &edge_list_input[0][0],
+                                    num_of_nodes, num_of_edges, model_output));
+}}
+"""
+
+    def build_top(self, testbench: Optional[Path] = None) -> Path:
+        """Compile the generated ``model.cpp`` into ``lib<name>.so`` (exports ``<name>_top``).
+        With ``testbench`` = a directory holding the REFERENCE's rendered ``model.h``,
+        ``gnn_builder_lib.h`` and ``model_tb.cpp`` (what ``gnnbuilder.Project.gen_hw_model /
+        gen_testbench`` write), also link the reference's own testbench against this top into
+        ``result`` -- flags of makefile_testbench.jinja:22-24."""
+        from . import _lib
+
+        _lib.load()  # builds libgnnb_b200.so if it is missing
+        src = self.model_dir / "model.cpp"
+        if not src.exists():
+            raise Exception(f"{self.name} - {src} does not exist. Call gen_hw_model() first.")
+        inc = Path(__file__).resolve().parent.parent / "include"
+        libdir = Path(_lib.LIB_PATH).parent
+        link = [f"-L{libdir}", "-lgnnb_b200", f"-Wl,-rpath,{libdir}"]
+        so = self.model_dir / f"lib{self.name}.so"
+        base = ["g++", "-O3", "-std=c++14", "-fPIC", f"-I{inc}"]
+        cmds = [base + ["-shared", str(src), "-o", str(so)] + link]
+        if testbench is not None:
+            tb = Path(testbench)
+            cmds.append(base + ["-w", "-DGNNB_REFERENCE_MODEL_H", f"-I{tb}", str(tb / "model_tb.cpp"), str(src),
+                                "-o", str(self.model_dir / "result")] + link)
+        for cmd in cmds:
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+        return so
 
     def gen_testbench(self, gen_testbench_data=True):
         os.makedirs(self.model_dir, exist_ok=True)
@@ -151,9 +263,20 @@ class Project:
 
     def gen_makefile(self):
         os.makedirs(self.model_dir, exist_ok=True)
+        inc = Path(__file__).resolve().parent.parent / "include"
+        libdir = Path(__file__).resolve().parent
         (self.model_dir / "makefile_testbench").write_text(
-            "# gnn_builder_b200: nothing to compile per model -- libgnnb_b200.so takes the model\n"
-            "# description at run time (see model_desc.json).\nrun:\n\t@true\n")
+            "# gnn_builder_b200: the Python flow needs nothing compiled per model (libgnnb_b200.so takes\n"
+            "# the model description at run time, see model_desc.json).  `make lib` builds the generated\n"
+            "# model.cpp (<name>_top with the reference's signature, forwarding to the GPU library);\n"
+            "# `make result` links the reference's own model_tb.cpp against it when model.h,\n"
+            "# gnn_builder_lib.h and model_tb.cpp of the reference are placed next to it.\n"
+            f"CXXFLAGS = -fPIC -O3 -std=c++14 -I{inc}\n"
+            f"LDLIBS = -L{libdir} -lgnnb_b200 -Wl,-rpath,{libdir}\n"
+            "run:\n\t@true\n"
+            f"lib: model.cpp\n\t$(CXX) $(CXXFLAGS) -shared model.cpp -o lib{self.name}.so $(LDLIBS)\n"
+            "result: model.cpp model_tb.cpp model.h\n"
+            "\t$(CXX) $(CXXFLAGS) -Wno-unused-result model.cpp model_tb.cpp -o result $(LDLIBS)\n")
 
     # ------------------------------------------------------------------ running
     def build_and_run_testbench(self, batched: bool = False):
