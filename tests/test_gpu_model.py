@@ -276,3 +276,39 @@ def test_non_finite_inputs_do_not_leak_between_graphs(gnnb, orc):
         eng.set_path(gnnb.PATH_AUTO)
         assert rel_err(eng.run(batch), clean) < TOL
         assert eng.last_kernel == "fused-tcgen05"
+
+
+VARIANTS = {
+    # (base workload, overrides): shapes and options the BASELINE configs do not reach
+    "gin_eps": ("c2_gin_qm9", dict(gin_eps=0.25)),                        # eps * x_v added in registers
+    "gin_gelu_noskip": ("c2_gin_qm9", dict(activation="gelu", skip=False, hidden_dim=64)),
+    "gin_min_width_wide_input": ("c2_gin_qm9", dict(hidden_dim=16, in_dim=40, mlp_hidden_dim=16)),
+    "gcn_48_tanh_4layers": ("c1_gcn_esol", dict(hidden_dim=48, num_layers=4, activation="tanh")),
+    "sage_96_max_pool": ("c3_sage_hiv", dict(hidden_dim=96, num_layers=2, pools=["max"],
+                                               mlp_hidden_layers=1)),
+    "sage_sigmoid_5layers": ("c3_sage_hiv", dict(hidden_dim=32, num_layers=5, activation="sigmoid")),
+    "gcn_one_layer": ("c1_gcn_esol", dict(num_layers=1, hidden_dim=128, pools=["add", "max"])),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_fused_tc_model_variants(gnnb, orc, variant):
+    """layer widths with 1-4 K atoms and partial column blocks, GIN eps, non-ReLU activations, with
+    and without skip connections, 1-5 layers, single pools: fused tcgen05 kernel against the oracle"""
+    import dataclasses
+
+    from conftest import workload_by_name
+    from gnn_builder_b200.models import build_model
+
+    base, over = VARIANTS[variant]
+    w = dataclasses.replace(workload_by_name(base), **over)
+    model = build_model(w, pna_delta=w.pna_delta, seed=11)
+    params = model.named_parameter_arrays()
+    batch = gnnb.make_molecular_batch(700, w.mu_nodes, w.mu_edges, w.in_dim, seed=5)
+    ref = orc.model_forward_batch(model.describe(), list(params.values()), batch)
+    with gnnb.Engine(model) as eng:
+        out = eng.run(batch)
+        assert eng.last_kernel == "fused-tcgen05", (variant, eng.last_kernel)
+        assert rel_err(out, ref) < TOL, (variant, rel_err(out, ref))
+        eng.set_path(gnnb.PATH_LAYERWISE)
+        assert rel_err(eng.run(batch), ref) < TOL
