@@ -485,10 +485,10 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
     }
     // degree bucketing only matters for big graphs (molecular graphs have in-degree <= ~8)
     int n_heavy = 0, heavy_slices = 0;
-    const int heavy_threshold = heavy_threshold();
+    const int heavy_thr = heavy_threshold();
     if (!strict && d.num_layers > 0 && d.conv_type != GNNB_CONV_PNA && n_graphs > 0 &&
         T64 / n_graphs > 50000) {
-        GNNB_TRY(find_heavy_rows(in_deg, T, heavy_threshold, m->tws, &n_heavy, s, launches));
+        GNNB_TRY(find_heavy_rows(in_deg, T, heavy_thr, m->tws, &n_heavy, s, launches));
         GNNB_TRY(heavy_setup(m->tws, n_heavy, maxf, &heavy_slices));
     }
 
@@ -513,7 +513,7 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
         a.x = cur; a.ldx = cur_ld; a.F = fi; a.out = m->agg.as<float>(); a.ldo = round_up(fi, 4);
         a.offsets = offsets; a.nbr = nbr; a.in_deg = in_deg; a.dinv = dinv; a.n = T;
         a.eps = d.gin_eps; a.heavy_rows = m->tws.heavy_rows.as<int32_t>(); a.n_heavy = n_heavy;
-        a.heavy_threshold = heavy_threshold;
+        a.heavy_threshold = heavy_thr;
         a.heavy_partial = m->tws.heavy_partial.as<float>(); a.heavy_slices = heavy_slices;
         switch (d.conv_type) {
         case GNNB_CONV_GCN: {
