@@ -156,3 +156,13 @@ def test_dataset_stats_and_tb_data_roundtrip(tmp_path):
     p2, b2, g2 = read_tb_data(tmp_path / "tb", 9, {"w": (2, 3)})
     assert np.array_equal(p2["w"], params["w"]) and np.array_equal(g2, np.ones((5, 2)))
     assert np.array_equal(b2.x, b.slice(0, 5).x) and np.array_equal(b2.coo, b.slice(0, 5).coo)
+
+
+def test_library_is_built_from_the_current_sources():
+    """a failed rebuild must not leave an older libgnnb_b200.so behind unnoticed: the in-tree
+    library may not be older than csrc/ or the public header (build.py rebuilds it)"""
+    from gnn_builder_b200 import build
+
+    if build._stale():
+        build.build()          # raises with the compiler output if the sources do not compile
+    assert not build._stale()
