@@ -312,3 +312,37 @@ def test_fused_tc_model_variants(gnnb, orc, variant):
         assert rel_err(out, ref) < TOL, (variant, rel_err(out, ref))
         eng.set_path(gnnb.PATH_LAYERWISE)
         assert rel_err(eng.run(batch), ref) < TOL
+
+
+def test_two_handles_from_two_host_threads(gnnb, orc):
+    """the boundary contract: handles are independent -- own stream, own weights and
+    workspaces, thread-local error state -- so two host threads can drive two models at once
+    (the generated top is not re-entrant: file-scope statics, model.cpp.jinja:7-22)"""
+    import threading
+
+    jobs = []
+    for name, seed in (("c2_gin_qm9", 31), ("c1_gcn_esol", 32), ("c4_pna_lipo", 33)):
+        w, model, params = model_and_params(name)
+        batch = gnnb.make_molecular_batch(3000, w.mu_nodes, w.mu_edges, w.in_dim, seed=seed)
+        ref = orc.model_forward_batch(model.describe(), list(params.values()), batch)
+        jobs.append((name, model, batch, ref))
+    errors, results = [], {}
+
+    def work(name, model, batch, ref):
+        try:
+            with gnnb.Engine(model) as eng:
+                for _ in range(6):
+                    out = eng.run(batch)
+                    if rel_err(out, ref) >= TOL:
+                        errors.append((name, rel_err(out, ref)))
+                results[name] = out
+        except Exception as exc:  # noqa: BLE001
+            errors.append((name, repr(exc)))
+
+    threads = [threading.Thread(target=work, args=j) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert set(results) == {j[0] for j in jobs}
