@@ -92,7 +92,6 @@ struct TLinear {
     const float *img;   // weight image: per K atom [hi N x 128 B | lo N x 128 B]
     const float *bias;
     int K, N, KA;
-    int split;          // output linear with N > 64: issued as two column halves [0,64) and [64,N)
 };
 
 struct TcParams {
@@ -245,30 +244,6 @@ __device__ __forceinline__ void produce_linear(Misc &ms, uint32_t ring, uint32_t
     const uint32_t bytes = (uint32_t)L.N * tc::ROW_BYTES;
     const unsigned char *hi = reinterpret_cast<const unsigned char *>(L.img) + copy_off;
     const unsigned char *lo = hi + bytes;
-    if (L.split) {
-        // per column half: rows [0,64) / [64,N) of every atom image; a unit = that half of two
-        // consecutive K atoms (2 x <= 8 KB in one slot), first all hi parts, then all lo parts
-        for (int nh = 0; nh < 2; nh++) {
-            const uint32_t hbytes = (uint32_t)(nh ? L.N - 64 : 64) * tc::ROW_BYTES;
-            const unsigned char *half = hi + (size_t)nh * 64 * tc::ROW_BYTES;
-            for (int part = 0; part < 2; part++) {
-                for (int ka0 = 0; ka0 < L.KA; ka0 += 2) {
-                    const int npair = min(2, L.KA - ka0);
-                    const uint32_t s = prod & (NSLOT - 1), use = prod / NSLOT;
-                    if (use > 0) tc::mbar_wait(&ms.bar_empty[s], (use - 1) & 1);
-                    if (leader) {
-                        tc::mbar_expect_tx(&ms.bar_full[s], hbytes * (uint32_t)npair);
-                        for (int j = 0; j < npair; j++)
-                            tc::bulk_g2s_addr(ring + s * SLOT_STRIDE + (uint32_t)j * (SLOT_STRIDE / 2),
-                                              half + (size_t)(2 * (ka0 + j) + part) * bytes, hbytes,
-                                              &ms.bar_full[s]);
-                    }
-                    prod++;
-                }
-            }
-        }
-        return;
-    }
     for (int part = 0; part < 2; part++) {
         const unsigned char *src = part ? lo : hi;
         for (int ka = 0; ka < L.KA; ka++) {
@@ -296,60 +271,6 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &co
     const int KA0 = KA < 2 ? KA : 2;   // atoms inside the first 64 columns
     const uint32_t idesc = tc::make_idesc_tf32(TM, L.N);
     const uint32_t tmem_d = tmem_base + dcol, ahi = tmem_base + TM_AHI, alo = tmem_base + TM_ALO;
-    if (L.split) {
-        // two column halves, each complete over K before the other starts (units: see
-        // produce_linear); done[h] is committed per half, so the output pass overlaps half 1
-        bool waited1 = false;
-#pragma unroll 1
-        for (int nh = 0; nh < 2; nh++) {
-            const uint32_t idesc_h = tc::make_idesc_tf32(TM, nh ? L.N - 64 : 64);
-            const uint32_t d_h = tmem_d + 64u * (uint32_t)nh;
-            if (nh == 0) {
-                tc::mbar_wait(&ms.bar_ready[0], ready_cnt & 1);
-                tc::tc_fence_after();
-            }
-#pragma unroll 1
-            for (int part = 0; part < 2; part++) {
-                for (int ka0 = 0; ka0 < KA; ka0 += 2) {
-                    if (!waited1 && (ka0 >= KA0 || part == 1)) {   // operands beyond the first 64 columns
-                        tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1);
-                        tc::tc_fence_after();
-                        waited1 = true;
-                    }
-                    const int npair = min(2, KA - ka0);
-                    const uint32_t s = cons & (NSLOT - 1);
-                    tc::mbar_wait(&ms.bar_full[s], (cons / NSLOT) & 1);
-                    tc::tc_fence_after();
-                    for (int j = 0; j < npair; j++) {
-                        const int ka = ka0 + j;
-                        const uint32_t col = (uint32_t)(ka * tc::ATOM_K);
-                        const uint64_t bd = tc::make_desc(ring + s * SLOT_STRIDE + (uint32_t)j * (SLOT_STRIDE / 2));
-                        const uint32_t first = (ka == 0 && part == 0 && !accumulate) ? 0u : 1u;
-                        if (leader) {
-#pragma unroll
-                            for (int k8 = 0; k8 < tc::ATOM_K / tc::MMA_K; k8++) {
-                                tc::mma_tf32_ts(d_h, ahi + col + k8 * tc::MMA_K, bd + (uint64_t)(2 * k8), idesc_h,
-                                                k8 == 0 ? first : 1u);
-                                if (part == 0)
-                                    tc::mma_tf32_ts(d_h, alo + col + k8 * tc::MMA_K, bd + (uint64_t)(2 * k8),
-                                                    idesc_h, 1u);
-                            }
-                        }
-                    }
-                    if (leader) tc::mma_commit(&ms.bar_empty[s]);
-                    cons++;
-                }
-            }
-            if (!waited1) {   // (KA <= 2 and no lo part cannot happen, kept for symmetry)
-                tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1);
-                tc::tc_fence_after();
-                waited1 = true;
-            }
-            if (leader) tc::mma_commit(&ms.bar_done[nh]);
-        }
-        ready_cnt++;
-        return;
-    }
     tc::mbar_wait(&ms.bar_ready[0], ready_cnt & 1);
     tc::tc_fence_after();
     for (int ka = 0; ka < KA; ka++) {   // hi atoms
@@ -1306,9 +1227,6 @@ int fused_tc_prepare(gnnb_model *m)
     }
     if (rc != GNNB_OK) { delete plan; return rc; }
     const float *base = plan->images.as<float>();
-    // (opt-in: measured 2 % SLOWER on C2 -- twice as many N = 64 MMAs cost more than the overlap of
-    // the output pass with the second half gains -- kept as a tested option)
-    const bool split_out = getenv("GNNB_TC_SPLIT") != nullptr;
     size_t pi = 0;
     for (int k = 0; k < d.num_layers; k++) {
         const LayerPack &L = m->layers[k];
@@ -1317,16 +1235,11 @@ int fused_tc_prepare(gnnb_model *m)
             TLinear t;
             t.img = base + q.off; t.bias = bias; t.K = q.K; t.N = q.N;
             t.KA = (q.K + tc::ATOM_K - 1) / tc::ATOM_K;
-            t.split = 0;
             return t;
         };
         p.l0[k] = mk(pend[pi++], L.a.bias);
         if (d.conv_type == GNNB_CONV_GIN) p.l1[k] = mk(pend[pi++], L.b.bias);
         else if (d.conv_type == GNNB_CONV_SAGE) p.l1[k] = mk(pend[pi++], nullptr);
-        // the linear whose result the layer's output pass reads (GCN: l0, GIN / SAGE: l1) is issued
-        // per column half, so that the pass starts on columns [0,64) while [64,N) is still computed
-        TLinear &outl = d.conv_type == GNNB_CONV_GCN ? p.l0[k] : p.l1[k];
-        outl.split = (split_out && outl.N > 64) ? 1 : 0;
     }
     for (int j = 0; j < d.mlp_num_linear; j++) {
         const HeadPending &h = hpend[j];
@@ -1334,7 +1247,7 @@ int fused_tc_prepare(gnnb_model *m)
         p.head_n[j] = h.n_true;
         for (int c = 0; c < h.nch; c++) {
             TLinear t;
-            t.img = base + h.off[c]; t.bias = base + h.bias; t.K = h.K[c]; t.N = h.N; t.split = 0;
+            t.img = base + h.off[c]; t.bias = base + h.bias; t.K = h.K[c]; t.N = h.N;
             t.KA = (h.K[c] + tc::ATOM_K - 1) / tc::ATOM_K;
             p.hl[j][c] = t;
         }

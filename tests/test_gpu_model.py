@@ -347,9 +347,3 @@ def test_two_handles_from_two_host_threads(gnnb, orc):
     assert not errors, errors
     assert set(results) == {j[0] for j in jobs}
 
-
-@pytest.mark.parametrize("variant", ["gin_eps", "sage_96_max_pool", "gcn_one_layer"])
-def test_fused_tc_split_output_linears(gnnb, orc, variant, monkeypatch):
-    """GNNB_TC_SPLIT: the layer's output linear issued as two column halves (opt-in, slower on C2)"""
-    monkeypatch.setenv("GNNB_TC_SPLIT", "1")
-    test_fused_tc_model_variants(gnnb, orc, variant)
