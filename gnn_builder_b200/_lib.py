@@ -50,6 +50,7 @@ EXPORTS = [
     "gnnb_partition_tables", "gnnb_degree_inv_sqrt", "gnnb_gcn_conv_partition",
     "gnnb_pool_partial",
     "gnnb_debug_tc_gemm", "gnnb_debug_tc_agg_gemm", "gnnb_debug_tc_mma_rate",
+    "gnnb_debug_tc_bf16_ts",
 ]
 
 _lib = None
@@ -113,6 +114,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.gnnb_debug_tc_gemm.argtypes = [vp, vp, vp, ci, ci]
     lib.gnnb_debug_tc_agg_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci]
     lib.gnnb_debug_tc_mma_rate.argtypes = [ci, ci, ci, vp]
+    lib.gnnb_debug_tc_bf16_ts.argtypes = [vp, vp, vp, ci, ci, ci]
     lib.gnnb_partition_tables.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]
     lib.gnnb_degree_inv_sqrt.argtypes = [vp, vp, ci, vp]
     lib.gnnb_pool_partial.argtypes = [vp, C.c_int64, ci, vp, vp]

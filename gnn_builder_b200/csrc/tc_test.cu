@@ -442,6 +442,105 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_lean_kernel(int N, int rep
     if (warp == 0) tc::tmem_dealloc(tmem_d, 512);
 }
 
+
+// Probe for the next kernel generation: a kind::f16 MMA whose A operand (bf16) lives in TENSOR
+// MEMORY.  C[128][N] = bf16(A)[128][K] . bf16(B)[N][K]^T, fp32 accumulate.  `variant` selects the
+// hypothesis for how 16-bit A elements sit in the 32-bit TMEM cells of a lane:
+//   0  packed pairs: cell j = { k = 2j in the low half, k = 2j + 1 in the high half }, 8 cells per MMA
+//   1  one element per cell, in the low 16 bits, 16 cells per MMA
+//   2  one element per cell, in the high 16 bits (an fp32 value truncated in place), 16 cells per MMA
+// tools/tmem_bf16_probe.py prints which one reproduces the fp64 product of the truncated operands.
+__global__ void __launch_bounds__(128, 1) tc_bf16_ts_test_kernel(const float *__restrict__ A,
+                                                                 const float *__restrict__ B,
+                                                                 float *__restrict__ C, int K, int N,
+                                                                 int variant)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar_done;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char *b_s = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int KB = (K + 63) / 64;   // 64-element K atoms of the bf16 B operand
+    constexpr uint32_t TM_A = 128;
+
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
+    if (tid == 0) {
+        tc::mbar_init(&bar_done, 1);
+        tc::mbar_fence_init();
+    }
+    // B -> bf16 (truncation), K-major SWIZZLE_128B atoms of 64 elements, rows at a 128-byte pitch
+    for (int idx = tid; idx < TM * KB * 8; idx += blockDim.x) {
+        const int n = idx / (KB * 8), c8 = (idx % (KB * 8)) * 8;
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float lo = (n < N && c8 + 2 * j < K) ? B[(size_t)n * K + c8 + 2 * j] : 0.0f;
+            const float hi = (n < N && c8 + 2 * j + 1 < K) ? B[(size_t)n * K + c8 + 2 * j + 1] : 0.0f;
+            w[j] = __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
+        }
+        *reinterpret_cast<uint4 *>(b_s + tc::adj_chunk_offset(n, c8)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    {   // this thread's row of A -> tensor memory (K <= 128, K % 32 == 0)
+        const float *arow = A + (size_t)(32 * (warp & 3) + lane) * K;
+        const int cells = variant == 0 ? K / 2 : K;
+        for (int c0 = 0; c0 < cells; c0 += 16) {
+            float cell[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                uint32_t u;
+                if (variant == 0)
+                    u = __byte_perm(__float_as_uint(arow[2 * (c0 + j)]), __float_as_uint(arow[2 * (c0 + j) + 1]),
+                                    0x7632);
+                else if (variant == 1)
+                    u = __float_as_uint(arow[c0 + j]) >> 16;
+                else
+                    u = __float_as_uint(arow[c0 + j]) & 0xffff0000u;
+                cell[j] = __uint_as_float(u);
+            }
+            tc::tmem_st16(tmem_base + TM_A + lane_base + (uint32_t)c0, cell);
+        }
+        tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (warp == 0) {
+        const bool leader = tc::elect_one();
+        const uint32_t idesc = tc::make_idesc_bf16(TM, N, 0);
+        const uint32_t cells_per_mma = variant == 0 ? 8u : 16u;
+        const uint32_t b_addr = tc::smem_u32(b_s);
+        for (int ks = 0; ks < K / 16; ks++) {   // 16 elements of K per MMA; 4 k-steps per 64-element atom
+            const uint64_t bd = tc::make_desc(b_addr + (uint32_t)(ks >> 2) * tc::PLANE_BLOCK_BYTES) +
+                                (uint64_t)(2 * (ks & 3));
+            if (leader)
+                tc::mma_bf16_ts(tmem_base, tmem_base + TM_A + (uint32_t)ks * cells_per_mma, bd, idesc,
+                                ks == 0 ? 0u : 1u);
+        }
+        if (leader) tc::mma_commit(&bar_done);
+    }
+    tc::mbar_wait(&bar_done, 0);
+    tc::tc_fence_after();
+    {
+        const int row = 32 * (warp & 3) + lane;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            float v[32];
+            tc::tmem_ld32(tmem_base + lane_base + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (c0 + j < N) C[(size_t)row * N + c0 + j] = v[j];
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+}
+
 }  // namespace
 }  // namespace gnnb
 
@@ -537,5 +636,29 @@ extern "C" int gnnb_debug_tc_mma_rate(int flavour, int N, int reps, long long *c
     GNNB_CUDA(cudaDeviceSynchronize());
     GNNB_CUDA(cudaMemcpy(cycles, d, 2 * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(d);
+    return GNNB_OK;
+}
+
+// Probe: kind::f16 MMA with a bf16 A operand in tensor memory (see tc_bf16_ts_test_kernel).
+extern "C" int gnnb_debug_tc_bf16_ts(const float *A, const float *B, float *C, int K, int N, int variant)
+{
+    GNNB_REQUIRE(A && B && C, "null argument");
+    GNNB_REQUIRE(K >= 32 && K <= 128 && K % 32 == 0 && N >= 16 && N <= 128 && N % 16 == 0,
+                 "tc bf16 ts probe: K a multiple of 32 up to 128, N a multiple of 16 up to 128");
+    GNNB_REQUIRE(variant >= 0 && variant <= 2, "tc bf16 ts probe: variant 0, 1 or 2");
+    float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    GNNB_CUDA(cudaMalloc(&dA, sizeof(float) * 128 * K));
+    GNNB_CUDA(cudaMalloc(&dB, sizeof(float) * N * K));
+    GNNB_CUDA(cudaMalloc(&dC, sizeof(float) * 128 * N));
+    GNNB_CUDA(cudaMemcpy(dA, A, sizeof(float) * 128 * K, cudaMemcpyHostToDevice));
+    GNNB_CUDA(cudaMemcpy(dB, B, sizeof(float) * N * K, cudaMemcpyHostToDevice));
+    const size_t smem = 1024 + (size_t)2 * tc::PLANE_BLOCK_BYTES;
+    GNNB_CUDA(cudaFuncSetAttribute(tc_bf16_ts_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    tc_bf16_ts_test_kernel<<<1, 128, smem>>>(dA, dB, dC, K, N, variant);
+    GNNB_CUDA(cudaGetLastError());
+    GNNB_CUDA(cudaDeviceSynchronize());
+    GNNB_CUDA(cudaMemcpy(C, dC, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
     return GNNB_OK;
 }

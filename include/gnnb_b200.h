@@ -244,6 +244,11 @@ int gnnb_debug_tc_mma_rate(int flavour, int N, int reps, long long *cycles);
 int gnnb_debug_tc_agg_gemm(const float *Adj, const float *X, const float *W, float *C, float *agg,
                            int F, int N);
 
+/* Probe for a kind::f16 MMA with a bf16 A operand in tensor memory: C[128][N] = bf16(A)[128][K] .
+ * bf16(B)[N][K]^T; `variant` = the assumed layout of 16-bit elements in the 32-bit TMEM cells
+ * (0 packed pairs, 1 low half, 2 high half; tools/tmem_bf16_probe.py).  Host buffers. */
+int gnnb_debug_tc_bf16_ts(const float *A, const float *B, float *C, int K, int N, int variant);
+
 #ifdef __cplusplus
 }
 #endif
