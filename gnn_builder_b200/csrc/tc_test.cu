@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int flavour_in, int
 // that the compiler keeps them in uniform registers), 16 MMAs unrolled per iteration with
 // compile-time offsets, one elected lane executes the instruction.
 template <int FLAVOUR>
-__global__ void __launch_bounds__(128, 1) tc_mma_rate_lean_kernel(int N, int reps, long long *cycles)
+__global__ void __launch_bounds__(128, 1) tc_mma_rate_lean_kernel(int M, int N, int reps, long long *cycles)
 {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_done;
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_lean_kernel(int N, int rep
     tc::tc_fence_after();
     if (warp == 0) {
         const uint32_t a = __shfl_sync(0xffffffffu, tc::smem_u32(base), 0), b = a + tc::PLANE_BYTES;
-        const uint32_t idesc = FLAVOUR <= 1 ? tc::make_idesc_tf32(TM, N) : tc::make_idesc_bf16(TM, N, FLAVOUR == 3);
+        const uint32_t idesc = FLAVOUR <= 1 ? tc::make_idesc_tf32(M, N) : tc::make_idesc_bf16(M, N, FLAVOUR == 3);
         const uint64_t da0 = tc::make_desc(a), db0 = tc::make_desc(b);
         const uint64_t dm0 = tc::make_desc_mn(b, tc::PLANE_BLOCK_BYTES, 1024u);
         const bool leader = tc::elect_one();
@@ -606,8 +606,11 @@ extern "C" int gnnb_debug_tc_agg_gemm(const float *Adj, const float *X, const fl
 // Diagnostic: cycles[0] = cycles to ISSUE `reps` back-to-back MMAs, cycles[1] = until they completed.
 extern "C" int gnnb_debug_tc_mma_rate(int flavour, int N, int reps, long long *cycles)
 {
+    const int M = flavour >= 1000 ? 64 : 128;   // thousands digit: 64-row MMAs (lean kernels only)
+    flavour %= 1000;
     const int nacc = flavour / 100 > 0 ? flavour / 100 : 1;   // hundreds digit: accumulators to alternate
     flavour %= 100;
+    GNNB_REQUIRE(M == 128 || flavour >= 20, "64-row MMAs: lean flavours (20..23) only");
     GNNB_REQUIRE(cycles != nullptr && flavour >= 0 && flavour <= 23 && N >= 16 && N <= 256 && N % 16 == 0 &&
                  reps >= 1, "bad argument");
     long long *d = nullptr;
@@ -619,16 +622,16 @@ extern "C" int gnnb_debug_tc_mma_rate(int flavour, int N, int reps, long long *c
         switch (flavour - 20) {
         case 0:
             GNNB_CUDA(cudaFuncSetAttribute(tc_mma_rate_lean_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tc_mma_rate_lean_kernel<0><<<1, 128, smem>>>(N, reps, d); break;
+            tc_mma_rate_lean_kernel<0><<<1, 128, smem>>>(M, N, reps, d); break;
         case 1:
             GNNB_CUDA(cudaFuncSetAttribute(tc_mma_rate_lean_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tc_mma_rate_lean_kernel<1><<<1, 128, smem>>>(N, reps, d); break;
+            tc_mma_rate_lean_kernel<1><<<1, 128, smem>>>(M, N, reps, d); break;
         case 2:
             GNNB_CUDA(cudaFuncSetAttribute(tc_mma_rate_lean_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tc_mma_rate_lean_kernel<2><<<1, 128, smem>>>(N, reps, d); break;
+            tc_mma_rate_lean_kernel<2><<<1, 128, smem>>>(M, N, reps, d); break;
         default:
             GNNB_CUDA(cudaFuncSetAttribute(tc_mma_rate_lean_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tc_mma_rate_lean_kernel<3><<<1, 128, smem>>>(N, reps, d); break;
+            tc_mma_rate_lean_kernel<3><<<1, 128, smem>>>(M, N, reps, d); break;
         }
     } else
         tc_mma_rate_kernel<<<1, 128, smem>>>(flavour, N, reps, nacc, d);

@@ -239,7 +239,8 @@ int gnnb_debug_tc_gemm(const float *A, const float *W, float *C, int K, int N);
  * the fused kernel.  agg (optional, [128][F]) receives Adj . X.  Host buffers. */
 /* Cycles to issue / complete `reps` back-to-back tcgen05.mma (M = 128, N columns); flavour 0 tf32
  * with both operands in shared memory, 1 tf32 with A in tensor memory, 2 bf16 K-major, 3 bf16 with
- * an MN-major B operand.  cycles[2]. */
+ * an MN-major B operand; + 20 = lean warp-uniform issue loop; + 1000 = M = 64 instead of 128 (lean
+ * flavours only).  cycles[2]. */
 int gnnb_debug_tc_mma_rate(int flavour, int N, int reps, long long *cycles);
 int gnnb_debug_tc_agg_gemm(const float *Adj, const float *X, const float *W, float *C, float *agg,
                            int F, int N);

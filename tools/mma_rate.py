@@ -11,9 +11,10 @@ from gnn_builder_b200 import _lib  # noqa: E402
 lib = _lib.load()
 names = ["tf32 SS", "tf32 TS (A in TMEM)", "bf16 SS K-major", "bf16 SS, B MN-major"]
 for flavour, name in [(f, n) for f, n in enumerate(names)] + [
-        (20 + f, n + " [lean warp-uniform issue]") for f, n in enumerate(names)]:
+        (20 + f, n + " [lean warp-uniform issue]") for f, n in enumerate(names)] + [
+        (1020 + f, n + " [lean, M = 64]") for f, n in enumerate(names)]:
     for N in (32, 64, 128, 256):
-        if flavour % 10 == 3 and N == 256:
+        if flavour % 10 == 3 and N == 256:   # (MN-major B: 128 columns staged)
             continue
         for reps in (512,):
             cyc = np.zeros(2, np.int64)
