@@ -166,3 +166,28 @@ def test_library_is_built_from_the_current_sources():
     if build._stale():
         build.build()          # raises with the compiler output if the sources do not compile
     assert not build._stale()
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """the boundary is a C ABI: include/gnnb_b200.h compiles as strict C99 and a C program links
+    against the library (no CUDA device needed for the calls it makes)"""
+    import subprocess
+
+    from gnn_builder_b200 import _lib
+
+    _lib.load()
+    src = tmp_path / "client.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "gnnb_b200.h"\n'
+        "int main(void)\n{\n    gnnb_model_desc d;\n    int count = -1;\n    (void)d;\n"
+        '    printf("version %d\\n", gnnb_version());\n'
+        "    if (gnnb_device_count(&count) != GNNB_OK && gnnb_last_error()[0] == 0) return 2;\n"
+        "    return 0;\n}\n")
+    libdir = Path(_lib.LIB_PATH).parent
+    exe = tmp_path / "client"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic",
+                        f"-I{ROOT / 'include'}", str(src), f"-L{libdir}", "-lgnnb_b200",
+                        f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("version ")
