@@ -49,11 +49,16 @@ EXPORTS = [
     "gnnb_global_add_pool", "gnnb_global_mean_pool", "gnnb_global_max_pool",
     "gnnb_partition_tables", "gnnb_degree_inv_sqrt", "gnnb_gcn_conv_partition",
     "gnnb_pool_partial",
-    "gnnb_debug_tc_gemm", "gnnb_debug_tc_agg_gemm", "gnnb_debug_tc_mma_rate",
-    "gnnb_debug_tc_bf16_ts",
+    "gnnb_halo_pack", "gnnb_halo_signal", "gnnb_halo_wait", "gnnb_ipc_alloc", "gnnb_ipc_open",
+    "gnnb_ipc_close", "gnnb_ipc_free", "gnnb_mark_hub_sources", "gnnb_gcn_conv_halo",
 ]
+# include/gnnb_b200_debug.h: tcgen05 probes in libgnnb_b200_debug.so (tests / tools only)
+DEBUG_LIB_PATH = PKG / "libgnnb_b200_debug.so"
+DEBUG_EXPORTS = ["gnnb_debug_tc_gemm", "gnnb_debug_tc_agg_gemm", "gnnb_debug_tc_mma_rate",
+                 "gnnb_debug_tc_bf16_ts"]
 
 _lib = None
+_debug_lib = None
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:
@@ -66,7 +71,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         from . import build as _build
 
         _build.build()
-    lib = C.CDLL(str(LIB_PATH), mode=getattr(os, "RTLD_NOW", 2))
+    lib = C.CDLL(str(LIB_PATH), mode=getattr(os, "RTLD_NOW", 2) | getattr(os, "RTLD_GLOBAL", 0x100))
     lib.gnnb_last_error.restype = C.c_char_p
     lib.gnnb_model_stream.restype = C.c_void_p
     lib.gnnb_model_stream.argtypes = [C.c_void_p]
@@ -111,16 +116,38 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.gnnb_simple_conv.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, vp, ci, ci]
     for k in ("add", "mean", "max"):
         getattr(lib, f"gnnb_global_{k}_pool").argtypes = [ci, ci, vp, vp, ci]
-    lib.gnnb_debug_tc_gemm.argtypes = [vp, vp, vp, ci, ci]
-    lib.gnnb_debug_tc_agg_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci]
-    lib.gnnb_debug_tc_mma_rate.argtypes = [ci, ci, ci, vp]
-    lib.gnnb_debug_tc_bf16_ts.argtypes = [vp, vp, vp, ci, ci, ci]
+    lib.gnnb_halo_pack.argtypes = [vp, ci, ci, vp, vp, vp, ci, ci, vp]
+    lib.gnnb_halo_signal.argtypes = [vp, ci, C.c_uint64, vp]
+    lib.gnnb_halo_wait.argtypes = [vp, ci, C.c_uint64, vp, vp]
+    lib.gnnb_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]
+    lib.gnnb_ipc_open.argtypes = [vp, C.POINTER(vp)]
+    lib.gnnb_ipc_close.argtypes = [vp]
+    lib.gnnb_ipc_free.argtypes = [vp]
+    lib.gnnb_mark_hub_sources.argtypes = [vp, ci, ci, ci, C.c_int64, C.POINTER(ci), vp]
+    lib.gnnb_gcn_conv_halo.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci,
+                                       ci, ci, ci, vp]
     lib.gnnb_partition_tables.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]
     lib.gnnb_degree_inv_sqrt.argtypes = [vp, vp, ci, vp]
     lib.gnnb_pool_partial.argtypes = [vp, C.c_int64, ci, vp, vp]
     lib.gnnb_gcn_conv_partition.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci,
                                             ci, ci, vp]
     _lib = lib
+    return lib
+
+
+def load_debug() -> C.CDLL:
+    """libgnnb_b200_debug.so (include/gnnb_b200_debug.h): the tcgen05 probes used by tests/tools."""
+    global _debug_lib
+    if _debug_lib is not None:
+        return _debug_lib
+    load()   # the debug library resolves its helpers against the product library
+    lib = C.CDLL(str(DEBUG_LIB_PATH), mode=getattr(os, "RTLD_NOW", 2))
+    vp, ci = C.c_void_p, C.c_int
+    lib.gnnb_debug_tc_gemm.argtypes = [vp, vp, vp, ci, ci]
+    lib.gnnb_debug_tc_agg_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci]
+    lib.gnnb_debug_tc_mma_rate.argtypes = [ci, ci, ci, vp]
+    lib.gnnb_debug_tc_bf16_ts.argtypes = [vp, vp, vp, ci, ci, ci]
+    _debug_lib = lib
     return lib
 
 

@@ -9,7 +9,9 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libgnnb_b200.so"
-SOURCES = ["model.cu", "layers.cu", "tables.cu", "agg.cu", "gemm.cu", "gemm_tc.cu", "pool.cu", "fused.cu", "fused_tc.cu", "tc_test.cu"]
+DEBUG_LIB = PKG / "libgnnb_b200_debug.so"
+SOURCES = ["model.cu", "layers.cu", "tables.cu", "agg.cu", "gemm.cu", "gemm_tc.cu", "pool.cu", "fused.cu", "fused_tc.cu"]
+DEBUG_SOURCES = ["tc_test.cu"]   # tcgen05 probes: a separate test library, not in the product
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -26,11 +28,11 @@ def nvcc() -> str:
 
 
 def _stale() -> bool:
-    if not LIB.exists():
+    if not LIB.exists() or not DEBUG_LIB.exists():
         return True
-    t = LIB.stat().st_mtime
+    t = min(LIB.stat().st_mtime, DEBUG_LIB.stat().st_mtime)
     deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [
-        PKG.parent / "include" / "gnnb_b200.h"]
+        PKG.parent / "include" / "gnnb_b200.h", PKG.parent / "include" / "gnnb_b200_debug.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 
@@ -41,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     obj_dir = PKG / "build"
     obj_dir.mkdir(exist_ok=True)
     procs = []
-    for src in SOURCES:
+    for src in SOURCES + DEBUG_SOURCES:
         obj = obj_dir / (src + ".o")
         cmd = [nvcc(), *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
@@ -54,11 +56,16 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
     (obj_dir / "ptxas.log").write_text("\n".join(log))
-    cmd = [nvcc(), "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    main_objs = objs[:len(SOURCES)]
+    dbg_objs = objs[len(SOURCES):]
+    for lib, lobjs, extra in (
+            (LIB, main_objs, []),
+            (DEBUG_LIB, dbg_objs, [f"-L{PKG}", "-l:libgnnb_b200.so", "-Xlinker", "-rpath=$ORIGIN"])):
+        cmd = [nvcc(), "-shared", "-o", str(lib), *lobjs, "-gencode",
+               "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", *extra]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     if verbose:
         print("\n".join(log))
     return LIB

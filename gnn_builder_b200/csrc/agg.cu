@@ -25,6 +25,7 @@ template <>
 struct Vec<1> {
     float v[1];
     __device__ __forceinline__ void load(const float *p) { v[0] = __ldg(p); }
+    __device__ __forceinline__ void load_rw(const float *p) { v[0] = *p; }   // data this kernel also writes
     __device__ __forceinline__ void store(float *p) const { p[0] = v[0]; }
 };
 template <>
@@ -35,11 +36,45 @@ struct Vec<4> {
         const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
+    __device__ __forceinline__ void load_rw(const float *p)
+    {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
     __device__ __forceinline__ void store(float *p) const
     {
         *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
 };
+
+// L2 eviction-priority policies for the gathers of a large graph (hub_bit mode): rows of hub
+// sources are kept (evict_last), everything else streams through (evict_first).
+__device__ __forceinline__ uint64_t l2_policy_keep()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+template <int VEC>
+__device__ __forceinline__ void load_hint(Vec<VEC> &x, const float *p, uint64_t pol);
+template <>
+__device__ __forceinline__ void load_hint<1>(Vec<1> &x, const float *p, uint64_t pol)
+{
+    asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;\n" : "=f"(x.v[0]) : "l"(p), "l"(pol));
+}
+template <>
+__device__ __forceinline__ void load_hint<4>(Vec<4> &x, const float *p, uint64_t pol)
+{
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;\n"
+        : "=f"(x.v[0]), "=f"(x.v[1]), "=f"(x.v[2]), "=f"(x.v[3])
+        : "l"(p), "l"(pol));
+}
 
 template <int MODE, bool STRICT>
 __device__ __forceinline__ float neighbor_scale(const AggArgs &a, int deg_v, float dinv_v, int u)
@@ -76,6 +111,35 @@ __device__ __forceinline__ void gather_range(const AggArgs &a, int off, int k0, 
                                              float dinv_v, int c, Vec<VEC> &acc)
 {
     int k = k0;
+    if (!STRICT && a.hub_bit) {
+        const uint64_t keep = l2_policy_keep(), stream = l2_policy_stream();
+        for (; k + 4 <= k1; k += 4) {
+            int u[4];
+            Vec<VEC> x[4];
+            float sc[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) u[j] = __ldg(a.nbr + off + k + j);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint64_t pol = u[j] < 0 ? keep : stream;
+                u[j] &= 0x7fffffff;
+                load_hint<VEC>(x[j], a.x + (size_t)u[j] * a.ldx + c, pol);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) sc[j] = neighbor_scale<MODE, STRICT>(a, deg_v, dinv_v, u[j]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) accumulate<VEC, MODE, STRICT>(acc, x[j], sc[j]);
+        }
+        for (; k < k1; k++) {
+            int u = __ldg(a.nbr + off + k);
+            const uint64_t pol = u < 0 ? keep : stream;
+            u &= 0x7fffffff;
+            Vec<VEC> x;
+            load_hint<VEC>(x, a.x + (size_t)u * a.ldx + c, pol);
+            accumulate<VEC, MODE, STRICT>(acc, x, neighbor_scale<MODE, STRICT>(a, deg_v, dinv_v, u));
+        }
+        return;
+    }
     for (; k + 4 <= k1; k += 4) {
         int u[4];
         Vec<VEC> x[4];
@@ -102,6 +166,10 @@ template <int VEC, int MODE, bool STRICT>
 __device__ __forceinline__ void finish_row(const AggArgs &a, int v, int deg_v, float dinv_v, int c,
                                            Vec<VEC> &acc)
 {
+    if (!STRICT && a.no_finish) {   // first part of a split CSR: the plain partial sum
+        acc.store(a.out + (size_t)v * a.ldo + c);
+        return;
+    }
     if (MODE == AGG_GCN) {
         Vec<VEC> xs;
         xs.load(a.x + (size_t)(v + a.row_base) * a.ldx + c);
@@ -147,14 +215,19 @@ __global__ void __launch_bounds__(256) agg_rows_kernel(const AggArgs a)
         const int v = (int)row0 + sub;
         if (v >= a.n) continue;
         const int deg_v = __ldg(a.in_deg + v);
-        if (a.n_heavy > 0 && deg_v > a.heavy_threshold) continue;  // CTA-per-row kernel does these
+        const int len_v = (!STRICT && a.counts != nullptr) ? __ldg(a.counts + v) : deg_v;
+        if (a.n_heavy > 0 && len_v > a.heavy_threshold) continue;  // CTA-per-row kernel does these
         const int off = __ldg(a.offsets + v);
         const float dinv_v = (MODE == AGG_GCN && !STRICT) ? __ldg(a.dinv + v + a.row_base) : 0.0f;
         for (int c = lg * VEC; c < a.F; c += LPR * VEC) {
             Vec<VEC> acc;
+            if (!STRICT && a.accumulate) {
+                acc.load_rw(a.out + (size_t)v * a.ldo + c);
+            } else {
 #pragma unroll
-            for (int i = 0; i < VEC; i++) acc.v[i] = 0.0f;
-            gather_range<VEC, MODE, STRICT>(a, off, 0, deg_v, deg_v, dinv_v, c, acc);
+                for (int i = 0; i < VEC; i++) acc.v[i] = 0.0f;
+            }
+            gather_range<VEC, MODE, STRICT>(a, off, 0, len_v, deg_v, dinv_v, c, acc);
             finish_row<VEC, MODE, STRICT>(a, v, deg_v, dinv_v, c, acc);
         }
     }
@@ -177,9 +250,10 @@ __global__ void __launch_bounds__(256) agg_heavy_kernel(const AggArgs a)
     for (int h = blockIdx.x; h < a.n_heavy; h += gridDim.x) {
         const int v = __ldg(a.heavy_rows + h);
         const int deg_v = __ldg(a.in_deg + v);
+        const int len_v = a.counts != nullptr ? __ldg(a.counts + v) : deg_v;
         const int off = __ldg(a.offsets + v);
         const float dinv_v = (MODE == AGG_GCN) ? __ldg(a.dinv + v + a.row_base) : 0.0f;
-        const int s0 = (int)((int64_t)deg_v * sl / S), s1 = (int)((int64_t)deg_v * (sl + 1) / S);
+        const int s0 = (int)((int64_t)len_v * sl / S), s1 = (int)((int64_t)len_v * (sl + 1) / S);
         const int per = (s1 - s0 + 7) / 8;
         const int k0 = min(s1, s0 + warp * per), k1 = min(s1, s0 + (warp + 1) * per);
         for (int c = lane * VEC; c < a.F; c += 32 * VEC) {
@@ -219,8 +293,12 @@ __global__ void __launch_bounds__(128) agg_heavy_combine_kernel(const AggArgs a)
         const float dinv_v = (MODE == AGG_GCN) ? __ldg(a.dinv + v + a.row_base) : 0.0f;
         for (int c = threadIdx.x * VEC; c < a.F; c += blockDim.x * VEC) {
             Vec<VEC> acc;
+            if (a.accumulate) {
+                acc.load_rw(a.out + (size_t)v * a.ldo + c);
+            } else {
 #pragma unroll
-            for (int i = 0; i < VEC; i++) acc.v[i] = 0.0f;
+                for (int i = 0; i < VEC; i++) acc.v[i] = 0.0f;
+            }
             for (int sl = 0; sl < S; sl++) {
                 Vec<VEC> t;
                 t.load(a.heavy_partial + ((size_t)h * S + sl) * a.F + c);
@@ -290,7 +368,11 @@ int launch_agg(const AggArgs &a_in, bool strict, cudaStream_t s, int *launches)
     AggArgs a = a_in;
     if (a.n <= 0) return GNNB_OK;
     GNNB_REQUIRE(a.F > 0, "aggregation: feature size must be positive");
-    if (strict) a.n_heavy = 0;
+    if (strict) {
+        GNNB_REQUIRE(a.counts == nullptr && !a.accumulate && !a.no_finish && !a.hub_bit,
+                     "split-CSR / hub-hint aggregation is FAST-mode only");
+        a.n_heavy = 0;
+    }
     if (a.mode == AGG_GCN && !strict)
         GNNB_REQUIRE(a.dinv != nullptr, "gcn aggregation needs the dinv table in fast mode");
     const bool v4 = (a.F % 4 == 0) && (a.ldx % 4 == 0) && (a.ldo % 4 == 0) && aligned16(a.x) &&

@@ -9,6 +9,13 @@ namespace gnnb {
 // ---------------------------------------------------------------- graph tables (tables.cu)
 struct TableWorkspace {
     DeviceBuf keys_in, keys_out, vals_in, vals_out, cub_tmp, heavy_rows, heavy_partial, counters;
+    DeviceBuf hub_hist, hub_cnt;
+    void release_all()
+    {
+        DeviceBuf *b[] = {&keys_in, &keys_out, &vals_in, &vals_out, &cub_tmp, &heavy_rows,
+                          &heavy_partial, &counters, &hub_hist, &hub_cnt};
+        for (DeviceBuf *x : b) x->release();
+    }
 };
 
 // edge_list [E][2] local ids; node_ptr/edge_ptr (device int64, G+1 entries) translate them to
@@ -19,14 +26,17 @@ struct TableWorkspace {
 int build_tables(const int32_t *edge_list, const int64_t *node_ptr, const int64_t *edge_ptr,
                  int64_t node_base, int64_t edge_base, int n_graphs, int n, int e, int32_t *in_deg, int32_t *out_deg, int32_t *offsets,
                  int32_t *nbr, int32_t *edge_index, TableWorkspace &ws, cudaStream_t s,
-                 int *launches);
+                 int *launches, int *bad = nullptr);
+// `bad` (device int, optional): set to 1 when an edge endpoint lies outside its graph; such edges
+// are dropped from the degree counts so the tables stay memory-safe, and the caller reports
+// GNNB_ERR_INVALID (the fused kernels report the same condition as status 2)
 // degree tables only (lib:1051-1083)
 int build_degree_tables(const int32_t *edge_list, int n, int e, int32_t *in_deg, int32_t *out_deg,
-                        cudaStream_t s, int *launches);
+                        cudaStream_t s, int *launches, int *bad = nullptr);
 // offsets + neighbor table from given in-degree (lib:1086-1166)
 int build_neighbor_tables(const int32_t *edge_list, const int32_t *in_deg, int n, int e,
                           int32_t *offsets, int32_t *nbr, int32_t *edge_index, TableWorkspace &ws,
-                          cudaStream_t s, int *launches);
+                          cudaStream_t s, int *launches, int *bad = nullptr);
 // CSR slice of a 1D row partition: edge_list holds the in-edges of the owned destination rows
 // [row_begin, row_begin + n_local) with GLOBAL node ids; neighbors keep their global ids
 int build_partition_tables(const int32_t *edge_list, int row_begin, int n_local, int e,
@@ -48,6 +58,21 @@ inline int heavy_threshold()
     return v;
 }
 int heavy_setup(TableWorkspace &ws, int n_heavy, int F, int *slices);
+// hub sources: copy of the neighbor table with bit 31 set on the most-referenced sources whose
+// feature rows fit budget_bytes (L2-resident set of the aggregation); tables.cu
+int mark_hub_sources(const int32_t *nbr_in, int32_t *nbr_out, int e, const int32_t *ref_cnt,
+                     int n_src, size_t row_bytes, size_t budget_bytes, TableWorkspace &ws,
+                     int *n_hubs_host, cudaStream_t s, int *launches);
+// L2 budget for hub rows in bytes (GNNB_HUB_L2_MB overrides; 0 disables the hints)
+inline size_t hub_l2_budget()
+{
+    static const size_t v = [] {
+        const char *e = getenv("GNNB_HUB_L2_MB");
+        const long mb = e ? atol(e) : 40;
+        return (size_t)(mb > 0 ? mb : 0) << 20;
+    }();
+    return v;
+}
 // dinv[i] = 1 / sqrt(1 + in_deg[i])
 int compute_dinv(const int32_t *in_deg, float *dinv, int n, cudaStream_t s, int *launches);
 
@@ -72,6 +97,14 @@ struct AggArgs {
     int heavy_slices;
     int row_base;          // row-partitioned graphs: global id of local row 0 (x / dinv are global,
                            // offsets / in_deg / out are local); 0 otherwise
+    // ---- FAST-mode extensions (all 0 / null by default)
+    const int32_t *counts; // row lengths when they differ from in_deg (one PART of a split CSR: the
+                           // rows' owned-source or halo-source edges); in_deg still feeds the mean
+    int accumulate;        // start every row sum from what `out` already holds (second CSR part)
+    int no_finish;         // store the plain partial sum: no self term / normalisation (first part)
+    int hub_bit;           // 1: bit 31 of a neighbor entry marks a hub source (high out-degree);
+                           // its row is loaded with an L2 evict_last policy, every other row with
+                           // evict_first, so the hub rows stay resident in the 126 MB L2
 };
 int launch_agg(const AggArgs &a, bool strict, cudaStream_t s, int *launches);
 

@@ -4,6 +4,7 @@
 // the reference; each call stages host buffers, runs the same kernels the model path uses on
 // the default stream, and returns when the results are back.
 #include <algorithm>
+#include <cstring>
 #include <utility>
 #include <vector>
 
@@ -65,9 +66,22 @@ class Stage {
             if (p.first == Wt) return p.second;
         return nullptr;
     }
+    // device int the table kernels set when an edge endpoint is outside [0, num_nodes)
+    int bad_flag(int **flag)
+    {
+        GNNB_TRY(scratch(1, &bad_));
+        GNNB_CUDA(cudaMemset(bad_, 0, sizeof(int)));
+        *flag = bad_;
+        return GNNB_OK;
+    }
     int finish()
     {
         GNNB_CUDA(cudaDeviceSynchronize());
+        if (bad_ != nullptr) {
+            int bad = 0;
+            GNNB_CUDA(cudaMemcpy(&bad, bad_, sizeof(int), cudaMemcpyDeviceToHost));
+            GNNB_REQUIRE(bad == 0, "edge_list holds a node index outside [0, num_nodes)");
+        }
         for (const Back &b : back_) GNNB_CUDA(cudaMemcpy(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost));
         return GNNB_OK;
     }
@@ -77,16 +91,12 @@ class Stage {
     std::vector<void *> owned_;
     std::vector<Back> back_;
     std::vector<std::pair<const float *, const float *>> images_;
+    int *bad_ = nullptr;
 };
 
 struct TempWs {
     TableWorkspace ws;
-    ~TempWs()
-    {
-        DeviceBuf *b[] = {&ws.keys_in, &ws.keys_out, &ws.vals_in, &ws.vals_out, &ws.cub_tmp,
-                          &ws.heavy_rows, &ws.heavy_partial, &ws.counters};
-        for (DeviceBuf *x : b) x->release();
-    }
+    ~TempWs() { ws.release_all(); }
 };
 
 // W[out][in] (reference layout, host or device) -> packed Wt[in][ldw] on the device
@@ -175,7 +185,9 @@ extern "C" int gnnb_compute_degree_tables(const int32_t *edge_list, int32_t *in_
     GNNB_TRY(st.in(edge_list, 2 * (size_t)num_edges, &coo));
     GNNB_TRY(st.out(in_degree_table, (size_t)num_nodes, &ind));
     GNNB_TRY(st.out(out_degree_table, (size_t)num_nodes, &outd));
-    GNNB_TRY(build_degree_tables(coo, num_nodes, num_edges, ind, outd, 0, nullptr));
+    int *bad;
+    GNNB_TRY(st.bad_flag(&bad));
+    GNNB_TRY(build_degree_tables(coo, num_nodes, num_edges, ind, outd, 0, nullptr, bad));
     return st.finish();
 }
 
@@ -195,7 +207,9 @@ extern "C" int gnnb_compute_neighbor_and_edge_index_tables(
     GNNB_TRY(st.out(neighbor_table_offsets, (size_t)num_nodes, &off));
     GNNB_TRY(st.out(neighbor_table, (size_t)num_edges, &nbr));
     if (edge_index_table) GNNB_TRY(st.out(edge_index_table, (size_t)num_edges, &eidx));
-    GNNB_TRY(build_neighbor_tables(coo, ind, num_nodes, num_edges, off, nbr, eidx, t.ws, 0, nullptr));
+    int *bad;
+    GNNB_TRY(st.bad_flag(&bad));
+    GNNB_TRY(build_neighbor_tables(coo, ind, num_nodes, num_edges, off, nbr, eidx, t.ws, 0, nullptr, bad));
     return st.finish();
 }
 
@@ -525,15 +539,110 @@ extern "C" int gnnb_global_max_pool(int num_nodes, int num_edges, const float *x
 // and the work is enqueued on `stream` (e.g. torch's current stream) so that it orders with the
 // NCCL all-gather of the feature shards issued on the same stream.
 namespace {
+// rows above the heavy threshold of one CSR (part), cached by the address of its row-length table
+struct HeavyCache {
+    const int32_t *key = nullptr;
+    int n = 0, n_heavy = 0;
+    DeviceBuf rows;
+};
 struct PartitionCache {
     TableWorkspace ws;
     DeviceBuf wt, img, agg, pool_tmp, pool_ptr;
     int64_t pool_n = -1;
     const int32_t *heavy_key = nullptr;
     int heavy_n = 0, n_heavy = 0, slices = 0;
+    HeavyCache part[2];   // owned-source / halo-source part of a split CSR
 };
 thread_local PartitionCache g_part;
+
+int heavy_rows_of(HeavyCache &hc, const int32_t *lengths, int n, cudaStream_t s)
+{
+    if (hc.key == lengths && hc.n == n) return GNNB_OK;
+    GNNB_TRY(find_heavy_rows(lengths, n, heavy_threshold(), g_part.ws, &hc.n_heavy, s, nullptr));
+    if (hc.n_heavy > 0) {
+        GNNB_TRY(hc.rows.ensure(sizeof(int32_t) * (size_t)hc.n_heavy));
+        GNNB_CUDA(cudaMemcpyAsync(hc.rows.ptr, g_part.ws.heavy_rows.ptr, sizeof(int32_t) * (size_t)hc.n_heavy,
+                                  cudaMemcpyDeviceToDevice, s));
+    }
+    hc.key = lengths;
+    hc.n = n;
+    return GNNB_OK;
+}
+
 }  // namespace
+
+// ---- halo exchange kernels ---------------------------------------------------------------
+namespace gnnb {
+namespace halo {
+constexpr int kMaxPeers = 16;
+struct PackArgs {
+    const float *x;
+    int ldx, F, n_peers;
+    const int32_t *send_idx;
+    long long off[kMaxPeers + 1];   // rows for peer p: send_idx[off[p] .. off[p+1])
+    float *dst[kMaxPeers];          // where they go: a local send buffer or the peer's halo region
+};
+// one warp per row: dst_p[i][:] = x[send_idx[off[p] + i]][:]; 16-byte stores when F % 4 == 0, so a
+// row of F = 128 floats leaves the SM as one coalesced 512-byte write (over NVLink when dst_p is
+// a peer mapping)
+__global__ void __launch_bounds__(256) halo_pack_kernel(const PackArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const long long total = a.off[a.n_peers];
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long stride = (long long)gridDim.x * (blockDim.x >> 5);
+    const bool v4 = (a.F % 4 == 0) && (a.ldx % 4 == 0);
+    for (long long i = warp0; i < total; i += stride) {
+        int p = 0;
+        while (p + 1 < a.n_peers && i >= a.off[p + 1]) p++;
+        const float *src = a.x + (size_t)__ldg(a.send_idx + i) * a.ldx;
+        float *dst = a.dst[p] + (size_t)(i - a.off[p]) * a.F;
+        if (v4) {
+            for (int c = lane * 4; c < a.F; c += 128)
+                *reinterpret_cast<float4 *>(dst + c) = __ldg(reinterpret_cast<const float4 *>(src + c));
+        } else {
+            for (int c = lane; c < a.F; c += 32) dst[c] = __ldg(src + c);
+        }
+    }
+}
+
+struct SignalArgs {
+    unsigned long long *flag[kMaxPeers];
+    int n;
+    unsigned long long value;
+};
+// The pack kernel before it on the stream has completed, so its stores are performed; a
+// system-scope release store of the epoch then tells every peer that this rank's rows landed.
+__global__ void halo_signal_kernel(const SignalArgs a)
+{
+    const int p = threadIdx.x;
+    if (p < a.n && a.flag[p] != nullptr) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(a.flag[p]), "l"(a.value) : "memory");
+    }
+}
+// Spins (acquire, system scope) until every flag has reached `value`; gives up after ~2 s of
+// SM clocks and reports through *timed_out instead of hanging the GPU.
+__global__ void halo_wait_kernel(const unsigned long long *flags, int n, unsigned long long value,
+                                 int *timed_out)
+{
+    const int p = threadIdx.x;
+    if (p >= n) return;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(flags + p) : "memory");
+        if (v >= value) break;
+        if (clock64() - t0 > 4000000000ll) {
+            atomicExch(timed_out, 1);
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+}  // namespace halo
+}  // namespace gnnb
+using namespace gnnb::halo;
 
 extern "C" int gnnb_partition_tables(const int32_t *edge_list_local, int row_begin, int n_local,
                                      int num_edges_local, int32_t *in_degree_local,
@@ -581,10 +690,12 @@ extern "C" int gnnb_gcn_conv_partition(int n_local, int row_begin, int n_total, 
     if (g_part.heavy_key != in_degree_local || g_part.heavy_n != n_local) {
         GNNB_TRY(find_heavy_rows(in_degree_local, n_local, heavy_threshold(), g_part.ws,
                                  &g_part.n_heavy, s, nullptr));
-        GNNB_TRY(heavy_setup(g_part.ws, g_part.n_heavy, emb_in, &g_part.slices));
         g_part.heavy_key = in_degree_local;
         g_part.heavy_n = n_local;
     }
+    // sized for THIS layer's emb_in on every call (ensure() only grows): the row list is cached
+    // across layers, the partial-sum scratch must follow the widest layer
+    GNNB_TRY(heavy_setup(g_part.ws, g_part.n_heavy, emb_in, &g_part.slices));
     AggArgs a{};
     a.mode = AGG_GCN; a.x = x_full; a.ldx = emb_in; a.F = emb_in; a.out = g_part.agg.as<float>();
     a.ldo = lda; a.offsets = offsets_local; a.nbr = neighbor_table_global; a.in_deg = in_degree_local;
@@ -620,4 +731,159 @@ extern "C" int gnnb_pool_partial(const float *x, int64_t n, int F, float *out, v
     const int pools[2] = {GNNB_POOL_ADD, GNNB_POOL_MAX};
     return launch_pool(x, F, F, g_part.pool_ptr.as<int64_t>(), 0, 1, n, pools, 2, out, g_part.pool_tmp, s,
                        nullptr);
+}
+
+// ============================================================================ halo exchange
+// Row partition with a true halo: every rank keeps its owned feature rows followed by
+// ONE copy of each remote row its in-edges reference ("ext" space: [owned | halo grouped by owner
+// rank]); gnn_builder_b200/distributed.py builds the index tables once.  Per layer the owners push
+// the rows their peers need (gnnb_halo_pack: into an NCCL send buffer, or straight into the peer's
+// halo region through a CUDA-IPC mapping, i.e. NVLink stores + gnnb_halo_signal / gnnb_halo_wait),
+// while the aggregation of the owned-source edges runs (phase 1 below); the halo-source edges,
+// the normalisation and the tcgen05 transform follow on arrival (phase 2).
+
+extern "C" int gnnb_halo_pack(const float *x, int ldx, int F, const int32_t *send_idx,
+                              const int64_t *send_off, float *const *dst, int n_peers, int max_ctas,
+                              void *stream)
+{
+    GNNB_REQUIRE(n_peers >= 0 && n_peers <= kMaxPeers, "halo pack: at most 16 peers");
+    GNNB_REQUIRE(F > 0 && ldx >= F && send_off != nullptr && dst != nullptr, "halo pack: bad arguments");
+    PackArgs a{};
+    a.x = x; a.ldx = ldx; a.F = F; a.n_peers = n_peers; a.send_idx = send_idx;
+    for (int p = 0; p <= n_peers; p++) a.off[p] = send_off[p];
+    for (int p = 0; p < n_peers; p++) {
+        GNNB_REQUIRE(send_off[p + 1] >= send_off[p], "halo pack: offsets must be non-decreasing");
+        a.dst[p] = dst[p];
+        GNNB_REQUIRE(send_off[p + 1] == send_off[p] || (dst[p] != nullptr && (reinterpret_cast<uintptr_t>(dst[p]) & 15) == 0),
+                     "halo pack: destination missing or not 16-byte aligned");
+    }
+    const long long total = a.off[n_peers];
+    if (total == 0) return GNNB_OK;
+    long long grid = (total + 7) / 8;
+    const long long cap = max_ctas > 0 ? max_ctas : kNumSMs * 8;
+    if (grid > cap) grid = cap;
+    halo_pack_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(a);
+    GNNB_CUDA(cudaGetLastError());
+    return GNNB_OK;
+}
+
+extern "C" int gnnb_halo_signal(uint64_t *const *peer_flags, int n_peers, uint64_t value, void *stream)
+{
+    GNNB_REQUIRE(n_peers >= 0 && n_peers <= kMaxPeers && peer_flags != nullptr, "halo signal: bad arguments");
+    if (n_peers == 0) return GNNB_OK;
+    SignalArgs a{};
+    a.n = n_peers; a.value = value;
+    for (int p = 0; p < n_peers; p++) a.flag[p] = reinterpret_cast<unsigned long long *>(peer_flags[p]);
+    halo_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+    GNNB_CUDA(cudaGetLastError());
+    return GNNB_OK;
+}
+
+extern "C" int gnnb_halo_wait(const uint64_t *flags, int n_flags, uint64_t value, int *timed_out,
+                              void *stream)
+{
+    GNNB_REQUIRE(n_flags >= 0 && n_flags <= 32 && flags != nullptr && timed_out != nullptr,
+                 "halo wait: bad arguments");
+    if (n_flags == 0) return GNNB_OK;
+    halo_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const unsigned long long *>(flags), n_flags, value, timed_out);
+    GNNB_CUDA(cudaGetLastError());
+    return GNNB_OK;
+}
+
+// CUDA-IPC plumbing for the peer mappings (one process per GPU): the library owns the allocation.
+extern "C" int gnnb_ipc_alloc(size_t bytes, void **ptr, void *handle64)
+{
+    GNNB_REQUIRE(ptr != nullptr && handle64 != nullptr && bytes > 0, "ipc alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    void *p = nullptr;
+    GNNB_CUDA(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return cuda_fail(e, "cudaIpcGetMemHandle", __FILE__, __LINE__);
+    }
+    memcpy(handle64, &h, 64);
+    *ptr = p;
+    return GNNB_OK;
+}
+extern "C" int gnnb_ipc_open(const void *handle64, void **ptr)
+{
+    GNNB_REQUIRE(ptr != nullptr && handle64 != nullptr, "ipc open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    GNNB_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GNNB_OK;
+}
+extern "C" int gnnb_ipc_close(void *ptr)
+{
+    if (ptr) GNNB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return GNNB_OK;
+}
+extern "C" int gnnb_ipc_free(void *ptr)
+{
+    if (ptr) GNNB_CUDA(cudaFree(ptr));
+    return GNNB_OK;
+}
+
+extern "C" int gnnb_mark_hub_sources(int32_t *neighbor_table, int num_entries, int num_sources,
+                                     int row_bytes, int64_t budget_bytes, int *num_hubs, void *stream)
+{
+    GNNB_REQUIRE(num_entries >= 0 && num_sources >= 0 && row_bytes > 0 && budget_bytes >= 0,
+                 "mark hub sources: bad arguments");
+    GNNB_REQUIRE(num_entries == 0 || is_device_pointer(neighbor_table), "mark hub sources takes a device pointer");
+    return mark_hub_sources(neighbor_table, neighbor_table, num_entries, nullptr, num_sources,
+                            (size_t)row_bytes, (size_t)budget_bytes, g_part.ws, num_hubs,
+                            (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int gnnb_gcn_conv_halo(int n_local, int n_ext, const float *x_ext, float *y_local,
+                                  const int32_t *own_offsets, const int32_t *own_counts,
+                                  const int32_t *own_nbr, const int32_t *halo_offsets,
+                                  const int32_t *halo_counts, const int32_t *halo_nbr,
+                                  const float *dinv_ext, const float *weight, const float *bias,
+                                  const float *skip_local, int emb_in, int emb_out, int act, int phase,
+                                  int hub_bit, void *stream)
+{
+    GNNB_REQUIRE(n_local >= 0 && n_ext >= n_local, "bad row counts");
+    GNNB_REQUIRE(emb_in > 0 && emb_out > 0 && act >= 0 && act <= GNNB_ACT_COS, "bad dims");
+    GNNB_REQUIRE(phase >= 1 && phase <= 3, "phase: 1 owned-source edges, 2 halo edges + transform, 3 both");
+    if (n_local == 0) return GNNB_OK;
+    GNNB_REQUIRE(is_device_pointer(x_ext) && is_device_pointer(y_local), "gnnb_gcn_conv_halo takes device pointers");
+    const bool has_halo = halo_counts != nullptr && n_ext > n_local;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int ldw = round_up(emb_out, 4), lda = round_up(emb_in, 4);
+    GNNB_TRY(g_part.agg.ensure(sizeof(float) * (size_t)n_local * lda));
+    AggArgs a{};
+    a.mode = AGG_GCN; a.x = x_ext; a.ldx = emb_in; a.F = emb_in; a.out = g_part.agg.as<float>();
+    a.ldo = lda; a.dinv = dinv_ext; a.n = n_local; a.row_base = 0;
+    a.heavy_threshold = heavy_threshold(); a.hub_bit = hub_bit ? 1 : 0;
+    auto run_part = [&](int which, const int32_t *off, const int32_t *cnt, const int32_t *nbr,
+                        bool accumulate, bool finish) -> int {
+        HeavyCache &hc = g_part.part[which];
+        GNNB_TRY(heavy_rows_of(hc, cnt, n_local, s));
+        int slices = 0;
+        GNNB_TRY(heavy_setup(g_part.ws, hc.n_heavy, emb_in, &slices));
+        AggArgs b = a;
+        b.offsets = off; b.nbr = nbr; b.in_deg = cnt;   // GCN fast mode reads the full degree from dinv only
+        b.heavy_rows = hc.rows.as<int32_t>(); b.n_heavy = hc.n_heavy;
+        b.heavy_partial = g_part.ws.heavy_partial.as<float>(); b.heavy_slices = slices;
+        b.accumulate = accumulate ? 1 : 0; b.no_finish = finish ? 0 : 1;
+        return launch_agg(b, false, s, nullptr);
+    };
+    if (phase & 1) GNNB_TRY(run_part(0, own_offsets, own_counts, own_nbr, false, !has_halo));
+    if (!(phase & 2)) return GNNB_OK;
+    if (has_halo) GNNB_TRY(run_part(1, halo_offsets, halo_counts, halo_nbr, true, true));
+    GNNB_TRY(g_part.wt.ensure(sizeof(float) * (size_t)emb_in * ldw));
+    GNNB_TRY(launch_transpose_weight(weight, g_part.wt.as<float>(), emb_out, emb_in, ldw, s, nullptr));
+    GNNB_TRY(g_part.img.ensure(sizeof(float) * gemm_tc_image_floats(emb_in, emb_out)));
+    GNNB_TRY(gemm_tc_build_image(g_part.wt.as<float>(), ldw, emb_in, emb_out, g_part.img.as<float>(), s));
+    GemmArgs g = simple_gemm(a.out, lda, emb_in, g_part.wt.as<float>(), ldw, bias, y_local, emb_out,
+                             n_local, emb_out, act);
+    g.skip = skip_local; g.ldskip = emb_in;
+    g.img1 = g_part.img.as<float>();
+    GNNB_TRY(launch_gemm(g, false, s, nullptr));
+    return GNNB_OK;
 }

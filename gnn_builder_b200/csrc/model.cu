@@ -188,8 +188,6 @@ extern "C" int gnnb_model_create(const gnnb_model_desc *desc, int device, gnnb_m
     GNNB_REQUIRE(d.gnn_act >= 0 && d.gnn_act <= GNNB_ACT_COS && d.mlp_act >= 0 &&
                      d.mlp_act <= GNNB_ACT_COS && d.out_act >= 0 && d.out_act <= GNNB_ACT_COS,
                  "unknown activation id");
-    if (d.skip && d.num_layers > 2)
-        GNNB_REQUIRE(true, "");  // interior layers are hidden->hidden: shapes always match
     int ndev = 0;
     GNNB_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0) GNNB_CUDA(cudaGetDevice(&device));
@@ -226,13 +224,11 @@ extern "C" int gnnb_model_destroy(gnnb_model_t *m)
     fused_tc_release(m);
     m->prof.release();
     DeviceBuf *bufs[] = {&m->weights, &m->weight_images, &m->st_x, &m->st_coo, &m->st_nptr, &m->st_eptr, &m->st_out,
-                         &m->in_deg, &m->out_deg, &m->offsets, &m->nbr, &m->dinv, &m->feat[0],
-                         &m->feat[1], &m->agg, &m->hid, &m->wide, &m->pooled, &m->hbuf[0],
-                         &m->hbuf[1], &m->pool_tmp, &m->ptr_tmp, &m->tws.keys_in, &m->tws.keys_out,
-                         &m->tws.vals_in, &m->tws.vals_out, &m->tws.cub_tmp, &m->tws.heavy_rows,
-                         &m->tws.heavy_partial,
-                         &m->tws.counters};
+                         &m->in_deg, &m->out_deg, &m->offsets, &m->nbr, &m->nbr_hub, &m->dinv,
+                         &m->feat[0], &m->feat[1], &m->agg, &m->hid, &m->wide, &m->pooled,
+                         &m->hbuf[0], &m->hbuf[1], &m->pool_tmp, &m->ptr_tmp, &m->edge_flag};
     for (DeviceBuf *b : bufs) b->release();
+    m->tws.release_all();
     for (int i = 0; i < 2; i++) {
         m->ch_x[i].release(); m->ch_coo[i].release(); m->ch_nptr[i].release(); m->ch_eptr[i].release();
         if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
@@ -406,11 +402,13 @@ extern "C" int gnnb_model_last_path(const gnnb_model_t *m) { return m ? m->last_
 extern "C" int gnnb_model_last_kernel(const gnnb_model_t *m) { return m ? m->last_kernel : 0; }
 extern "C" void *gnnb_model_stream(gnnb_model_t *m) { return m ? (void *)m->stream : nullptr; }
 static int fused_any_status(gnnb_model_t *m, int *status);
+static int edge_flag_check(gnnb_model_t *m);
 extern "C" int gnnb_model_synchronize(gnnb_model_t *m)
 {
     GNNB_REQUIRE(m != nullptr, "null model");
     GNNB_CUDA(cudaSetDevice(m->device));
     GNNB_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->last_path == GNNB_PATH_LAYERWISE) GNNB_TRY(edge_flag_check(m));
     if (m->last_path == GNNB_PATH_FUSED) {
         // the async entry point cannot fall back by itself: report capacity/index problems here
         int status = 0;
@@ -475,7 +473,7 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
         ProfScope ps(m->prof, PROF_TABLES, s);
         GNNB_TRY(build_tables(coo, n_graphs > 1 ? node_ptr : nullptr, edge_ptr, node_base, edge_base,
                               n_graphs, T, E, in_deg, m->out_deg.as<int32_t>(), offsets, nbr,
-                              nullptr, m->tws, s, launches));
+                              nullptr, m->tws, s, launches, m->edge_flag.as<int>()));
     }
     const float *dinv = nullptr;
     if (d.conv_type == GNNB_CONV_GCN && !strict && d.num_layers > 0) {
@@ -484,12 +482,27 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
         dinv = m->dinv.as<float>();
     }
     // degree bucketing only matters for big graphs (molecular graphs have in-degree <= ~8)
-    int n_heavy = 0, heavy_slices = 0;
+    int n_heavy = 0, heavy_slices = 0, hub_bit = 0;
     const int heavy_thr = heavy_threshold();
+    m->last_hub_rows = 0;
     if (!strict && d.num_layers > 0 && d.conv_type != GNNB_CONV_PNA && n_graphs > 0 &&
         T64 / n_graphs > 50000) {
         GNNB_TRY(find_heavy_rows(in_deg, T, heavy_thr, m->tws, &n_heavy, s, launches));
         GNNB_TRY(heavy_setup(m->tws, n_heavy, maxf, &heavy_slices));
+        // a feature matrix larger than L2: keep the rows of the most-referenced sources resident
+        // (the out-degree table, lib:1051-1083, is what ranks them)
+        const size_t row_bytes = sizeof(float) * (size_t)std::max(d.in_dim, d.hidden_dim);
+        if (hub_l2_budget() > 0 && E > 0 && (size_t)T * row_bytes > (96u << 20)) {
+            ProfScope ps(m->prof, PROF_TABLES, s);
+            GNNB_TRY(m->nbr_hub.ensure(sizeof(int32_t) * (size_t)En));
+            GNNB_TRY(mark_hub_sources(nbr, m->nbr_hub.as<int32_t>(), E, m->out_deg.as<int32_t>(), T,
+                                      row_bytes, hub_l2_budget(), m->tws, &m->last_hub_rows, s,
+                                      launches));
+            if (m->last_hub_rows > 0) {
+                nbr = m->nbr_hub.as<int32_t>();
+                hub_bit = 1;
+            }
+        }
     }
 
     GNNB_TRY(m->feat[0].ensure(sizeof(float) * (size_t)Tn * ldf));
@@ -515,6 +528,7 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
         a.eps = d.gin_eps; a.heavy_rows = m->tws.heavy_rows.as<int32_t>(); a.n_heavy = n_heavy;
         a.heavy_threshold = heavy_thr;
         a.heavy_partial = m->tws.heavy_partial.as<float>(); a.heavy_slices = heavy_slices;
+        a.hub_bit = hub_bit;
         switch (d.conv_type) {
         case GNNB_CONV_GCN: {
             a.mode = AGG_GCN;
@@ -606,6 +620,26 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
 }  // namespace gnnb
 
 // ---------------------------------------------------------------------------- run entry points
+// layerwise path: the table kernels flag edge endpoints outside their graph (like status 2 of the
+// fused kernels); cleared before a run, read once the stream has been synchronised
+static int edge_flag_reset(gnnb_model_t *m, cudaStream_t s)
+{
+    GNNB_TRY(m->edge_flag.ensure(sizeof(int)));
+    GNNB_CUDA(cudaMemsetAsync(m->edge_flag.ptr, 0, sizeof(int), s));
+    return GNNB_OK;
+}
+static int edge_flag_check(gnnb_model_t *m)
+{
+    int bad = 0;
+    if (m->edge_flag.ptr == nullptr) return GNNB_OK;
+    GNNB_CUDA(cudaMemcpy(&bad, m->edge_flag.ptr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) {
+        set_error("edge_list holds a node index outside its graph");
+        return GNNB_ERR_INVALID;
+    }
+    return GNNB_OK;
+}
+
 static int check_ready(gnnb_model_t *m)
 {
     GNNB_REQUIRE(m != nullptr, "null model");
@@ -681,6 +715,7 @@ extern "C" int gnnb_model_run_batch_async(gnnb_model_t *m, const float *x, const
     if (path == GNNB_PATH_FUSED)
         return run_fused(m, kernel, x, edge_list, node_ptr, edge_ptr, n_graphs, total_nodes, hint_n,
                          out, s);
+    GNNB_TRY(edge_flag_reset(m, s));
     return run_layerwise(m, x, edge_list, node_ptr, edge_ptr, 0, 0, n_graphs, total_nodes,
                          total_edges, out, s, &m->last_launches);
 }
@@ -879,10 +914,13 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
     GNNB_TRY(choose_path(m, (int)max_n, (int)max_e, &path, &kernel));
     m->last_path = path;
     m->last_kernel = kernel;
+    bool ran_layerwise = false;
     auto layerwise_chunks = [&]() -> int {
         // chunk the union so that the per-layer activations stay within a fixed budget
         const int64_t kChunkNodes = 4ll << 20;
         int g0 = 0;
+        ran_layerwise = true;
+        GNNB_TRY(edge_flag_reset(m, s));
         while (g0 < n_graphs) {
             int g1 = g0 + 1;
             while (g1 < n_graphs && hn[g1 + 1] - hn[g0] <= kChunkNodes) g1++;
@@ -922,6 +960,7 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
         GNNB_CUDA(cudaMemcpyAsync(out, dout, sizeof(float) * (size_t)n_graphs * d.mlp_out,
                                   cudaMemcpyDeviceToHost, s));
     GNNB_CUDA(cudaStreamSynchronize(s));
+    if (ran_layerwise) GNNB_TRY(edge_flag_check(m));
     return GNNB_OK;
 }
 

@@ -99,9 +99,11 @@ struct gnnb_model {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     // layerwise workspaces
-    gnnb::DeviceBuf in_deg, out_deg, offsets, nbr, dinv, feat[2], agg, hid, wide, pooled, hbuf[2],
-        pool_tmp, ptr_tmp;
+    gnnb::DeviceBuf in_deg, out_deg, offsets, nbr, nbr_hub, dinv, feat[2], agg, hid, wide, pooled,
+        hbuf[2], pool_tmp, ptr_tmp;
+    int last_hub_rows = 0;   // sources whose feature rows the last large-graph run kept L2-resident
     gnnb::TableWorkspace tws;
+    gnnb::DeviceBuf edge_flag;   // layerwise path: set by the table kernels on an out-of-range endpoint
 
     gnnb::Profiler prof;
     int last_launches = 0;

@@ -32,19 +32,32 @@ template <bool COUNT, bool VAL_IS_EDGE_INDEX>
 __global__ void edge_prepare_kernel(const int32_t *__restrict__ edge_list,
                                     const int64_t *__restrict__ node_ptr,
                                     const int64_t *__restrict__ edge_ptr, int64_t node_base,
-                                    int64_t edge_base, int n_graphs, int e,
+                                    int64_t edge_base, int n_graphs, int n, int e,
                                     uint32_t *__restrict__ keys, int32_t *__restrict__ vals,
-                                    int32_t *__restrict__ in_deg, int32_t *__restrict__ out_deg)
+                                    int32_t *__restrict__ in_deg, int32_t *__restrict__ out_deg,
+                                    int *__restrict__ bad)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
         const int2 sd = __ldg(reinterpret_cast<const int2 *>(edge_list) + i);
         int src = sd.x, dst = sd.y;
+        int limit = n;   // node ids are local to their graph: valid range [0, graph size)
+        int base = 0;
         if (node_ptr != nullptr) {
             const int g = find_segment(edge_ptr, n_graphs, (int64_t)i + edge_base);
-            const int base = (int)(__ldg(node_ptr + g) - node_base);
-            src += base;
-            dst += base;
+            const int64_t b0 = __ldg(node_ptr + g);
+            base = (int)(b0 - node_base);
+            limit = (int)(__ldg(node_ptr + g + 1) - b0);
         }
+        if ((unsigned)src >= (unsigned)limit || (unsigned)dst >= (unsigned)limit) {
+            // an endpoint outside its graph (the reference would index out of bounds, lib:1060-1062):
+            // flag it, keep the tables memory-safe (the edge is dropped from the degree counts and
+            // parked on node 0 in the sort input) -- the caller turns the flag into GNNB_ERR_INVALID
+            if (bad != nullptr) atomicExch(bad, 1);
+            if (keys) { keys[i] = 0u; vals[i] = 0; }
+            continue;
+        }
+        src += base;
+        dst += base;
         if (keys) {
             keys[i] = (uint32_t)dst;
             vals[i] = VAL_IS_EDGE_INDEX ? i : src;
@@ -99,6 +112,37 @@ __global__ void dinv_kernel(const int32_t *__restrict__ in_deg, float *__restric
         dinv[i] = 1.0f / sqrtf(1.0f + (float)__ldg(in_deg + i));
 }
 
+// ---- hub sources (large graphs): the sources referenced most often are marked in a copy of the
+// neighbor table (bit 31) so that the aggregation keeps their feature rows in L2 (agg.cu)
+__global__ void ref_count_kernel(const int32_t *__restrict__ nbr, int e, int32_t *__restrict__ cnt)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x)
+        atomicAdd(cnt + (__ldg(nbr + i) & 0x7fffffff), 1);
+}
+constexpr int kHubBins = 4096;
+__global__ void __launch_bounds__(256) count_hist_kernel(const int32_t *__restrict__ cnt, int n,
+                                                         unsigned int *__restrict__ hist)
+{
+    __shared__ unsigned int h[kHubBins];
+    for (int i = threadIdx.x; i < kHubBins; i += blockDim.x) h[i] = 0u;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = __ldg(cnt + i);
+        atomicAdd(&h[c < kHubBins - 1 ? c : kHubBins - 1], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHubBins; i += blockDim.x)
+        if (h[i]) atomicAdd(hist + i, h[i]);
+}
+__global__ void mark_hubs_kernel(const int32_t *nbr_in, int32_t *nbr_out,   // (may alias)
+                                 int e, const int32_t *__restrict__ cnt, int threshold)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
+        const int u = nbr_in[i] & 0x7fffffff;
+        nbr_out[i] = __ldg(cnt + u) >= threshold ? (u | (int32_t)0x80000000) : u;
+    }
+}
+
 inline int grid_for(int64_t work, int block)
 {
     int64_t g = ceil_div64(work, block);
@@ -145,7 +189,7 @@ int sort_pairs(TableWorkspace &ws, int e, int n, int32_t *vals_out, cudaStream_t
 }  // namespace
 
 int build_degree_tables(const int32_t *edge_list, int n, int e, int32_t *in_deg, int32_t *out_deg,
-                        cudaStream_t s, int *launches)
+                        cudaStream_t s, int *launches, int *bad)
 {
     if (n > 0) {
         GNNB_CUDA(cudaMemsetAsync(in_deg, 0, sizeof(int32_t) * (size_t)n, s));
@@ -153,7 +197,7 @@ int build_degree_tables(const int32_t *edge_list, int n, int e, int32_t *in_deg,
     }
     if (e > 0) {
         edge_prepare_kernel<true, false><<<grid_for(e, 256), 256, 0, s>>>(
-            edge_list, nullptr, nullptr, 0, 0, 0, e, nullptr, nullptr, in_deg, out_deg);
+            edge_list, nullptr, nullptr, 0, 0, 0, n, e, nullptr, nullptr, in_deg, out_deg, bad);
         GNNB_CUDA(cudaGetLastError());
         if (launches) ++*launches;
     }
@@ -162,7 +206,7 @@ int build_degree_tables(const int32_t *edge_list, int n, int e, int32_t *in_deg,
 
 int build_neighbor_tables(const int32_t *edge_list, const int32_t *in_deg, int n, int e,
                           int32_t *offsets, int32_t *nbr, int32_t *edge_index, TableWorkspace &ws,
-                          cudaStream_t s, int *launches)
+                          cudaStream_t s, int *launches, int *bad)
 {
     if (n <= 0) return GNNB_OK;
     GNNB_TRY(scan_offsets(in_deg, offsets, n, ws, s, launches));
@@ -171,8 +215,8 @@ int build_neighbor_tables(const int32_t *edge_list, const int32_t *in_deg, int n
     GNNB_TRY(ws.vals_in.ensure(sizeof(int32_t) * (size_t)e));
     if (edge_index) {
         edge_prepare_kernel<false, true><<<grid_for(e, 256), 256, 0, s>>>(
-            edge_list, nullptr, nullptr, 0, 0, 0, e, ws.keys_in.as<uint32_t>(), ws.vals_in.as<int32_t>(),
-            nullptr, nullptr);
+            edge_list, nullptr, nullptr, 0, 0, 0, n, e, ws.keys_in.as<uint32_t>(), ws.vals_in.as<int32_t>(),
+            nullptr, nullptr, bad);
         GNNB_CUDA(cudaGetLastError());
         GNNB_TRY(sort_pairs(ws, e, n, edge_index, s, launches));
         gather_sources_kernel<<<grid_for(e, 256), 256, 0, s>>>(edge_list, edge_index, e, nbr);
@@ -180,8 +224,8 @@ int build_neighbor_tables(const int32_t *edge_list, const int32_t *in_deg, int n
         if (launches) *launches += 2;
     } else {
         edge_prepare_kernel<false, false><<<grid_for(e, 256), 256, 0, s>>>(
-            edge_list, nullptr, nullptr, 0, 0, 0, e, ws.keys_in.as<uint32_t>(), ws.vals_in.as<int32_t>(),
-            nullptr, nullptr);
+            edge_list, nullptr, nullptr, 0, 0, 0, n, e, ws.keys_in.as<uint32_t>(), ws.vals_in.as<int32_t>(),
+            nullptr, nullptr, bad);
         GNNB_CUDA(cudaGetLastError());
         GNNB_TRY(sort_pairs(ws, e, n, nbr, s, launches));
         if (launches) ++*launches;
@@ -192,7 +236,7 @@ int build_neighbor_tables(const int32_t *edge_list, const int32_t *in_deg, int n
 int build_tables(const int32_t *edge_list, const int64_t *node_ptr, const int64_t *edge_ptr,
                  int64_t node_base, int64_t edge_base, int n_graphs, int n, int e, int32_t *in_deg, int32_t *out_deg, int32_t *offsets,
                  int32_t *nbr, int32_t *edge_index, TableWorkspace &ws, cudaStream_t s,
-                 int *launches)
+                 int *launches, int *bad)
 {
     if (n <= 0) return GNNB_OK;
     GNNB_CUDA(cudaMemsetAsync(in_deg, 0, sizeof(int32_t) * (size_t)n, s));
@@ -203,13 +247,13 @@ int build_tables(const int32_t *edge_list, const int64_t *node_ptr, const int64_
         if (edge_index) {
             GNNB_REQUIRE(node_ptr == nullptr, "edge-index tables are single-graph only");
             edge_prepare_kernel<true, true><<<grid_for(e, 256), 256, 0, s>>>(
-                edge_list, nullptr, nullptr, 0, 0, 0, e, ws.keys_in.as<uint32_t>(),
-                ws.vals_in.as<int32_t>(), in_deg, out_deg);
+                edge_list, nullptr, nullptr, 0, 0, 0, n, e, ws.keys_in.as<uint32_t>(),
+                ws.vals_in.as<int32_t>(), in_deg, out_deg, bad);
         } else {
             edge_prepare_kernel<true, false><<<grid_for(e, 256), 256, 0, s>>>(
-                edge_list, node_ptr, edge_ptr, node_base, edge_base, n_graphs, e,
+                edge_list, node_ptr, edge_ptr, node_base, edge_base, n_graphs, n, e,
                 ws.keys_in.as<uint32_t>(),
-                ws.vals_in.as<int32_t>(), in_deg, out_deg);
+                ws.vals_in.as<int32_t>(), in_deg, out_deg, bad);
         }
         GNNB_CUDA(cudaGetLastError());
         if (launches) ++*launches;
@@ -272,6 +316,48 @@ int find_heavy_rows(const int32_t *in_deg, int n, int threshold, TableWorkspace 
     GNNB_CUDA(cudaMemcpyAsync(n_heavy_host, ws.counters.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost,
                               s));
     GNNB_CUDA(cudaStreamSynchronize(s));
+    return GNNB_OK;
+}
+
+// Marks the most-referenced sources of a neighbor table: nbr_out[i] = nbr_in[i] | bit 31 when the
+// source is one of the top rows by reference count whose feature rows (row_bytes each) fit
+// `budget_bytes` together.  ref_cnt: per-source reference counts (the out-degree table of
+// lib:1051-1083, which the reference computes and never reads), or null to count them here.
+// One host synchronisation (the 16 KB histogram).  nbr_out may alias nbr_in.
+int mark_hub_sources(const int32_t *nbr_in, int32_t *nbr_out, int e, const int32_t *ref_cnt,
+                     int n_src, size_t row_bytes, size_t budget_bytes, TableWorkspace &ws,
+                     int *n_hubs_host, cudaStream_t s, int *launches)
+{
+    if (n_hubs_host) *n_hubs_host = 0;
+    if (e <= 0 || n_src <= 0) return GNNB_OK;
+    GNNB_TRY(ws.counters.ensure(sizeof(int32_t) * 4));
+    GNNB_TRY(ws.hub_hist.ensure(sizeof(unsigned int) * kHubBins));
+    GNNB_CUDA(cudaMemsetAsync(ws.hub_hist.ptr, 0, sizeof(unsigned int) * kHubBins, s));
+    if (ref_cnt == nullptr) {
+        GNNB_TRY(ws.hub_cnt.ensure(sizeof(int32_t) * (size_t)n_src));
+        GNNB_CUDA(cudaMemsetAsync(ws.hub_cnt.ptr, 0, sizeof(int32_t) * (size_t)n_src, s));
+        ref_count_kernel<<<grid_for(e, 256), 256, 0, s>>>(nbr_in, e, ws.hub_cnt.as<int32_t>());
+        GNNB_CUDA(cudaGetLastError());
+        if (launches) ++*launches;
+        ref_cnt = ws.hub_cnt.as<int32_t>();
+    }
+    count_hist_kernel<<<grid_for(n_src, 256), 256, 0, s>>>(ref_cnt, n_src, ws.hub_hist.as<unsigned int>());
+    GNNB_CUDA(cudaGetLastError());
+    static thread_local unsigned int hist[kHubBins];
+    GNNB_CUDA(cudaMemcpyAsync(hist, ws.hub_hist.ptr, sizeof(hist), cudaMemcpyDeviceToHost, s));
+    GNNB_CUDA(cudaStreamSynchronize(s));
+    const size_t max_rows = budget_bytes / (row_bytes ? row_bytes : 1);
+    size_t rows = 0;
+    int threshold = kHubBins;   // nothing marked
+    for (int b = kHubBins - 1; b >= 2; b--) {   // a source referenced once gains nothing
+        if (rows + hist[b] > max_rows) break;
+        rows += hist[b];
+        threshold = b;
+    }
+    if (n_hubs_host) *n_hubs_host = (int)rows;
+    mark_hubs_kernel<<<grid_for(e, 256), 256, 0, s>>>(nbr_in, nbr_out, e, ref_cnt, threshold);
+    GNNB_CUDA(cudaGetLastError());
+    if (launches) *launches += 2;
     return GNNB_OK;
 }
 

@@ -2,37 +2,17 @@
 //   C[128][N] = A[128][K] . W[N][K]^T      (3xTF32, fp32 accumulate in tensor memory)
 // with exactly the operand layouts, descriptors, bulk copies and barriers the fused kernel uses.
 // Exposed as gnnb_debug_tc_gemm so that a parity test can pin the primitives in isolation.
+// Built into libgnnb_b200_debug.so (test/diagnostic library), NOT into the product library.
 #include <vector>
 
+#include "../../include/gnnb_b200_debug.h"
 #include "kernels.h"
 #include "tc.cuh"
 
 namespace gnnb {
 
-// Weight image for the tensor-core path: for every K atom (32 columns of K) the N x 128-byte
-// rows of W in the canonical swizzled layout, hi part followed by lo part.
-// Rows >= n_valid of the image are zero (N padded up to the MMA granule).
 void build_weight_image(const float *W, int N, int n_valid, int K, int ld, int col0,
-                        std::vector<float> &img)
-{
-    const int KA = (K + tc::ATOM_K - 1) / tc::ATOM_K;
-    const size_t atom_floats = (size_t)2 * N * tc::ATOM_K;
-    const size_t base = img.size();
-    img.resize(base + (size_t)KA * atom_floats, 0.0f);
-    for (int ka = 0; ka < KA; ka++) {
-        float *hi = img.data() + base + (size_t)ka * atom_floats;
-        float *lo = hi + (size_t)N * tc::ATOM_K;
-        for (int n = 0; n < N; n++)
-            for (int kk = 0; kk < tc::ATOM_K; kk++) {
-                const int k = ka * tc::ATOM_K + kk;
-                const float v = (k < K && n < n_valid) ? W[(size_t)n * ld + col0 + k] : 0.0f;
-                const float h = tc::tf32_hi(v);
-                const uint32_t off = tc::canon_offset(n, kk, N) / 4;  // atom-local (k < 32)
-                hi[off] = h;
-                lo[off] = v - h;
-            }
-    }
-}
+                        std::vector<float> &img);   // fused_tc.cu (libgnnb_b200.so)
 
 namespace {
 

@@ -6,11 +6,17 @@ Two ways the hot path shards:
   balanced by node count; every rank runs its shard through its own ``Engine``; there is NO
   data-path collective (``run_sharded`` optionally gathers the per-graph outputs at the end).
 * **one large graph** (BASELINE config 5, GCN): 1D partition by destination row.  Rank g owns
-  rows ``[g*n/W, (g+1)*n/W)``, their CSR slice (in-edges, global source ids) and the matching
-  feature rows.  Per layer the feature shards are all-gathered over NVLink (for a power-law
-  graph the halo is practically every remote row, so the halo exchange is ``all_gather`` of the
-  ``[n/W][F]`` shards), then each rank aggregates + transforms its own rows.  The in-degree
-  table is all-gathered once.  Pooling: local partials + ``all_reduce`` (sum / max).
+  rows ``[g*n/W, (g+1)*n/W)``, their CSR slice (in-edges) and the matching feature rows, plus a
+  **halo**: ONE copy of every remote row its in-edges reference (on the 2M-node power-law graph
+  that is 84 % / 65 % / 45 % of the remote rows at W = 2 / 4 / 8).  Sources are renumbered into
+  the compact "ext" space ``[owned rows | halo rows grouped by owner]`` and the CSR is split by
+  source into an owned-source and a halo-source part (``HaloPlan``, built once).  Per layer the
+  owners push the rows their peers need -- ``gnnb_halo_pack`` straight into the peer's halo
+  region through CUDA-IPC mappings (NVLink stores + flag hand-off, transport ``"p2p"``) or into a
+  send buffer for ``all_to_all_single`` (transport ``"nccl"``) -- on a communication stream while
+  the compute stream aggregates the owned-source edges; the halo-source edges, normalisation and
+  the tcgen05 transform follow on arrival.  The in-degree table is all-gathered once.  Pooling:
+  local partials + ``all_reduce`` (sum / max).
 
 The collective plumbing is backend-agnostic (``gloo`` on CPU for the host-logic tests); the
 compute goes through a small backend object -- ``CudaBackend`` (the C-ABI library) by default.
@@ -89,6 +95,79 @@ class RowPartition:
         return np.ascontiguousarray(coo[m])
 
 
+class HaloPlan:
+    """Index tables of one rank of a row-partitioned graph in "ext" space (built once).
+
+    ext index space = [owned rows 0..n_local) | halo rows n_local..n_ext), the halo rows sorted
+    by global id and therefore grouped by owner rank.  ``own_*`` / ``halo_*``: the rank's CSR
+    split by where the source lives (offsets / counts per owned row, neighbor entries = ext
+    indices), each part in the stable neighbor order of lib:1086-1124.  ``send_idx`` /
+    ``send_counts``: the owned rows every peer needs, in that peer's halo order.
+    Works on torch tensors of any device (the gloo tests run it on CPU)."""
+
+    def __init__(self, ind_local, nbr_global, rank: int, part: RowPartition, dist=None):
+        import torch
+
+        W, n_local = part.world, part.n_local
+        r0 = rank * n_local
+        dev = ind_local.device
+        nbr = nbr_global.long()[: int(ind_local.sum().item())]
+        rows = torch.repeat_interleave(torch.arange(n_local, device=dev), ind_local.long())
+        is_halo = (nbr < r0) | (nbr >= r0 + n_local)
+        self.halo_ids = torch.unique(nbr[is_halo])                       # sorted global ids
+        self.halo_counts = torch.bincount(self.halo_ids // n_local, minlength=W)[:W].cpu().tolist()
+        self.n_local, self.n_halo = n_local, int(self.halo_ids.numel())
+        self.n_ext = n_local + self.n_halo
+        ext = torch.where(is_halo, n_local + torch.searchsorted(self.halo_ids, nbr), nbr - r0)
+        own = ~is_halo
+        # one contiguous table [owned-source part | halo-source part] (hub marking runs over both)
+        self.nbr_all = torch.cat([ext[own], ext[is_halo]]).to(torch.int32).contiguous()
+        self.n_own_entries = int(own.sum().item())
+        self.own_nbr = self.nbr_all[: self.n_own_entries]
+        self.halo_nbr = self.nbr_all[self.n_own_entries:]
+
+        def csr(mask):
+            cnt = torch.bincount(rows[mask], minlength=n_local)
+            off = torch.cumsum(cnt, 0) - cnt
+            return off.to(torch.int32).contiguous(), cnt.to(torch.int32).contiguous()
+
+        self.own_off, self.own_cnt = csr(own)
+        self.halo_off, self.halo_cnt = csr(is_halo)
+        # which of MY rows does every peer need?  all-to-all of the request lists
+        if W == 1 or dist is None:
+            self.send_counts = [0] * W
+            self.send_idx = torch.zeros(0, dtype=torch.int32, device=dev)
+        else:
+            want = torch.tensor(self.halo_counts, dtype=torch.int64, device=dev)
+            asked = torch.empty(W, dtype=torch.int64, device=dev)
+            dist.all_to_all_single(asked, want)
+            self.send_counts = asked.cpu().tolist()
+            req = torch.empty(int(sum(self.send_counts)), dtype=torch.int64, device=dev)
+            dist.all_to_all_single(req, self.halo_ids.contiguous(), self.send_counts, self.halo_counts)
+            assert bool(((req >= r0) & (req < r0 + n_local)).all()), "peer asked for a row this rank does not own"
+            self.send_idx = (req - r0).to(torch.int32).contiguous()
+        self.send_off = np.concatenate([[0], np.cumsum(self.send_counts)]).astype(np.int64)
+        self.recv_off = np.concatenate([[0], np.cumsum(self.halo_counts)]).astype(np.int64)
+        self.hub_rows = 0
+
+    def ext_ids(self, rank: int):
+        """global node id of every ext row"""
+        import torch
+
+        r0 = rank * self.n_local
+        own = torch.arange(r0, r0 + self.n_local, device=self.halo_ids.device)
+        return torch.cat([own, self.halo_ids])
+
+
+class _DevBuf:
+    """a library-owned (CUDA-IPC exportable) device allocation seen as a torch tensor"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = ptr, nbytes
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
 class CudaBackend:
     """Compute through libgnnb_b200.so on torch CUDA tensors (current stream)."""
 
@@ -101,6 +180,9 @@ class CudaBackend:
         self._lib = _lib
         self.lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device())
+        self.comm = torch.cuda.Stream()
+        self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self._owned, self._opened = [], []
 
     def _p(self, t):
         return C.c_void_p(t.data_ptr()) if t is not None else None
@@ -113,6 +195,18 @@ class CudaBackend:
 
     def empty(self, shape, dtype="float32"):
         return self.torch.empty(shape, dtype=getattr(self.torch, dtype), device=self.device)
+
+    # ---- streams: the exchange runs on `comm`, everything else on the current stream
+    def fork(self):
+        self._ev_fork.record(self.torch.cuda.current_stream())
+        self.comm.wait_event(self._ev_fork)
+
+    def join(self):
+        self._ev_join.record(self.comm)
+        self.torch.cuda.current_stream().wait_event(self._ev_join)
+
+    def comm_ctx(self):
+        return self.torch.cuda.stream(self.comm)
 
     def partition_tables(self, coo_local, row_begin, n_local):
         e = int(coo_local.shape[0])
@@ -129,16 +223,67 @@ class CudaBackend:
                                                       int(in_deg_full.shape[0]), self._stream()))
         return out
 
-    def gcn_layer(self, x_full, tables, dinv_full, row_begin, W, b, skip, act):
-        ind, off, nbr = tables
-        n_local, n_total = int(ind.shape[0]), int(x_full.shape[0])
-        fo, fi = int(W.shape[0]), int(W.shape[1])
-        y = self.empty((n_local, fo))
-        self._lib.check(self.lib.gnnb_gcn_conv_partition(
-            n_local, row_begin, n_total, int(nbr.shape[0]), self._p(x_full), self._p(y),
-            self._p(off), self._p(nbr), self._p(ind), self._p(dinv_full), self._p(W), self._p(b),
-            self._p(skip), fi, fo, act, self._stream()))
-        return y
+    def mark_hubs(self, nbr_all, n_sources: int, row_bytes: int, budget_bytes: int) -> int:
+        n = C.c_int(0)
+        self._lib.check(self.lib.gnnb_mark_hub_sources(self._p(nbr_all), int(nbr_all.numel()),
+                                                       n_sources, row_bytes, budget_bytes,
+                                                       C.byref(n), self._stream()))
+        return n.value
+
+    def gcn_layer_halo(self, x_ext, y_local, plan: HaloPlan, dinv_ext, W, b, skip, act, phase,
+                       emb_in, emb_out):
+        self._lib.check(self.lib.gnnb_gcn_conv_halo(
+            plan.n_local, plan.n_ext, self._p(x_ext), self._p(y_local), self._p(plan.own_off),
+            self._p(plan.own_cnt), self._p(plan.own_nbr), self._p(plan.halo_off),
+            self._p(plan.halo_cnt), self._p(plan.halo_nbr), self._p(dinv_ext), self._p(W),
+            self._p(b), self._p(skip), emb_in, emb_out, act, phase, 1 if plan.hub_rows else 0,
+            self._stream()))
+
+    def halo_pack(self, x_own, F: int, plan: HaloPlan, dst_ptrs, max_ctas: int = 0):
+        """dst_ptrs: one raw device address per peer (0 where nothing is sent)"""
+        W = len(dst_ptrs)
+        off = (C.c_int64 * (W + 1))(*[int(v) for v in plan.send_off])
+        dst = (C.c_void_p * W)(*[C.c_void_p(int(p)) for p in dst_ptrs])
+        self._lib.check(self.lib.gnnb_halo_pack(self._p(x_own), F, F, self._p(plan.send_idx), off,
+                                                dst, W, max_ctas, self._stream()))
+
+    def pack_rows(self, x_own, F: int, plan: HaloPlan, send):
+        """send[send_off[p] + i] = x_own[send_idx[...]]: the rows of every peer, contiguous (NCCL)"""
+        base = send.data_ptr()
+        self.halo_pack(x_own, F, plan, [base + 4 * F * int(plan.send_off[p])
+                                        for p in range(len(plan.send_counts))])
+
+    def halo_signal(self, flag_ptrs, value: int):
+        W = len(flag_ptrs)
+        arr = (C.c_void_p * W)(*[C.c_void_p(int(p)) if p else None for p in flag_ptrs])
+        self._lib.check(self.lib.gnnb_halo_signal(arr, W, value, self._stream()))
+
+    def halo_wait(self, flags_ptr: int, n: int, value: int, timed_out):
+        self._lib.check(self.lib.gnnb_halo_wait(C.c_void_p(flags_ptr), n, value,
+                                                self._p(timed_out), self._stream()))
+
+    # ---- CUDA-IPC allocations (peer-mapped halo buffers)
+    def ipc_alloc(self, nbytes: int):
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        self._lib.check(self.lib.gnnb_ipc_alloc(nbytes, C.byref(ptr), handle))
+        self._owned.append(ptr.value)
+        t = self.torch.as_tensor(_DevBuf(ptr.value, nbytes), device=self.device)
+        return t, ptr.value, bytes(handle)
+
+    def ipc_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._lib.check(self.lib.gnnb_ipc_open(buf, C.byref(ptr)))
+        self._opened.append(ptr.value)
+        return ptr.value
+
+    def release(self):
+        self.torch.cuda.synchronize()
+        for p in self._opened:
+            self.lib.gnnb_ipc_close(C.c_void_p(p))
+        for p in self._owned:
+            self.lib.gnnb_ipc_free(C.c_void_p(p))
+        self._opened, self._owned = [], []
 
     def pool_partial(self, x_local):
         n, f = int(x_local.shape[0]), int(x_local.shape[1])
@@ -170,9 +315,15 @@ class CudaBackend:
 
 
 class LargeGraphGCN:
-    """GCN GNNModel over one large row-partitioned graph (BASELINE config 5)."""
+    """GCN GNNModel over one large row-partitioned graph (BASELINE config 5) with a per-layer halo
+    exchange overlapped with the aggregation of the owned-source edges.
 
-    def __init__(self, model, n_total: int, rank: int, world: int, dist=None, backend=None):
+    transport: "p2p" (owners store the halo rows straight into the peers' buffers over NVLink
+    through CUDA-IPC mappings; flag hand-off on the device), "nccl" (pack + all_to_all_single) or
+    "auto" (p2p when every rank can map its peers, else nccl)."""
+
+    def __init__(self, model, n_total: int, rank: int, world: int, dist=None, backend=None,
+                 transport: str = "auto", hub_l2_mb: Optional[int] = None):
         d = model.describe()
         if d["conv_type"] != 0:
             raise NotImplementedError("the row-partitioned path implements GCN (BASELINE config 5)")
@@ -180,6 +331,10 @@ class LargeGraphGCN:
         self.part = RowPartition(n_total, world)
         self.rank, self.world, self.dist = rank, world, dist
         self.backend = backend if backend is not None else CudaBackend()
+        self.transport_req = transport
+        import os
+
+        self.hub_l2_mb = int(os.environ.get("GNNB_HUB_L2_MB", 40)) if hub_l2_mb is None else hub_l2_mb
         params = model.named_parameter_arrays()
         names = list(params)
         nh = d["mlp_num_linear"]
@@ -190,38 +345,169 @@ class LargeGraphGCN:
         for k in range(d["num_layers"]):  # [conv_bias, conv_lin_weight] per layer
             b, W = params[names[2 * nh + 2 * k]], params[names[2 * nh + 2 * k + 1]]
             self.layers.append((B.to_device(W), B.to_device(b)))
+        self.dims = [int(W.shape[1]) for W, _ in self.layers] + [int(self.layers[-1][0].shape[0])]
         self.tables = None
-        self.dinv_full = None
+        self.plan: Optional[HaloPlan] = None
+        self.dinv_ext = None
+        self.transport = "none"
+        self.epoch = 0
+        self.stats = {}
 
+    # ------------------------------------------------------------------ setup
     def setup(self, coo_local: np.ndarray):
-        """Build this rank's CSR slice and the global 1/sqrt(1+deg) table (one all-gather)."""
-        B = self.backend
+        """Build this rank's CSR slice (bit-exact tables), the halo plan, the ext buffers and --
+        for the p2p transport -- the peer mappings.  Collective: every rank must call it."""
+        B, W = self.backend, self.world
         r0, _ = self.part.rows(self.rank)
-        self.tables = B.partition_tables(B.to_device(coo_local.astype(np.int32)), r0,
-                                         self.part.n_local)
-        ind_local = self.tables[0]
-        if self.world > 1:
+        n_local = self.part.n_local
+        self.tables = B.partition_tables(B.to_device(coo_local.astype(np.int32)), r0, n_local)
+        ind_local, _, nbr_global = self.tables
+        if W > 1:
             ind_full = B.all_gather_rows(self.dist, ind_local.view(-1, 1), self.part.n_total).view(-1)
         else:
             ind_full = ind_local
-        self.dinv_full = B.dinv(ind_full)
+        dinv_full = B.dinv(ind_full)
+        self.plan = plan = HaloPlan(ind_local, nbr_global, self.rank, self.part,
+                                    self.dist if W > 1 else None)
+        self.dinv_ext = dinv_full[plan.ext_ids(self.rank)].contiguous()
+        fmax = max(self.dims)
+        if self.hub_l2_mb > 0 and hasattr(B, "mark_hubs") and plan.n_ext * fmax * 4 > (96 << 20):
+            plan.hub_rows = B.mark_hubs(plan.nbr_all, plan.n_ext, fmax * 4, self.hub_l2_mb << 20)
+        self._setup_buffers(fmax)
+        self.stats = {
+            "n_local": n_local, "halo_rows": plan.n_halo,
+            "halo_frac_of_remote_rows": plan.n_halo / max(1, self.part.n_total - n_local),
+            "send_rows": int(plan.send_off[-1]), "hub_rows": plan.hub_rows,
+            "transport": self.transport,
+        }
         return self
 
-    def forward(self, x_local, return_embeddings: bool = False):
-        """x_local: this rank's feature rows (backend tensor or numpy).  Returns the model output
-        (identical on every rank) and optionally the rank's node-embedding rows."""
-        B, d = self.backend, self.desc
-        if isinstance(x_local, np.ndarray):
-            x_local = B.to_device(x_local.astype(np.float32))
-        r0, _ = self.part.rows(self.rank)
+    def _setup_buffers(self, fmax: int):
+        B, W, plan = self.backend, self.world, self.plan
+        want_p2p = W > 1 and self.transport_req in ("auto", "p2p") and hasattr(B, "ipc_alloc")
+        self.ext = None
+        if want_p2p:
+            try:
+                self._setup_p2p(fmax)
+            except Exception as e:   # a rank that cannot map its peers: every rank falls back
+                self._p2p_error = str(e)
+                self.ext = None
+            ok = B.to_device(np.array([1 if self.ext is not None else 0], np.int32))
+            self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if self.transport_req == "p2p":
+                    raise RuntimeError("p2p transport requested but a rank could not map its peers: "
+                                       + getattr(self, "_p2p_error", "(another rank)"))
+                self.ext = None
+        if self.ext is None:
+            self.ext = [B.empty((plan.n_ext * fmax,)) for _ in range(2)]
+            self.transport = "nccl" if W > 1 else "none"
+            if W > 1:
+                self.send_buf = B.empty((max(1, int(plan.send_off[-1])) * fmax,))
+        else:
+            self.transport = "p2p"
+
+    def _setup_p2p(self, fmax: int):
+        """ext buffers + flags in CUDA-IPC memory; every rank maps its peers' and learns where in
+        each peer's halo region its rows go"""
+        import torch
+
+        B, W, plan, dist = self.backend, self.world, self.plan, self.dist
+        nbytes = max(plan.n_ext * fmax * 4, 256)
+        bufs = [B.ipc_alloc(nbytes) for _ in range(2)]
+        flags_t, flags_ptr, flags_h = B.ipc_alloc(8 * 32)
+        self.ext = [t.view(torch.float32) for t, _, _ in bufs]
+        self._ext_ptr = [p for _, p, _ in bufs]
+        self._flags, self._flags_ptr = flags_t.view(torch.int64), flags_ptr
+        self._timed_out = torch.zeros(1, dtype=torch.int32, device=flags_t.device)
+        mine = torch.frombuffer(bytearray(bufs[0][2] + bufs[1][2] + flags_h), dtype=torch.uint8).to(flags_t.device)
+        allh = torch.empty(W * 192, dtype=torch.uint8, device=flags_t.device)
+        dist.all_gather_into_tensor(allh, mine)
+        allh = allh.cpu().numpy().tobytes()
+        # where do MY rows start inside peer p's halo region?  p's recv_off[my rank], in rows
+        recv_off = torch.tensor(plan.recv_off[:W], dtype=torch.int64, device=flags_t.device)
+        at_peer = torch.empty(W, dtype=torch.int64, device=flags_t.device)
+        dist.all_to_all_single(at_peer, recv_off)
+        self._row_at_peer = [int(v) for v in at_peer.cpu().tolist()]
+        self._peer_ext = [[0] * W, [0] * W]
+        self._peer_flag = [0] * W
+        for p in range(W):
+            if p == self.rank:
+                continue
+            h = allh[192 * p: 192 * (p + 1)]
+            self._peer_ext[0][p] = B.ipc_open(h[0:64])
+            self._peer_ext[1][p] = B.ipc_open(h[64:128])
+            self._peer_flag[p] = B.ipc_open(h[128:192]) + 8 * self.rank
+        self._peer_flag[self.rank] = flags_ptr + 8 * self.rank
+
+    def close(self):
+        if hasattr(self.backend, "release"):
+            if self.dist is not None and self.world > 1:
+                self.dist.barrier()
+            self.backend.release()
+            self.ext = None
+
+    # ------------------------------------------------------------------ forward
+    def input_view(self):
+        """where the layer-0 input of this rank lives: [n_local][in_dim] (write here to skip a copy)"""
+        return self.ext[0][: self.part.n_local * self.dims[0]].view(self.part.n_local, self.dims[0])
+
+    def _exchange(self, k: int, F: int):
+        """fills the halo region of ext[k & 1] with the peers' layer-k input rows (comm stream)"""
+        B, W, plan = self.backend, self.world, self.plan
+        cur = self.ext[k & 1]
+        x_own = cur[: plan.n_local * F]
+        self.epoch += 1
+        B.fork()
+        with B.comm_ctx():
+            if self.transport == "p2p":
+                n_local = plan.n_local
+                dst = [0 if p == self.rank or plan.send_counts[p] == 0 else
+                       self._peer_ext[k & 1][p] + 4 * F * (n_local + self._row_at_peer[p])
+                       for p in range(W)]
+                B.halo_pack(x_own, F, plan, dst)
+                B.halo_signal(self._peer_flag, self.epoch)
+            else:
+                send = self.send_buf[: int(plan.send_off[-1]) * F].view(-1, F)
+                B.pack_rows(x_own, F, plan, send)
+                recv = cur[plan.n_local * F: plan.n_ext * F].view(-1, F)
+                self.dist.all_to_all_single(recv, send, plan.halo_counts, plan.send_counts)
+
+    def _arrived(self):
+        B = self.backend
+        if self.transport == "p2p":   # device-side wait on the compute stream
+            B.halo_wait(self._flags_ptr, self.world, self.epoch, self._timed_out)
+        else:
+            B.join()
+
+    def forward(self, x_local=None, return_embeddings: bool = False):
+        """x_local: this rank's feature rows (backend tensor or numpy), or None when the caller has
+        already written them into ``input_view()``.  Returns the model output (identical on every
+        rank) and optionally the rank's node-embedding rows."""
+        B, d, plan = self.backend, self.desc, self.plan
+        n_local = plan.n_local
+        if x_local is not None:
+            if isinstance(x_local, np.ndarray):
+                x_local = B.to_device(x_local.astype(np.float32))
+            self.input_view().copy_(x_local)
         L = d["num_layers"]
         for k, (W, b) in enumerate(self.layers):
-            x_full = (B.all_gather_rows(self.dist, x_local, self.part.n_total)
-                      if self.world > 1 else x_local)
+            fi, fo = self.dims[k], self.dims[k + 1]
+            cur, nxt = self.ext[k & 1], self.ext[(k + 1) & 1]
+            x_ext = cur[: plan.n_ext * fi]
+            y_local = nxt[: n_local * fo]
             do_skip = bool(d["skip"]) and k != 0 and k != L - 1
-            x_local = B.gcn_layer(x_full, self.tables, self.dinv_full, r0, W, b,
-                                  x_local if do_skip else None, d["gnn_act"])
-        s, mx = B.pool_partial(x_local)
+            skip = cur[: n_local * fi] if do_skip else None
+            args = (x_ext, y_local, plan, self.dinv_ext, W, b, skip, d["gnn_act"])
+            if self.world > 1:   # (every rank takes part in the exchange, even with an empty halo)
+                self._exchange(k, fi)
+                B.gcn_layer_halo(*args, 1, fi, fo)      # owned-source edges: overlaps the exchange
+                self._arrived()
+                B.gcn_layer_halo(*args, 2, fi, fo)      # halo-source edges, normalise, transform
+            else:
+                B.gcn_layer_halo(*args, 3, fi, fo)
+        emb = self.ext[L & 1][: n_local * self.dims[L]].view(n_local, self.dims[L])
+        s, mx = B.pool_partial(emb)
         if self.world > 1:
             s = B.all_reduce(self.dist, s, self.dist.ReduceOp.SUM)
             mx = B.all_reduce(self.dist, mx, self.dist.ReduceOp.MAX)
@@ -230,7 +516,12 @@ class LargeGraphGCN:
             pools.append({0: s, 1: s / float(self.part.n_total), 2: mx}[pid])
         pooled = _cat(pools)
         out = B.head(pooled, self.head, d["mlp_act"], d["out_act"])
-        return (out, x_local) if return_embeddings else out
+        return (out, emb.clone()) if return_embeddings else out
+
+    def check_transport(self):
+        """after a synchronisation: raises if a device-side halo wait gave up (p2p transport)"""
+        if self.transport == "p2p" and int(self._timed_out.item()) != 0:
+            raise RuntimeError("halo exchange: a peer's rows did not arrive within the wait limit")
 
 
 def _cat(ts):

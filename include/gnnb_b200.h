@@ -229,26 +229,46 @@ int gnnb_gcn_conv_partition(int n_local, int row_begin, int n_total, int num_edg
  * The ranks combine them with all_reduce(sum) / all_reduce(max). */
 int gnnb_pool_partial(const float *x, int64_t n, int F, float *out, void *stream);
 
-/* ---- diagnostics ------------------------------------------------------------------------- */
-/* One-CTA tensor-core GEMM C[128][N] = A[128][K] . W[N][K]^T (tcgen05, 3xTF32) built from the
- * same primitives as the fused kernel's node transform; host buffers; K <= 128, N % 16 == 0. */
-int gnnb_debug_tc_gemm(const float *A, const float *W, float *C, int K, int N);
-/* One-tile check of the tensor-core aggregation path: C[128][N] = (Adj . X) . W^T where Adj
- * [128][128] holds edge multiplicities (small non-negative integers), X is [128][F]; the
- * aggregation runs as bf16x3 MMAs and the transform takes its A operand from tensor memory, as in
- * the fused kernel.  agg (optional, [128][F]) receives Adj . X.  Host buffers. */
-/* Cycles to issue / complete `reps` back-to-back tcgen05.mma (M = 128, N columns); flavour 0 tf32
- * with both operands in shared memory, 1 tf32 with A in tensor memory, 2 bf16 K-major, 3 bf16 with
- * an MN-major B operand; + 20 = lean warp-uniform issue loop; + 1000 = M = 64 instead of 128 (lean
- * flavours only).  cycles[2]. */
-int gnnb_debug_tc_mma_rate(int flavour, int N, int reps, long long *cycles);
-int gnnb_debug_tc_agg_gemm(const float *Adj, const float *X, const float *W, float *C, float *agg,
-                           int F, int N);
-
-/* Probe for a kind::f16 MMA with a bf16 A operand in tensor memory: C[128][N] = bf16(A)[128][K] .
- * bf16(B)[N][K]^T; `variant` = the assumed layout of 16-bit elements in the 32-bit TMEM cells
- * (0 packed pairs, 1 low half, 2 high half; tools/tmem_bf16_probe.py).  Host buffers. */
-int gnnb_debug_tc_bf16_ts(const float *A, const float *B, float *C, int K, int N, int variant);
+/* ---- halo exchange for the row partition (no reference counterpart) -------------
+ * Every rank keeps its owned feature rows followed by ONE copy of each remote row its in-edges
+ * reference: the "ext" space [owned rows | halo rows grouped by owner rank], built once by
+ * gnn_builder_b200/distributed.py.  DEVICE pointers, work enqueued on `stream`. */
+/* dst[p][i][0..F) = x[send_idx[send_off[p] + i]][0..F) for every peer p < n_peers (<= 16).
+ * send_off (n_peers + 1 entries) and dst (n_peers pointers) are HOST arrays; dst[p] is a local
+ * send buffer (NCCL transport) or the peer's halo region through a CUDA-IPC mapping (the rows
+ * then leave as NVLink stores).  max_ctas <= 0: default grid. */
+int gnnb_halo_pack(const float *x, int ldx, int F, const int32_t *send_idx, const int64_t *send_off,
+                   float *const *dst, int n_peers, int max_ctas, void *stream);
+/* system-scope release store of `value` to peer_flags[p] (HOST array of n_peers device pointers,
+ * NULL entries skipped): "this rank's rows for epoch `value` have landed" */
+int gnnb_halo_signal(uint64_t *const *peer_flags, int n_peers, uint64_t value, void *stream);
+/* waits on the device until flags[0..n_flags) >= value (acquire, system scope); after ~2 s of SM
+ * clocks it sets *timed_out (device int) instead of hanging */
+int gnnb_halo_wait(const uint64_t *flags, int n_flags, uint64_t value, int *timed_out, void *stream);
+/* CUDA-IPC plumbing for the peer mappings: a zeroed device allocation + its 64-byte handle; open /
+ * close a peer's handle in this process; free */
+int gnnb_ipc_alloc(size_t bytes, void **ptr, void *handle64);
+int gnnb_ipc_open(const void *handle64, void **ptr);
+int gnnb_ipc_close(void *ptr);
+int gnnb_ipc_free(void *ptr);
+/* Sets bit 31 on the entries of a neighbor table whose source is among the most-referenced ones
+ * whose feature rows (row_bytes each) fit budget_bytes: the aggregation keeps those rows resident
+ * in L2 (evict_last) and streams the others (evict_first).  In place; *num_hubs (host) = marked
+ * sources.  One host synchronisation. */
+int gnnb_mark_hub_sources(int32_t *neighbor_table, int num_entries, int num_sources, int row_bytes,
+                          int64_t budget_bytes, int *num_hubs, void *stream);
+/* One GCN layer on the owned rows of an ext-space partition with its CSR split by source:
+ * own_* = edges whose source this rank owns, halo_* = edges whose source is a halo row (offsets /
+ * counts per owned row, neighbor entries = ext indices).  phase 1: aggregate the owned-source
+ * edges (needs no halo: overlaps the exchange); phase 2: add the halo-source edges, normalise
+ * (lib:1246-1278) and transform, y_local[n_local][emb_out] = act(agg.W^T + b (+ skip_local));
+ * phase 3: both.  dinv_ext[n_ext] = 1/sqrt(1 + in-degree) of every ext row. */
+int gnnb_gcn_conv_halo(int n_local, int n_ext, const float *x_ext, float *y_local,
+                       const int32_t *own_offsets, const int32_t *own_counts, const int32_t *own_nbr,
+                       const int32_t *halo_offsets, const int32_t *halo_counts,
+                       const int32_t *halo_nbr, const float *dinv_ext, const float *weight,
+                       const float *bias, const float *skip_local, int emb_in, int emb_out, int act,
+                       int phase, int hub_bit, void *stream);
 
 #ifdef __cplusplus
 }

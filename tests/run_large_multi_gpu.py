@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Row-partitioned GCN over N GPUs (NCCL all-gather of the feature shards per layer), checked
-against the single-GPU layerwise path and -- at a size the CPU oracle finishes in seconds --
-against the oracle.  Launch on a multi-GPU box:
+"""Row-partitioned GCN over N GPUs (per-layer halo exchange, transport p2p or nccl), checked -- at a
+size the CPU oracle finishes in seconds -- against the oracle.  tests/test_gpu_multi.py launches
+it under torchrun; by hand on a multi-GPU box:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29511 tests/run_large_multi_gpu.py [--nodes 200000] [--bench]
@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--nodes", type=int, default=80000)
     ap.add_argument("--bench", action="store_true")
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"])
     args = ap.parse_args()
 
     import torch
@@ -46,12 +47,19 @@ def main():
     x, coo = gnnb.make_powerlaw_graph(n, 16, w.in_dim, seed=5, max_degree=5000)
     part = RowPartition(n, world)
     r0, r1 = part.rows(rank)
-    runner = LargeGraphGCN(model, n, rank, world, dist=dist if world > 1 else None)
+    runner = LargeGraphGCN(model, n, rank, world, dist=dist if world > 1 else None,
+                           transport=args.transport)
     runner.setup(part.local_edges(coo, rank))
     x_local = torch.from_numpy(x[r0:r1]).cuda()
     out, emb = runner.forward(x_local, return_embeddings=True)
     torch.cuda.synchronize()
-    result = {"rank": rank, "world": world, "nodes": n, "edges": int(coo.shape[0])}
+    runner.check_transport()
+    # run-to-run: the same input again gives the same bits (fixed reduction order everywhere)
+    out_b, emb_b = runner.forward(x_local, return_embeddings=True)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(out, out_b) and torch.equal(emb, emb_b))
+    result = {"rank": rank, "world": world, "nodes": n, "edges": int(coo.shape[0]),
+              "stats": runner.stats, "bit_identical_rerun": same}
     if rank == 0 and n <= 200000:
         from oracle import Oracle
 
@@ -62,7 +70,8 @@ def main():
         err_out = float(np.abs(out.cpu().numpy() - ref).max() / max(1.0, np.abs(ref).max()))
         err_emb = float(np.abs(emb.cpu().numpy() - ref_emb[r0:r1]).max()
                         / max(1.0, np.abs(ref_emb).max()))
-        result.update(err_out=err_out, err_emb=err_emb, ok=bool(err_out < 1e-4 and err_emb < 1e-4))
+        result.update(err_out=err_out, err_emb=err_emb,
+                      ok=bool(err_out < 1e-4 and err_emb < 1e-4 and same))
     if args.bench:
         for _ in range(2):
             runner.forward(x_local)
@@ -80,8 +89,10 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         result.update(ms_per_forward=float(ms.item()),
                       edges_per_sec=float(coo.shape[0] * w.num_layers / (ms.item() * 1e-3)))
+    runner.check_transport()
     if rank == 0:
         print(json.dumps(result), flush=True)
+    runner.close()
     if world > 1:
         dist.destroy_process_group()
     if rank == 0 and result.get("ok") is False:

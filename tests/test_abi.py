@@ -22,6 +22,16 @@ def test_header_symbols_are_exported():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.gnnb_version() >= 100
+    # the tcgen05 probes live in a separate test library with its own header: none of them may
+    # leak into the product ABI
+    assert not any(n.startswith("gnnb_debug") for n in declared)
+    dbg = _lib.load_debug()
+    dheader = (ROOT / "include" / "gnnb_b200_debug.h").read_text()
+    ddeclared = set(re.findall(r"\b(gnnb_debug_[a-z_0-9]+)\s*\(", dheader))
+    assert ddeclared == set(_lib.DEBUG_EXPORTS)
+    for name in ddeclared:
+        assert hasattr(dbg, name), name
+        assert not hasattr(lib, name), f"{name} is exported by the product library"
 
 
 def test_model_desc_struct_matches_header():

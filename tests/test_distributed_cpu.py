@@ -2,7 +2,8 @@
 
 The product has no CPU compute path, so these tests inject a *checker* backend (numpy + the
 oracle) into the orchestration code and verify what the orchestration is responsible for: shard
-ranges, the row partition, the all-gather / all-reduce plumbing and the assembly of results."""
+ranges, the row partition, the all-gather / all-reduce plumbing, the halo plan (ext index space, split CSR, all-to-all of the request lists and of
+the feature rows) and the assembly of results."""
 import os
 import sys
 from pathlib import Path
@@ -32,19 +33,48 @@ class NumpyBackend:
     def dinv(self, in_deg_full):
         return 1.0 / (1.0 + in_deg_full.float()).sqrt()
 
-    def gcn_layer(self, x_full, tables, dinv_full, row_begin, W, b, skip, act):
+    # the exchange runs "on another stream" in the product; here everything is synchronous
+    def fork(self):
+        pass
+
+    def join(self):
+        pass
+
+    def comm_ctx(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def empty(self, shape, dtype="float32"):
         import torch
-        ind, off, nbr = tables
-        n_local = ind.shape[0]
-        rows = torch.repeat_interleave(torch.arange(n_local), ind.long())
-        msg = x_full[nbr.long()] * dinv_full[nbr.long()].view(-1, 1)
-        agg = torch.zeros(n_local, x_full.shape[1]).index_add_(0, rows, msg)
-        dv = dinv_full[row_begin:row_begin + n_local].view(-1, 1)
-        agg = agg * dv + x_full[row_begin:row_begin + n_local] * dv * dv
+        return torch.zeros(shape, dtype=getattr(torch, dtype))
+
+    def pack_rows(self, x_own, F, plan, send):
+        send[:] = x_own.view(-1, F)[plan.send_idx.long()]
+
+    def gcn_layer_halo(self, x_ext, y_local, plan, dinv_ext, W, b, skip, act, phase, fi, fo):
+        """numpy/torch restatement of gnnb_gcn_conv_halo on the ext index space"""
+        import torch
+        n_local = plan.n_local
+        x = x_ext.view(-1, fi)
+        if phase & 1:
+            self._agg = torch.zeros(n_local, fi)
+            parts = [(plan.own_cnt, plan.own_nbr)]
+        else:
+            parts = []
+        if phase & 2:
+            parts.append((plan.halo_cnt, plan.halo_nbr))
+        for cnt, nbr in parts:
+            rows = torch.repeat_interleave(torch.arange(n_local), cnt.long())
+            src = (nbr.long() & 0x7fffffff)
+            self._agg.index_add_(0, rows, x[src] * dinv_ext[src].view(-1, 1))
+        if not (phase & 2):
+            return
+        dv = dinv_ext[:n_local].view(-1, 1)
+        agg = self._agg * dv + x[:n_local] * dv * dv
         y = agg @ W.T + b
         if skip is not None:
-            y = y + skip
-        return torch.relu(y) if act == 1 else y
+            y = y + skip.view(n_local, fi)
+        y_local.view(n_local, fo)[:] = torch.relu(y) if act == 1 else y
 
     def pool_partial(self, x_local):
         return x_local.sum(0), x_local.max(0).values
@@ -125,17 +155,28 @@ def _worker(rank, world, port, result_dir):
                                              return_node_emb=True)
         assert np.abs(emb_local.numpy() - ref_emb[r0:r1]).max() < 1e-5
         assert np.abs(out.numpy() - ref_out).max() < 1e-4 * max(1.0, np.abs(ref_out).max())
+        # the halo plan: ext space = owned rows + ONE copy of each referenced remote row
+        plan = runner.plan
+        refs = np.unique(part.local_edges(coo, rank)[:, 0])
+        remote = refs[(refs < r0) | (refs >= r1)]
+        assert np.array_equal(plan.halo_ids.numpy(), remote)
+        assert plan.n_ext == (r1 - r0) + remote.size and runner.transport == "nccl"
+        assert int(plan.own_cnt.sum() + plan.halo_cnt.sum()) == part.local_edges(coo, rank).shape[0]
+        # a second forward reuses the buffers (odd/even ext buffers, send buffer) unchanged
+        out2 = runner.forward(x[r0:r1])
+        assert np.array_equal(out2.numpy(), out.numpy())
         Path(result_dir, f"ok_{rank}").write_text("ok")
     finally:
         dist.destroy_process_group()
 
 
-def test_world_size_2_gloo(tmp_path):
+@pytest.mark.parametrize("world", [2, 3])
+def test_world_size_n_gloo(tmp_path, world):
     import torch.multiprocessing as mp
 
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
+    port = 29500 + ((os.getpid() + 13 * world) % 2000)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok_{r}").exists() for r in range(world))
 
 
 def test_shard_ranges_balance_and_cover():

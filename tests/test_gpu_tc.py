@@ -16,7 +16,7 @@ def tc_gemm(A, W):
     W = np.ascontiguousarray(W, np.float32)
     K, N = A.shape[1], W.shape[0]
     out = np.empty((128, N), np.float32)
-    _lib.check(_lib.load().gnnb_debug_tc_gemm(C.c_void_p(A.ctypes.data), C.c_void_p(W.ctypes.data),
+    _lib.check(_lib.load_debug().gnnb_debug_tc_gemm(C.c_void_p(A.ctypes.data), C.c_void_p(W.ctypes.data),
                                               C.c_void_p(out.ctypes.data), K, N))
     return out
 
@@ -58,7 +58,7 @@ def tc_agg_gemm(Adj, X, W):
     F, N = X.shape[1], W.shape[0]
     out = np.empty((128, N), np.float32)
     agg = np.empty((128, F), np.float32)
-    _lib.check(_lib.load().gnnb_debug_tc_agg_gemm(
+    _lib.check(_lib.load_debug().gnnb_debug_tc_agg_gemm(
         C.c_void_p(Adj.ctypes.data), C.c_void_p(X.ctypes.data), C.c_void_p(W.ctypes.data),
         C.c_void_p(out.ctypes.data), C.c_void_p(agg.ctypes.data), F, N))
     return out, agg

@@ -8,7 +8,7 @@ import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from gnn_builder_b200 import _lib  # noqa: E402
 
-lib = _lib.load()
+lib = _lib.load_debug()
 names = ["tf32 SS", "tf32 TS (A in TMEM)", "bf16 SS K-major", "bf16 SS, B MN-major"]
 for flavour, name in [(f, n) for f, n in enumerate(names)] + [
         (20 + f, n + " [lean warp-uniform issue]") for f, n in enumerate(names)] + [

@@ -16,7 +16,7 @@ def trunc_bf16(a):
     return (a.view(np.uint32) & np.uint32(0xFFFF0000)).view(np.float32)
 
 
-lib = _lib.load()
+lib = _lib.load_debug()
 rng = np.random.default_rng(0)
 names = ["packed pairs (k even low half, k odd high half)", "one element per cell, low 16 bits",
          "one element per cell, high 16 bits"]
