@@ -7,7 +7,8 @@ running anything does (there is no CPU fallback).
 """
 from .code_gen import FPX, Project  # noqa: F401
 from .configs import WORKLOADS, Workload  # noqa: F401
-from .data import GraphBatch, make_molecular_batch, make_powerlaw_graph  # noqa: F401
+from .data import (GraphBatch, cached_powerlaw_graph, make_molecular_batch,  # noqa: F401
+                   make_powerlaw_graph)
 from .engine import (MATH_FAST, MATH_STRICT, PATH_AUTO, PATH_FUSED, PATH_LAYERWISE,  # noqa: F401
                      Engine)
 from .models import (MLP, GCNConv_GNNB, GINConv_GNNB, GlobalPooling, GNNModel,  # noqa: F401

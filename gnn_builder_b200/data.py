@@ -166,6 +166,26 @@ def make_powerlaw_graph(num_nodes: int, avg_degree: int, in_dim: int, seed: int,
     return x, coo
 
 
+def cached_powerlaw_graph(num_nodes: int, avg_degree: int, in_dim: int, seed: int,
+                          cache_dir: Optional[os.PathLike] = None, generate: bool = True):
+    """``make_powerlaw_graph`` through an on-disk cache (the 2M-node graph takes ~25 s of numpy):
+    returns memory-mapped (x, coo).  With ``generate=False`` the files must already exist (other
+    ranks wait for rank 0 to write them, then map only the pages they touch)."""
+    d = Path(cache_dir or os.environ.get("GNNB_CACHE_DIR", "/tmp/gnnb_cache"))
+    stem = f"powerlaw_n{num_nodes}_d{avg_degree}_f{in_dim}_s{seed}"
+    fx, fc = d / f"{stem}_x.npy", d / f"{stem}_coo.npy"
+    if not (fx.exists() and fc.exists()):
+        if not generate:
+            raise FileNotFoundError(f"{fx} has not been generated")
+        d.mkdir(parents=True, exist_ok=True)
+        x, coo = make_powerlaw_graph(num_nodes, avg_degree, in_dim, seed)
+        for f, a in ((fx, x), (fc, coo)):
+            tmp = f.with_suffix(f".tmp{os.getpid()}.npy")
+            np.save(tmp, a)
+            os.replace(tmp, f)
+    return np.load(fx, mmap_mode="r"), np.load(fc, mmap_mode="r")
+
+
 def in_degree_histogram(batch: GraphBatch) -> np.ndarray:
     """Histogram of node in-degrees over the batch (utils.py:80-96 compute_in_deg_histogram)."""
     gid_of_edge = np.repeat(np.arange(batch.n_graphs, dtype=np.int64), np.diff(batch.edge_ptr))

@@ -480,10 +480,12 @@ class LargeGraphGCN:
         else:
             B.join()
 
-    def forward(self, x_local=None, return_embeddings: bool = False):
+    def forward(self, x_local=None, return_embeddings: bool = False, capture=None):
         """x_local: this rank's feature rows (backend tensor or numpy), or None when the caller has
         already written them into ``input_view()``.  Returns the model output (identical on every
-        rank) and optionally the rank's node-embedding rows."""
+        rank) and optionally the rank's node-embedding rows.  capture = (layer, rows): keep a copy
+        of the first ``rows`` owned output rows of that conv layer in ``self.captured`` (parity
+        checks against the reference's gcn_conv at full size)."""
         B, d, plan = self.backend, self.desc, self.plan
         n_local = plan.n_local
         if x_local is not None:
@@ -506,6 +508,8 @@ class LargeGraphGCN:
                 B.gcn_layer_halo(*args, 2, fi, fo)      # halo-source edges, normalise, transform
             else:
                 B.gcn_layer_halo(*args, 3, fi, fo)
+            if capture is not None and capture[0] == k:
+                self.captured = y_local[: min(capture[1], n_local) * fo].view(-1, fo).clone()
         emb = self.ext[L & 1][: n_local * self.dims[L]].view(n_local, self.dims[L])
         s, mx = B.pool_partial(emb)
         if self.world > 1:
