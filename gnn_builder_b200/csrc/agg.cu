@@ -6,8 +6,8 @@
 // with float4 (16 B) gathers of each neighbor row, so one neighbor row of F=128 floats is one
 // fully coalesced 512 B warp request; neighbor loop unrolled x4 so four independent gathers are
 // in flight per lane.  Rows are bucketed by in-degree: rows above `heavy_threshold` are skipped
-// here and handled by a CTA-per-row kernel that splits the neighbor list across its 8 warps and
-// reduces the partials in shared memory in a fixed order (deterministic).
+// here and handled by the chunked heavy-row kernels below (a warp per 128-neighbor chunk, chunk
+// sums added in a fixed order: deterministic).
 //
 // HBM roofline: algorithmic bytes per layer = E*(4F + 4 [nbr idx] + 4 [dinv/deg]) +
 // N*(4F self + 4F_out write + 8 [offset, degree]).  Neighbors are visited in table order, so in
@@ -233,65 +233,57 @@ __global__ void __launch_bounds__(256) agg_rows_kernel(const AggArgs a)
     }
 }
 
-// Heavy rows (in-degree above the threshold): the neighbor list of row h is cut into
-// `heavy_slices` slices, one CTA per (row, slice); its 8 warps split the slice, reduce their
-// partial sums in shared memory in warp order and write partial[h][slice][F].  A second kernel
-// adds the slices in order and applies the self term / normalisation, so the result does not
-// depend on scheduling.  (Measured alternatives: giving each heavy row to ONE CTA ran a
-// 100k-neighbor hub for ~5 ms on 8 warps while 147 SMs idled; slicing only rows above 4096
-// neighbors and letting one CTA finish the others directly was 2 % slower on the C5 step, the
-// bucket boundary -- GNNB_HEAVY_THRESHOLD, 64 ... 1024 -- moves the step by < 1 %.)
+// Heavy rows (longer than the threshold; on the 2M-node power-law graph 0.5 % of the rows hold
+// 49 % of the edges): the neighbor list of row h is cut into chunks of kHeavyChunk neighbors and
+// every chunk is one warp's work item (grid-stride over all chunks of all heavy rows, so a
+// 300-neighbor row and a 100 000-neighbor hub load the machine alike); the chunk sums go to
+// partial[chunk][F].  A second kernel adds a row's chunks in order and applies the self term /
+// normalisation, so the result does not depend on scheduling.  (Round 1 cut every heavy row into
+// a fixed number of slices x 8 warps: rows just above the threshold then gave each warp one or two
+// neighbors, and the kernel reached 38 % of the DRAM rate the light-row kernel reaches.)
 template <int VEC, int MODE>
-__global__ void __launch_bounds__(256) agg_heavy_kernel(const AggArgs a)
+__global__ void __launch_bounds__(256) agg_heavy_chunk_kernel(const AggArgs a)
 {
-    extern __shared__ float partial[];  // [8][F]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int S = a.heavy_slices, sl = blockIdx.y;
-    for (int h = blockIdx.x; h < a.n_heavy; h += gridDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int warp_stride = gridDim.x * warps_per_block;
+    for (int chunk = warp_global; chunk < a.heavy_chunks; chunk += warp_stride) {
+        const int h = __ldg(a.heavy_chunk_row + chunk);
         const int v = __ldg(a.heavy_rows + h);
+        const int j = chunk - __ldg(a.heavy_chunk_base + h);
         const int deg_v = __ldg(a.in_deg + v);
         const int len_v = a.counts != nullptr ? __ldg(a.counts + v) : deg_v;
         const int off = __ldg(a.offsets + v);
         const float dinv_v = (MODE == AGG_GCN) ? __ldg(a.dinv + v + a.row_base) : 0.0f;
-        const int s0 = (int)((int64_t)len_v * sl / S), s1 = (int)((int64_t)len_v * (sl + 1) / S);
-        const int per = (s1 - s0 + 7) / 8;
-        const int k0 = min(s1, s0 + warp * per), k1 = min(s1, s0 + (warp + 1) * per);
+        const int k0 = j * kHeavyChunk, k1 = min(len_v, k0 + kHeavyChunk);
+        float *dst = a.heavy_partial + (size_t)chunk * a.F;
         for (int c = lane * VEC; c < a.F; c += 32 * VEC) {
             Vec<VEC> acc;
 #pragma unroll
             for (int i = 0; i < VEC; i++) acc.v[i] = 0.0f;
             gather_range<VEC, MODE, false>(a, off, k0, k1, deg_v, dinv_v, c, acc);
-#pragma unroll
-            for (int i = 0; i < VEC; i++) partial[warp * a.F + c + i] = acc.v[i];
+            acc.store(dst + c);
         }
-        __syncthreads();
-        if (warp == 0) {
-            float *dst = a.heavy_partial + ((size_t)h * S + sl) * a.F;
-            for (int c = lane * VEC; c < a.F; c += 32 * VEC) {
-                Vec<VEC> acc;
-#pragma unroll
-                for (int i = 0; i < VEC; i++) {
-                    float t = 0.0f;
-#pragma unroll
-                    for (int w = 0; w < 8; w++) t += partial[w * a.F + c + i];
-                    acc.v[i] = t;
-                }
-                acc.store(dst + c);
-            }
-        }
-        __syncthreads();
     }
 }
 
+// one warp per heavy row: chunk sums added in chunk order, then the row is finished
 template <int VEC, int MODE>
-__global__ void __launch_bounds__(128) agg_heavy_combine_kernel(const AggArgs a)
+__global__ void __launch_bounds__(256) agg_heavy_combine_kernel(const AggArgs a)
 {
-    const int S = a.heavy_slices;
-    for (int h = blockIdx.x; h < a.n_heavy; h += gridDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int warp_stride = gridDim.x * warps_per_block;
+    for (int h = warp_global; h < a.n_heavy; h += warp_stride) {
         const int v = __ldg(a.heavy_rows + h);
         const int deg_v = __ldg(a.in_deg + v);
+        const int len_v = a.counts != nullptr ? __ldg(a.counts + v) : deg_v;
+        const int nch = (len_v + kHeavyChunk - 1) / kHeavyChunk;
+        const float *src = a.heavy_partial + (size_t)__ldg(a.heavy_chunk_base + h) * a.F;
         const float dinv_v = (MODE == AGG_GCN) ? __ldg(a.dinv + v + a.row_base) : 0.0f;
-        for (int c = threadIdx.x * VEC; c < a.F; c += blockDim.x * VEC) {
+        for (int c = lane * VEC; c < a.F; c += 32 * VEC) {
             Vec<VEC> acc;
             if (a.accumulate) {
                 acc.load_rw(a.out + (size_t)v * a.ldo + c);
@@ -299,9 +291,19 @@ __global__ void __launch_bounds__(128) agg_heavy_combine_kernel(const AggArgs a)
 #pragma unroll
                 for (int i = 0; i < VEC; i++) acc.v[i] = 0.0f;
             }
-            for (int sl = 0; sl < S; sl++) {
+            int j = 0;
+            for (; j + 4 <= nch; j += 4) {     // four independent loads in flight, added in order
+                Vec<VEC> t[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) t[q].load_rw(src + (size_t)(j + q) * a.F + c);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int i = 0; i < VEC; i++) acc.v[i] += t[q].v[i];
+            }
+            for (; j < nch; j++) {
                 Vec<VEC> t;
-                t.load(a.heavy_partial + ((size_t)h * S + sl) * a.F + c);
+                t.load_rw(src + (size_t)j * a.F + c);
 #pragma unroll
                 for (int i = 0; i < VEC; i++) acc.v[i] += t.v[i];
             }
@@ -340,10 +342,10 @@ int launch_lpr(const AggArgs &a, int lpr, int grid, cudaStream_t s)
 template <int VEC, int MODE>
 void launch_heavy_mode(const AggArgs &a, cudaStream_t s)
 {
-    const int gx = a.n_heavy < kNumSMs * 8 ? a.n_heavy : kNumSMs * 8;
-    const size_t smem = sizeof(float) * 8 * (size_t)a.F;
-    agg_heavy_kernel<VEC, MODE><<<dim3(gx, a.heavy_slices), 256, smem, s>>>(a);
-    agg_heavy_combine_kernel<VEC, MODE><<<gx, 128, 0, s>>>(a);
+    const int cap = kNumSMs * 8;   // 8 resident CTAs per SM, grid-stride beyond
+    const int g1 = min((a.heavy_chunks + 7) / 8, cap), g2 = min((a.n_heavy + 7) / 8, cap);
+    agg_heavy_chunk_kernel<VEC, MODE><<<g1, 256, 0, s>>>(a);
+    agg_heavy_combine_kernel<VEC, MODE><<<g2, 256, 0, s>>>(a);
 }
 
 template <int VEC>
@@ -393,7 +395,8 @@ int launch_agg(const AggArgs &a_in, bool strict, cudaStream_t s, int *launches)
     GNNB_CUDA(cudaGetLastError());
     if (launches) ++*launches;
     if (a.n_heavy > 0) {
-        GNNB_REQUIRE(a.heavy_rows != nullptr && a.heavy_partial != nullptr && a.heavy_slices > 0,
+        GNNB_REQUIRE(a.heavy_rows != nullptr && a.heavy_partial != nullptr && a.heavy_chunks > 0 &&
+                         a.heavy_chunk_base != nullptr && a.heavy_chunk_row != nullptr,
                      "heavy row list / partial buffer missing");
         GNNB_TRY(vec == 4 ? launch_heavy<4>(a, s) : launch_heavy<1>(a, s));
         GNNB_CUDA(cudaGetLastError());

@@ -8,11 +8,11 @@ namespace gnnb {
 
 // ---------------------------------------------------------------- graph tables (tables.cu)
 struct TableWorkspace {
-    DeviceBuf keys_in, keys_out, vals_in, vals_out, cub_tmp, heavy_rows, heavy_partial, counters;
+    DeviceBuf keys_in, keys_out, vals_in, vals_out, cub_tmp, heavy_partial, counters;
     DeviceBuf hub_hist, hub_cnt;
     void release_all()
     {
-        DeviceBuf *b[] = {&keys_in, &keys_out, &vals_in, &vals_out, &cub_tmp, &heavy_rows,
+        DeviceBuf *b[] = {&keys_in, &keys_out, &vals_in, &vals_out, &cub_tmp,
                           &heavy_partial, &counters, &hub_hist, &hub_cnt};
         for (DeviceBuf *x : b) x->release();
     }
@@ -42,9 +42,20 @@ int build_neighbor_tables(const int32_t *edge_list, const int32_t *in_deg, int n
 int build_partition_tables(const int32_t *edge_list, int row_begin, int n_local, int e,
                            int32_t *in_deg_local, int32_t *offsets_local, int32_t *nbr_global,
                            TableWorkspace &ws, cudaStream_t s, int *launches);
-// rows with in-degree > threshold, compacted into ws.heavy_rows; count returned through host ptr
-int find_heavy_rows(const int32_t *in_deg, int n, int threshold, TableWorkspace &ws,
-                    int *n_heavy_host, cudaStream_t s, int *launches);
+// Degree bucketing: rows longer than `threshold` ("heavy" rows; on the 2M-node power-law graph
+// 0.5 % of the rows hold 49 % of the edges) are cut into chunks of kHeavyChunk neighbors, one warp
+// per chunk, and a second kernel adds a row's chunk sums in order (deterministic).
+constexpr int kHeavyChunk = 128;
+struct HeavyList {
+    DeviceBuf rows;        // [n_heavy] row ids
+    DeviceBuf chunk_base;  // [n_heavy] first chunk of the row
+    DeviceBuf chunk_row;   // [n_chunks] index into rows[] of the chunk's row
+    int n_heavy = 0, n_chunks = 0;
+    void release() { rows.release(); chunk_base.release(); chunk_row.release(); n_heavy = n_chunks = 0; }
+};
+// fills `hl` from the row lengths (two small kernels and one host synchronisation)
+int find_heavy_rows(const int32_t *lengths, int n, int threshold, TableWorkspace &ws, HeavyList &hl,
+                    cudaStream_t s, int *launches);
 // degree bucketing parameters + partial-sum scratch for the heavy-row kernels
 constexpr int kHeavyThreshold = 256;
 // (tuning hook: GNNB_HEAVY_THRESHOLD overrides the bucket boundary)
@@ -57,7 +68,8 @@ inline int heavy_threshold()
     }();
     return v;
 }
-int heavy_setup(TableWorkspace &ws, int n_heavy, int F, int *slices);
+// partial-sum scratch of the heavy rows: [n_chunks][F] floats (grow-only)
+int heavy_setup(TableWorkspace &ws, int n_chunks, int F);
 // hub sources: copy of the neighbor table with bit 31 set on the most-referenced sources whose
 // feature rows fit budget_bytes (L2-resident set of the aggregation); tables.cu
 int mark_hub_sources(const int32_t *nbr_in, int32_t *nbr_out, int e, const int32_t *ref_cnt,
@@ -90,11 +102,18 @@ struct AggArgs {
     const float *dinv;     // AGG_GCN fast mode only
     int n;
     float eps;             // AGG_GIN
-    const int32_t *heavy_rows;  // optional list of rows handled by the CTA-per-row kernel
+    const int32_t *heavy_rows;  // optional list of rows handled by the chunked heavy-row kernels
     int n_heavy;
     int heavy_threshold;
-    float *heavy_partial;  // [n_heavy][heavy_slices][F] slice sums of the heavy rows
-    int heavy_slices;
+    float *heavy_partial;  // [heavy_chunks][F] chunk sums of the heavy rows
+    const int32_t *heavy_chunk_base, *heavy_chunk_row;
+    int heavy_chunks;
+    void set_heavy(const HeavyList &hl, float *partial)
+    {
+        heavy_rows = hl.rows.as<int32_t>(); n_heavy = hl.n_heavy;
+        heavy_chunk_base = hl.chunk_base.as<int32_t>(); heavy_chunk_row = hl.chunk_row.as<int32_t>();
+        heavy_chunks = hl.n_chunks; heavy_partial = partial;
+    }
     int row_base;          // row-partitioned graphs: global id of local row 0 (x / dinv are global,
                            // offsets / in_deg / out are local); 0 otherwise
     // ---- FAST-mode extensions (all 0 / null by default)

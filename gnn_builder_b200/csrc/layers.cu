@@ -542,15 +542,14 @@ namespace {
 // rows above the heavy threshold of one CSR (part), cached by the address of its row-length table
 struct HeavyCache {
     const int32_t *key = nullptr;
-    int n = 0, n_heavy = 0;
-    DeviceBuf rows;
+    int n = 0;
+    HeavyList list;
 };
 struct PartitionCache {
     TableWorkspace ws;
     DeviceBuf wt, img, agg, pool_tmp, pool_ptr;
     int64_t pool_n = -1;
-    const int32_t *heavy_key = nullptr;
-    int heavy_n = 0, n_heavy = 0, slices = 0;
+    HeavyCache whole;     // gnnb_gcn_conv_partition (one CSR)
     HeavyCache part[2];   // owned-source / halo-source part of a split CSR
 };
 thread_local PartitionCache g_part;
@@ -558,17 +557,11 @@ thread_local PartitionCache g_part;
 int heavy_rows_of(HeavyCache &hc, const int32_t *lengths, int n, cudaStream_t s)
 {
     if (hc.key == lengths && hc.n == n) return GNNB_OK;
-    GNNB_TRY(find_heavy_rows(lengths, n, heavy_threshold(), g_part.ws, &hc.n_heavy, s, nullptr));
-    if (hc.n_heavy > 0) {
-        GNNB_TRY(hc.rows.ensure(sizeof(int32_t) * (size_t)hc.n_heavy));
-        GNNB_CUDA(cudaMemcpyAsync(hc.rows.ptr, g_part.ws.heavy_rows.ptr, sizeof(int32_t) * (size_t)hc.n_heavy,
-                                  cudaMemcpyDeviceToDevice, s));
-    }
+    GNNB_TRY(find_heavy_rows(lengths, n, heavy_threshold(), g_part.ws, hc.list, s, nullptr));
     hc.key = lengths;
     hc.n = n;
     return GNNB_OK;
 }
-
 }  // namespace
 
 // ---- halo exchange kernels ---------------------------------------------------------------
@@ -652,7 +645,8 @@ extern "C" int gnnb_partition_tables(const int32_t *edge_list_local, int row_beg
     GNNB_REQUIRE(n_local >= 0 && num_edges_local >= 0 && row_begin >= 0, "negative size");
     GNNB_REQUIRE(num_edges_local == 0 || is_device_pointer(edge_list_local),
                  "gnnb_partition_tables takes device pointers");
-    g_part.heavy_key = nullptr;
+    g_part.whole.key = nullptr;
+    g_part.part[0].key = g_part.part[1].key = nullptr;
     return build_partition_tables(edge_list_local, row_begin, n_local, num_edges_local,
                                   in_degree_local, offsets_local, neighbor_table_global, g_part.ws,
                                   (cudaStream_t)stream, nullptr);
@@ -687,22 +681,16 @@ extern "C" int gnnb_gcn_conv_partition(int n_local, int row_begin, int n_total, 
     // tensor-core image of the same weight (two tiny kernels per call; the GEMM then runs on tcgen05)
     GNNB_TRY(g_part.img.ensure(sizeof(float) * gemm_tc_image_floats(emb_in, emb_out)));
     GNNB_TRY(gemm_tc_build_image(g_part.wt.as<float>(), ldw, emb_in, emb_out, g_part.img.as<float>(), s));
-    if (g_part.heavy_key != in_degree_local || g_part.heavy_n != n_local) {
-        GNNB_TRY(find_heavy_rows(in_degree_local, n_local, heavy_threshold(), g_part.ws,
-                                 &g_part.n_heavy, s, nullptr));
-        g_part.heavy_key = in_degree_local;
-        g_part.heavy_n = n_local;
-    }
-    // sized for THIS layer's emb_in on every call (ensure() only grows): the row list is cached
-    // across layers, the partial-sum scratch must follow the widest layer
-    GNNB_TRY(heavy_setup(g_part.ws, g_part.n_heavy, emb_in, &g_part.slices));
+    // the row list is cached across layers; the partial-sum scratch is sized for THIS layer's
+    // emb_in on every call (ensure() only grows)
+    GNNB_TRY(heavy_rows_of(g_part.whole, in_degree_local, n_local, s));
+    GNNB_TRY(heavy_setup(g_part.ws, g_part.whole.list.n_chunks, emb_in));
     AggArgs a{};
     a.mode = AGG_GCN; a.x = x_full; a.ldx = emb_in; a.F = emb_in; a.out = g_part.agg.as<float>();
     a.ldo = lda; a.offsets = offsets_local; a.nbr = neighbor_table_global; a.in_deg = in_degree_local;
     a.dinv = dinv_full; a.n = n_local; a.row_base = row_begin;
-    a.heavy_rows = g_part.ws.heavy_rows.as<int32_t>(); a.n_heavy = g_part.n_heavy;
     a.heavy_threshold = heavy_threshold();
-    a.heavy_partial = g_part.ws.heavy_partial.as<float>(); a.heavy_slices = g_part.slices;
+    a.set_heavy(g_part.whole.list, g_part.ws.heavy_partial.as<float>());
     GNNB_TRY(launch_agg(a, false, s, nullptr));
     GemmArgs g = simple_gemm(a.out, lda, emb_in, g_part.wt.as<float>(), ldw, bias, y_local, emb_out,
                              n_local, emb_out, act);
@@ -864,12 +852,10 @@ extern "C" int gnnb_gcn_conv_halo(int n_local, int n_ext, const float *x_ext, fl
                         bool accumulate, bool finish) -> int {
         HeavyCache &hc = g_part.part[which];
         GNNB_TRY(heavy_rows_of(hc, cnt, n_local, s));
-        int slices = 0;
-        GNNB_TRY(heavy_setup(g_part.ws, hc.n_heavy, emb_in, &slices));
+        GNNB_TRY(heavy_setup(g_part.ws, hc.list.n_chunks, emb_in));
         AggArgs b = a;
         b.offsets = off; b.nbr = nbr; b.in_deg = cnt;   // GCN fast mode reads the full degree from dinv only
-        b.heavy_rows = hc.rows.as<int32_t>(); b.n_heavy = hc.n_heavy;
-        b.heavy_partial = g_part.ws.heavy_partial.as<float>(); b.heavy_slices = slices;
+        b.set_heavy(hc.list, g_part.ws.heavy_partial.as<float>());
         b.accumulate = accumulate ? 1 : 0; b.no_finish = finish ? 0 : 1;
         return launch_agg(b, false, s, nullptr);
     };

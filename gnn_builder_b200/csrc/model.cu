@@ -229,6 +229,7 @@ extern "C" int gnnb_model_destroy(gnnb_model_t *m)
                          &m->hbuf[0], &m->hbuf[1], &m->pool_tmp, &m->ptr_tmp, &m->edge_flag};
     for (DeviceBuf *b : bufs) b->release();
     m->tws.release_all();
+    m->heavy.release();
     for (int i = 0; i < 2; i++) {
         m->ch_x[i].release(); m->ch_coo[i].release(); m->ch_nptr[i].release(); m->ch_eptr[i].release();
         if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
@@ -482,13 +483,14 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
         dinv = m->dinv.as<float>();
     }
     // degree bucketing only matters for big graphs (molecular graphs have in-degree <= ~8)
-    int n_heavy = 0, heavy_slices = 0, hub_bit = 0;
+    int hub_bit = 0;
+    m->heavy.n_heavy = m->heavy.n_chunks = 0;
     const int heavy_thr = heavy_threshold();
     m->last_hub_rows = 0;
     if (!strict && d.num_layers > 0 && d.conv_type != GNNB_CONV_PNA && n_graphs > 0 &&
         T64 / n_graphs > 50000) {
-        GNNB_TRY(find_heavy_rows(in_deg, T, heavy_thr, m->tws, &n_heavy, s, launches));
-        GNNB_TRY(heavy_setup(m->tws, n_heavy, maxf, &heavy_slices));
+        GNNB_TRY(find_heavy_rows(in_deg, T, heavy_thr, m->tws, m->heavy, s, launches));
+        GNNB_TRY(heavy_setup(m->tws, m->heavy.n_chunks, maxf));
         // a feature matrix larger than L2: keep the rows of the most-referenced sources resident
         // (the out-degree table, lib:1051-1083, is what ranks them)
         const size_t row_bytes = sizeof(float) * (size_t)std::max(d.in_dim, d.hidden_dim);
@@ -525,9 +527,9 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
         AggArgs a{};
         a.x = cur; a.ldx = cur_ld; a.F = fi; a.out = m->agg.as<float>(); a.ldo = round_up(fi, 4);
         a.offsets = offsets; a.nbr = nbr; a.in_deg = in_deg; a.dinv = dinv; a.n = T;
-        a.eps = d.gin_eps; a.heavy_rows = m->tws.heavy_rows.as<int32_t>(); a.n_heavy = n_heavy;
+        a.eps = d.gin_eps;
         a.heavy_threshold = heavy_thr;
-        a.heavy_partial = m->tws.heavy_partial.as<float>(); a.heavy_slices = heavy_slices;
+        a.set_heavy(m->heavy, m->tws.heavy_partial.as<float>());
         a.hub_bit = hub_bit;
         switch (d.conv_type) {
         case GNNB_CONV_GCN: {

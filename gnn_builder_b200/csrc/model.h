@@ -103,6 +103,7 @@ struct gnnb_model {
         hbuf[2], pool_tmp, ptr_tmp;
     int last_hub_rows = 0;   // sources whose feature rows the last large-graph run kept L2-resident
     gnnb::TableWorkspace tws;
+    gnnb::HeavyList heavy;       // rows above the heavy threshold of the current layerwise run
     gnnb::DeviceBuf edge_flag;   // layerwise path: set by the table kernels on an out-of-range endpoint
 
     gnnb::Profiler prof;

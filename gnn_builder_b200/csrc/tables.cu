@@ -99,11 +99,33 @@ __global__ void edge_prepare_partition_kernel(const int32_t *__restrict__ edge_l
     }
 }
 
-__global__ void heavy_rows_kernel(const int32_t *__restrict__ in_deg, int n, int threshold,
-                                  int32_t *__restrict__ rows, int32_t *__restrict__ counter)
+// counters: [0] heavy rows, [1] their chunks (pass 1); [2], [3] the same as running cursors (pass 2)
+__global__ void heavy_count_kernel(const int32_t *__restrict__ len, int n, int threshold,
+                                   int32_t *__restrict__ counters)
 {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        if (__ldg(in_deg + i) > threshold) rows[atomicAdd(counter, 1)] = i;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int l = __ldg(len + i);
+        if (l > threshold) {
+            atomicAdd(counters, 1);
+            atomicAdd(counters + 1, (l + kHeavyChunk - 1) / kHeavyChunk);
+        }
+    }
+}
+__global__ void heavy_fill_kernel(const int32_t *__restrict__ len, int n, int threshold,
+                                  int32_t *__restrict__ counters, int32_t *__restrict__ rows,
+                                  int32_t *__restrict__ chunk_base, int32_t *__restrict__ chunk_row)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int l = __ldg(len + i);
+        if (l > threshold) {
+            const int nch = (l + kHeavyChunk - 1) / kHeavyChunk;
+            const int pos = atomicAdd(counters + 2, 1);
+            const int cb = atomicAdd(counters + 3, nch);
+            rows[pos] = i;
+            chunk_base[pos] = cb;
+            for (int j = 0; j < nch; j++) chunk_row[cb + j] = pos;
+        }
+    }
 }
 
 __global__ void dinv_kernel(const int32_t *__restrict__ in_deg, float *__restrict__ dinv, int n)
@@ -300,22 +322,30 @@ int build_partition_tables(const int32_t *edge_list, int row_begin, int n_local,
     return GNNB_OK;
 }
 
-int find_heavy_rows(const int32_t *in_deg, int n, int threshold, TableWorkspace &ws,
-                    int *n_heavy_host, cudaStream_t s, int *launches)
+int find_heavy_rows(const int32_t *lengths, int n, int threshold, TableWorkspace &ws, HeavyList &hl,
+                    cudaStream_t s, int *launches)
 {
-    *n_heavy_host = 0;
+    hl.n_heavy = hl.n_chunks = 0;
     if (n <= 0) return GNNB_OK;
-    GNNB_TRY(ws.heavy_rows.ensure(sizeof(int32_t) * (size_t)n));
     GNNB_TRY(ws.counters.ensure(sizeof(int32_t) * 4));
     GNNB_CUDA(cudaMemsetAsync(ws.counters.ptr, 0, sizeof(int32_t) * 4, s));
-    heavy_rows_kernel<<<grid_for(n, 256), 256, 0, s>>>(in_deg, n, threshold,
-                                                      ws.heavy_rows.as<int32_t>(),
-                                                      ws.counters.as<int32_t>());
+    heavy_count_kernel<<<grid_for(n, 256), 256, 0, s>>>(lengths, n, threshold, ws.counters.as<int32_t>());
     GNNB_CUDA(cudaGetLastError());
     if (launches) ++*launches;
-    GNNB_CUDA(cudaMemcpyAsync(n_heavy_host, ws.counters.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost,
-                              s));
+    int32_t host[2] = {0, 0};
+    GNNB_CUDA(cudaMemcpyAsync(host, ws.counters.ptr, sizeof(host), cudaMemcpyDeviceToHost, s));
     GNNB_CUDA(cudaStreamSynchronize(s));
+    if (host[0] <= 0) return GNNB_OK;
+    GNNB_TRY(hl.rows.ensure(sizeof(int32_t) * (size_t)host[0]));
+    GNNB_TRY(hl.chunk_base.ensure(sizeof(int32_t) * (size_t)host[0]));
+    GNNB_TRY(hl.chunk_row.ensure(sizeof(int32_t) * (size_t)host[1]));
+    heavy_fill_kernel<<<grid_for(n, 256), 256, 0, s>>>(lengths, n, threshold, ws.counters.as<int32_t>(),
+                                                      hl.rows.as<int32_t>(), hl.chunk_base.as<int32_t>(),
+                                                      hl.chunk_row.as<int32_t>());
+    GNNB_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+    hl.n_heavy = host[0];
+    hl.n_chunks = host[1];
     return GNNB_OK;
 }
 
@@ -361,11 +391,9 @@ int mark_hub_sources(const int32_t *nbr_in, int32_t *nbr_out, int e, const int32
     return GNNB_OK;
 }
 
-int heavy_setup(TableWorkspace &ws, int n_heavy, int F, int *slices)
+int heavy_setup(TableWorkspace &ws, int n_chunks, int F)
 {
-    *slices = n_heavy <= 4096 ? 32 : (n_heavy <= 65536 ? 8 : 2);
-    if (n_heavy > 0)
-        GNNB_TRY(ws.heavy_partial.ensure(sizeof(float) * (size_t)n_heavy * *slices * (size_t)F));
+    if (n_chunks > 0) GNNB_TRY(ws.heavy_partial.ensure(sizeof(float) * (size_t)n_chunks * (size_t)F));
     return GNNB_OK;
 }
 
