@@ -104,10 +104,10 @@ def test_partition_layer_wider_second_call_with_hub_row(setup, orc):
         Wm = rng.uniform(-0.3, 0.3, (fo, fi)).astype(np.float32)
         bm = rng.uniform(-0.1, 0.1, fo).astype(np.float32)
         y = torch.empty((n2, fo), device="cuda")
+        dxs, dW, db = (torch.from_numpy(a).cuda() for a in (xs, Wm, bm))   # (kept alive over the call)
         _lib.check(lib.gnnb_gcn_conv_partition(
-            n2, 0, n2, coo2.shape[0], _p(torch.from_numpy(xs).cuda()), _p(y), _p(off), _p(nbr), _p(ind),
-            _p(dinv), _p(torch.from_numpy(Wm).cuda()), _p(torch.from_numpy(bm).cuda()), None, fi, fo,
-            1, None))
+            n2, 0, n2, coo2.shape[0], _p(dxs), _p(y), _p(off), _p(nbr), _p(ind), _p(dinv), _p(dW),
+            _p(db), None, fi, fo, 1, None))
         torch.cuda.synchronize()
         assert rel_err(y.cpu().numpy(), _gcn_rows_ref(orc, xs, coo2, n2, Wm, bm)) < TOL, (fi, fo)
 
