@@ -716,8 +716,8 @@ def measure_large(ctx: Ctx, w, nodes: int, steps: int, warmup: int, cpu_baseline
         ctx.barrier()
         B, plan = runner.backend, runner.plan
         W0, b0 = runner.layers[0]
-        x_ext = runner.ext[0][: plan.n_ext * F]
-        y_loc = runner.ext[1][: plan.n_local * F]
+        x_ext = runner.ext[runner._buf(0)][: plan.n_ext * F]
+        y_loc = runner.ext[runner._buf(1)][: plan.n_local * F]
         ev[2].record()
         for _ in range(iters):
             B.gcn_layer_halo(x_ext, y_loc, plan, runner.dinv_ext, W0, b0, None, 1, 3, F, F)

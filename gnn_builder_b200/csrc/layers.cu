@@ -575,9 +575,13 @@ struct PackArgs {
     long long off[kMaxPeers + 1];   // rows for peer p: send_idx[off[p] .. off[p+1])
     float *dst[kMaxPeers];          // where they go: a local send buffer or the peer's halo region
 };
-// one warp per row: dst_p[i][:] = x[send_idx[off[p] + i]][:]; 16-byte stores when F % 4 == 0, so a
-// row of F = 128 floats leaves the SM as one coalesced 512-byte write (over NVLink when dst_p is
-// a peer mapping)
+// A warp moves PACK_ROWS rows per iteration: all their loads are issued before the first store, so
+// every warp keeps PACK_ROWS x 512 bytes (F = 128) in flight and a grid of ONE CTA per SM already
+// holds several MB -- enough for the ~670 GB/s one NVLink direction delivers -- while leaving the
+// other seven CTA slots of every SM to the aggregation kernel that runs beside it.  16-byte
+// accesses when F % 4 == 0, so a row leaves the SM as one coalesced 512-byte write (over NVLink
+// when dst_p is a peer mapping).
+constexpr int PACK_ROWS = 8;
 __global__ void __launch_bounds__(256) halo_pack_kernel(const PackArgs a)
 {
     const int lane = threadIdx.x & 31;
@@ -585,16 +589,41 @@ __global__ void __launch_bounds__(256) halo_pack_kernel(const PackArgs a)
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long stride = (long long)gridDim.x * (blockDim.x >> 5);
     const bool v4 = (a.F % 4 == 0) && (a.ldx % 4 == 0);
-    for (long long i = warp0; i < total; i += stride) {
-        int p = 0;
-        while (p + 1 < a.n_peers && i >= a.off[p + 1]) p++;
-        const float *src = a.x + (size_t)__ldg(a.send_idx + i) * a.ldx;
-        float *dst = a.dst[p] + (size_t)(i - a.off[p]) * a.F;
+    for (long long i0 = warp0 * PACK_ROWS; i0 < total; i0 += stride * PACK_ROWS) {
+        const float *src[PACK_ROWS];
+        float *dst[PACK_ROWS];
+#pragma unroll
+        for (int r = 0; r < PACK_ROWS; r++) {
+            const long long i = i0 + r;
+            src[r] = nullptr;
+            dst[r] = nullptr;
+            if (i < total) {
+                int p = 0;
+                while (p + 1 < a.n_peers && i >= a.off[p + 1]) p++;
+                src[r] = a.x + (size_t)__ldg(a.send_idx + i) * a.ldx;
+                dst[r] = a.dst[p] + (size_t)(i - a.off[p]) * a.F;
+            }
+        }
         if (v4) {
-            for (int c = lane * 4; c < a.F; c += 128)
-                *reinterpret_cast<float4 *>(dst + c) = __ldg(reinterpret_cast<const float4 *>(src + c));
+            for (int c = lane * 4; c < a.F; c += 128) {
+                float4 v[PACK_ROWS];
+#pragma unroll
+                for (int r = 0; r < PACK_ROWS; r++)
+                    if (src[r] != nullptr) v[r] = __ldg(reinterpret_cast<const float4 *>(src[r] + c));
+#pragma unroll
+                for (int r = 0; r < PACK_ROWS; r++)
+                    if (dst[r] != nullptr) *reinterpret_cast<float4 *>(dst[r] + c) = v[r];
+            }
         } else {
-            for (int c = lane; c < a.F; c += 32) dst[c] = __ldg(src + c);
+            for (int c = lane; c < a.F; c += 32) {
+                float v[PACK_ROWS];
+#pragma unroll
+                for (int r = 0; r < PACK_ROWS; r++)
+                    if (src[r] != nullptr) v[r] = __ldg(src[r] + c);
+#pragma unroll
+                for (int r = 0; r < PACK_ROWS; r++)
+                    if (dst[r] != nullptr) dst[r][c] = v[r];
+            }
         }
     }
 }
@@ -747,8 +776,8 @@ extern "C" int gnnb_halo_pack(const float *x, int ldx, int F, const int32_t *sen
     }
     const long long total = a.off[n_peers];
     if (total == 0) return GNNB_OK;
-    long long grid = (total + 7) / 8;
-    const long long cap = max_ctas > 0 ? max_ctas : kNumSMs * 8;
+    long long grid = (total + 8 * PACK_ROWS - 1) / (8 * PACK_ROWS);
+    const long long cap = max_ctas > 0 ? max_ctas : kNumSMs;   // one CTA per SM: see the kernel
     if (grid > cap) grid = cap;
     halo_pack_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(a);
     GNNB_CUDA(cudaGetLastError());

@@ -180,7 +180,12 @@ class CudaBackend:
         self._lib = _lib
         self.lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.comm = torch.cuda.Stream()
+        # the exchange stream outranks the compute stream: its few CTAs are placed first and the
+        # aggregation fills the rest of every SM
+        self.comm = torch.cuda.Stream(priority=-1)
+        import os
+
+        self.pack_ctas = int(os.environ.get("GNNB_HALO_PACK_CTAS", 0))
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         self._owned, self._opened = [], []
 
@@ -245,7 +250,7 @@ class CudaBackend:
         off = (C.c_int64 * (W + 1))(*[int(v) for v in plan.send_off])
         dst = (C.c_void_p * W)(*[C.c_void_p(int(p)) for p in dst_ptrs])
         self._lib.check(self.lib.gnnb_halo_pack(self._p(x_own), F, F, self._p(plan.send_idx), off,
-                                                dst, W, max_ctas, self._stream()))
+                                                dst, W, max_ctas or self.pack_ctas, self._stream()))
 
     def pack_rows(self, x_own, F: int, plan: HaloPlan, send):
         """send[send_off[p] + i] = x_own[send_idx[...]]: the rows of every peer, contiguous (NCCL)"""
@@ -400,7 +405,7 @@ class LargeGraphGCN:
                                        + getattr(self, "_p2p_error", "(another rank)"))
                 self.ext = None
         if self.ext is None:
-            self.ext = [B.empty((plan.n_ext * fmax,)) for _ in range(2)]
+            self.ext = [B.empty((plan.n_ext * fmax,)) for _ in range(3)]
             self.transport = "nccl" if W > 1 else "none"
             if W > 1:
                 self.send_buf = B.empty((max(1, int(plan.send_off[-1])) * fmax,))
@@ -414,14 +419,15 @@ class LargeGraphGCN:
 
         B, W, plan, dist = self.backend, self.world, self.plan, self.dist
         nbytes = max(plan.n_ext * fmax * 4, 256)
-        bufs = [B.ipc_alloc(nbytes) for _ in range(2)]
+        bufs = [B.ipc_alloc(nbytes) for _ in range(3)]
         flags_t, flags_ptr, flags_h = B.ipc_alloc(8 * 32)
         self.ext = [t.view(torch.float32) for t, _, _ in bufs]
         self._ext_ptr = [p for _, p, _ in bufs]
         self._flags, self._flags_ptr = flags_t.view(torch.int64), flags_ptr
         self._timed_out = torch.zeros(1, dtype=torch.int32, device=flags_t.device)
-        mine = torch.frombuffer(bytearray(bufs[0][2] + bufs[1][2] + flags_h), dtype=torch.uint8).to(flags_t.device)
-        allh = torch.empty(W * 192, dtype=torch.uint8, device=flags_t.device)
+        mine = torch.frombuffer(bytearray(bufs[0][2] + bufs[1][2] + bufs[2][2] + flags_h),
+                                dtype=torch.uint8).to(flags_t.device)
+        allh = torch.empty(W * 256, dtype=torch.uint8, device=flags_t.device)
         dist.all_gather_into_tensor(allh, mine)
         allh = allh.cpu().numpy().tobytes()
         # where do MY rows start inside peer p's halo region?  p's recv_off[my rank], in rows
@@ -429,15 +435,15 @@ class LargeGraphGCN:
         at_peer = torch.empty(W, dtype=torch.int64, device=flags_t.device)
         dist.all_to_all_single(at_peer, recv_off)
         self._row_at_peer = [int(v) for v in at_peer.cpu().tolist()]
-        self._peer_ext = [[0] * W, [0] * W]
+        self._peer_ext = [[0] * W, [0] * W, [0] * W]
         self._peer_flag = [0] * W
         for p in range(W):
             if p == self.rank:
                 continue
-            h = allh[192 * p: 192 * (p + 1)]
-            self._peer_ext[0][p] = B.ipc_open(h[0:64])
-            self._peer_ext[1][p] = B.ipc_open(h[64:128])
-            self._peer_flag[p] = B.ipc_open(h[128:192]) + 8 * self.rank
+            h = allh[256 * p: 256 * (p + 1)]
+            for i in range(3):
+                self._peer_ext[i][p] = B.ipc_open(h[64 * i: 64 * (i + 1)])
+            self._peer_flag[p] = B.ipc_open(h[192:256]) + 8 * self.rank
         self._peer_flag[self.rank] = flags_ptr + 8 * self.rank
 
     def close(self):
@@ -448,14 +454,20 @@ class LargeGraphGCN:
             self.ext = None
 
     # ------------------------------------------------------------------ forward
+    @staticmethod
+    def _buf(k: int) -> int:
+        """ext buffer that holds the INPUT of conv layer k (and receives its halo): the layer-0
+        input has a buffer of its own, so a forward never overwrites it; the others alternate"""
+        return 2 if k == 0 else (k & 1)
+
     def input_view(self):
         """where the layer-0 input of this rank lives: [n_local][in_dim] (write here to skip a copy)"""
-        return self.ext[0][: self.part.n_local * self.dims[0]].view(self.part.n_local, self.dims[0])
+        return self.ext[2][: self.part.n_local * self.dims[0]].view(self.part.n_local, self.dims[0])
 
     def _exchange(self, k: int, F: int):
-        """fills the halo region of ext[k & 1] with the peers' layer-k input rows (comm stream)"""
+        """fills the halo region of layer k's input buffer with the peers' rows (comm stream)"""
         B, W, plan = self.backend, self.world, self.plan
-        cur = self.ext[k & 1]
+        cur = self.ext[self._buf(k)]
         x_own = cur[: plan.n_local * F]
         self.epoch += 1
         B.fork()
@@ -463,7 +475,7 @@ class LargeGraphGCN:
             if self.transport == "p2p":
                 n_local = plan.n_local
                 dst = [0 if p == self.rank or plan.send_counts[p] == 0 else
-                       self._peer_ext[k & 1][p] + 4 * F * (n_local + self._row_at_peer[p])
+                       self._peer_ext[self._buf(k)][p] + 4 * F * (n_local + self._row_at_peer[p])
                        for p in range(W)]
                 B.halo_pack(x_own, F, plan, dst)
                 B.halo_signal(self._peer_flag, self.epoch)
@@ -495,7 +507,7 @@ class LargeGraphGCN:
         L = d["num_layers"]
         for k, (W, b) in enumerate(self.layers):
             fi, fo = self.dims[k], self.dims[k + 1]
-            cur, nxt = self.ext[k & 1], self.ext[(k + 1) & 1]
+            cur, nxt = self.ext[self._buf(k)], self.ext[self._buf(k + 1)]
             x_ext = cur[: plan.n_ext * fi]
             y_local = nxt[: n_local * fo]
             do_skip = bool(d["skip"]) and k != 0 and k != L - 1
@@ -510,7 +522,7 @@ class LargeGraphGCN:
                 B.gcn_layer_halo(*args, 3, fi, fo)
             if capture is not None and capture[0] == k:
                 self.captured = y_local[: min(capture[1], n_local) * fo].view(-1, fo).clone()
-        emb = self.ext[L & 1][: n_local * self.dims[L]].view(n_local, self.dims[L])
+        emb = self.ext[self._buf(L)][: n_local * self.dims[L]].view(n_local, self.dims[L])
         s, mx = B.pool_partial(emb)
         if self.world > 1:
             s = B.all_reduce(self.dist, s, self.dist.ReduceOp.SUM)

@@ -236,7 +236,8 @@ int gnnb_pool_partial(const float *x, int64_t n, int F, float *out, void *stream
 /* dst[p][i][0..F) = x[send_idx[send_off[p] + i]][0..F) for every peer p < n_peers (<= 16).
  * send_off (n_peers + 1 entries) and dst (n_peers pointers) are HOST arrays; dst[p] is a local
  * send buffer (NCCL transport) or the peer's halo region through a CUDA-IPC mapping (the rows
- * then leave as NVLink stores).  max_ctas <= 0: default grid. */
+ * then leave as NVLink stores).  max_ctas <= 0: one CTA per SM, which keeps enough bytes in flight
+ * for one NVLink direction and leaves the rest of every SM to the kernel running beside it. */
 int gnnb_halo_pack(const float *x, int ldx, int F, const int32_t *send_idx, const int64_t *send_off,
                    float *const *dst, int n_peers, int max_ctas, void *stream);
 /* system-scope release store of `value` to peer_flags[p] (HOST array of n_peers device pointers,
