@@ -38,8 +38,20 @@
 //
 // Supported: GCN, GIN and SAGE, layer widths a multiple of 16 up to 128; everything else uses
 // fused.cu / the layerwise path.
+//
+// Arithmetic of the node transform (GNNB_TC_BF2, default 1): "bf16x2".  The north star asks for
+// <= 1e-4 relative; round 1's 3xTF32 (three kind::tf32 MMAs per product, ~2^-21) measured 5e-6 and
+// spent 20x more tensor-pipe time than the budget needs.  With GNNB_TC_BF2 every fp32 operand is
+// split into two bf16 values  v ~= hi + mid  (both rounded to nearest, |v - hi - mid| <= 2^-18 |v|)
+// and a product is  A_hi.W_hi + A_mid.W_hi + A_hi.W_mid  as three kind::f16 MMAs, each covering
+// K = 16 instead of 8: half the tensor-pipe time and half the weight bytes streamed per linear.
+// The A operand sits in tensor memory as PACKED bf16 pairs (K elements 2j, 2j+1 in the low / high
+// half of column j; layout pinned by tools/tmem_bf16_probe.py, profiles/r2_tmem_bf16_layout_probe.txt)
+// and the layer input keeps two bf16 planes instead of three.  -DGNNB_TC_BF2=0 rebuilds the
+// 3xTF32 kernel for A/B runs.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "model.h"
@@ -73,6 +85,41 @@ void build_weight_image(const float *W, int N, int n_valid, int K, int ld, int c
 }
 
 
+// bf16 rounded to nearest (ties away from zero in magnitude), as an fp32 bit pattern
+static inline uint32_t bf16_rn_bits_host(float v)
+{
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    return (u + 0x8000u) & 0xffff0000u;
+}
+// bf16x2 weight image: per K atom (64 columns of K) the N x 128-byte rows of W as bf16 in the
+// canonical K-major SWIZZLE_128B layout, hi part (W rounded to bf16) followed by the mid part
+// (the residual rounded to bf16).  Same byte size per atom as the TF32 image of 32 columns.
+void build_weight_image_bf2(const float *W, int N, int n_valid, int K, int ld, int col0,
+                            std::vector<float> &img)
+{
+    const int KA = (K + 63) / 64;
+    const size_t atom_floats = (size_t)2 * N * 32;   // 2 units of N x 128 bytes
+    const size_t base = img.size();
+    img.resize(base + (size_t)KA * atom_floats, 0.0f);
+    for (int ka = 0; ka < KA; ka++) {
+        uint16_t *hi = reinterpret_cast<uint16_t *>(img.data() + base + (size_t)ka * atom_floats);
+        uint16_t *mid = hi + (size_t)N * 64;
+        for (int n = 0; n < N; n++)
+            for (int kk = 0; kk < 64; kk++) {
+                const int k = ka * 64 + kk;
+                const float v = (k < K && n < n_valid) ? W[(size_t)n * ld + col0 + k] : 0.0f;
+                const uint32_t hb = bf16_rn_bits_host(v);
+                float hf;
+                memcpy(&hf, &hb, 4);
+                const uint32_t mb = bf16_rn_bits_host(v - hf);
+                const size_t off = (size_t)n * 64 + (size_t)(((kk >> 3) ^ (n & 7)) * 8) + (kk & 7);
+                hi[off] = (uint16_t)(hb >> 16);
+                mid[off] = (uint16_t)(mb >> 16);
+            }
+    }
+}
+
 namespace {
 
 constexpr int TM = 128;
@@ -95,8 +142,17 @@ constexpr int SLOT_STRIDE = 16384;
 constexpr int RING_BYTES = NSLOT * SLOT_STRIDE;
 constexpr int CNT_BYTES = TM * TM;
 constexpr int MAX_NODES_PER_GRAPH = TM;   // a graph must fit one tile
+#ifndef GNNB_TC_BF2
+#define GNNB_TC_BF2 1
+#endif
+constexpr bool BF2 = GNNB_TC_BF2 != 0;
+constexpr int NPLANES = BF2 ? 2 : 3;            // bf16 planes of the layer input
+constexpr int WATOM_K = BF2 ? 64 : 32;          // K elements per 128-byte row of a weight atom
+constexpr int WMMA_K = BF2 ? 16 : 8;            // K per MMA of the node transform
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TM_D0 = 0, TM_AHI = 128, TM_ALO = 256, TM_D1 = 384;
+// A operand: bf16x2 = packed pairs, 64 columns per 128 K for each of hi / mid; 3xTF32 = 128 each
+constexpr uint32_t TM_D0 = 0, TM_AHI = 128, TM_ALO = BF2 ? 192 : 256, TM_D1 = 384;
+static_assert(!BF2 || GNNB_TC_WORKERS == 256, "bf16x2 packs 32-column chunks into 16 cells: 8 worker warps");
 static_assert(NWARPS == 8 || NWARPS == 16, "row passes: 8 worker warps (two 32-column blocks each) or 16 (one each)");
 constexpr int PASS_STEPS = 2;                // one step per 64-column half
 constexpr int STEP_COLS = 256 / NWARPS;      // columns of its rows a warp converts per step (32 or 16)
@@ -285,6 +341,74 @@ __device__ __forceinline__ void produce_linear(Misc &ms, uint32_t ring, uint32_t
 // (A_hi.B_hi and A_lo.B_hi), then the lo atoms (A_hi.B_lo).  All lanes of the issuing warp.
 // The A operand arrives in two halves: the hi atoms that only touch columns [0, 64) are issued as
 // soon as ready[0] completes, i.e. while the workers are still converting columns [64, 128).
+#if GNNB_TC_BF2
+// bf16x2 version: a weight atom covers K = 64 (= one 64-column half of the A operand, i.e. 32
+// packed TMEM columns per part), 4 k-steps of K = 16; hi atoms feed A_hi.W_hi and A_mid.W_hi, the
+// mid atoms A_hi.W_mid.  Only the k-steps that cover real K columns are issued (layer 0 of the
+// QM9 model has K = 11: one k-step).
+__device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &cons, uint32_t tmem_base,
+                                           uint32_t dcol, const TLinear &L, bool accumulate,
+                                           uint32_t &ready_cnt)
+{
+    const bool leader = tc::elect_one();
+    const int KA = L.KA;
+    const uint32_t idesc = tc::make_idesc_bf16(TM, L.N, 0);
+    const uint32_t tmem_d = tmem_base + dcol, ahi = tmem_base + TM_AHI, amid = tmem_base + TM_ALO;
+    tc::mbar_wait(&ms.bar_ready[0], ready_cnt & 1);
+    tc::tc_fence_after();
+    for (int ka = 0; ka < KA; ka++) {   // hi atoms
+        if (ka == 1) {
+            tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1);
+            tc::tc_fence_after();
+        }
+        const uint32_t s = cons & (NSLOT - 1);
+        tc::mbar_wait(&ms.bar_full[s], (cons / NSLOT) & 1);
+        tc::tc_fence_after();
+        const uint32_t col = (uint32_t)(ka * 32);
+        const int nk = min(4, (L.K - ka * 64 + 15) >> 4);
+        const uint64_t bd = tc::make_desc(ring + s * SLOT_STRIDE);
+        const uint32_t first = (ka == 0 && !accumulate) ? 0u : 1u;
+        if (leader) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) {
+                if (k4 < nk) {
+                    // +2 per k-step: 16 bf16 = 32 bytes along K inside the swizzle atom (>> 4)
+                    tc::mma_bf16_ts(tmem_d, ahi + col + 8 * k4, bd + (uint64_t)(2 * k4), idesc,
+                                    k4 == 0 ? first : 1u);
+                    tc::mma_bf16_ts(tmem_d, amid + col + 8 * k4, bd + (uint64_t)(2 * k4), idesc, 1u);
+                }
+            }
+            tc::mma_commit(&ms.bar_empty[s]);
+        }
+        cons++;
+    }
+    if (KA <= 1) {
+        tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1);
+        tc::tc_fence_after();
+    }
+    ready_cnt++;
+    for (int ka = 0; ka < KA; ka++) {   // mid atoms
+        const uint32_t s = cons & (NSLOT - 1);
+        tc::mbar_wait(&ms.bar_full[s], (cons / NSLOT) & 1);
+        tc::tc_fence_after();
+        const uint32_t col = (uint32_t)(ka * 32);
+        const int nk = min(4, (L.K - ka * 64 + 15) >> 4);
+        const uint64_t bd = tc::make_desc(ring + s * SLOT_STRIDE);
+        if (leader) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++)
+                if (k4 < nk)
+                    tc::mma_bf16_ts(tmem_d, ahi + col + 8 * k4, bd + (uint64_t)(2 * k4), idesc, 1u);
+            tc::mma_commit(&ms.bar_empty[s]);
+        }
+        cons++;
+    }
+    if (leader) {
+        tc::mma_commit(&ms.bar_done[0]);
+        tc::mma_commit(&ms.bar_done[1]);
+    }
+}
+#else
 __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &cons, uint32_t tmem_base,
                                            uint32_t dcol, const TLinear &L, bool accumulate,
                                            uint32_t &ready_cnt)
@@ -343,6 +467,7 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &co
         tc::mma_commit(&ms.bar_done[1]);
     }
 }
+#endif
 
 // AGG[128][n_cols] = ADJ . (Xh + Xm + Xl), K = source nodes (16 per MMA, only the k-steps that
 // cover the tile's rows).  Warp-uniform, like gemm_issue.  Issued per 64-column half of the
@@ -363,7 +488,7 @@ __device__ __forceinline__ void agg_issue(Misc &ms, uint32_t tmem_d, uint32_t ad
         if (nh > 0) {
             const uint32_t idesc = tc::make_idesc_bf16(TM, nh, 1);
 #pragma unroll
-            for (int pl = 0; pl < 3; pl++) {
+            for (int pl = 0; pl < NPLANES; pl++) {
                 const uint64_t b0 = tc::make_desc_mn(xp + (uint32_t)pl * tc::PLANE_BYTES +
                                                          (uint32_t)h * tc::PLANE_BLOCK_BYTES,
                                                      tc::PLANE_BLOCK_BYTES, 1024u);
@@ -383,31 +508,77 @@ __device__ __forceinline__ void agg_issue(Misc &ms, uint32_t tmem_d, uint32_t ad
 // ---------------------------------------------------------------------------------------
 // Thread-per-row helpers.  Warp w owns TMEM lanes [32 (w & 3), +32) and the column blocks
 // c0 = 32 (w >> 2), +64, ...
+// bf16 rounded to nearest (ties away from zero), as an fp32 bit pattern with a zero low half
+__device__ __forceinline__ uint32_t bf16_rn_bits(float v)
+{
+    return (__float_as_uint(v) + 0x8000u) & 0xffff0000u;
+}
 __device__ __forceinline__ void load_row8(const unsigned char *XP, int row, int c, float (&v)[8])
 {
     const uint32_t off = tc::plane_chunk_offset(row, c);
     const uint4 h = *reinterpret_cast<const uint4 *>(XP + off);
     const uint4 m = *reinterpret_cast<const uint4 *>(XP + tc::PLANE_BYTES + off);
-    const uint4 l = *reinterpret_cast<const uint4 *>(XP + 2 * tc::PLANE_BYTES + off);
-    tc::join3_unpack8(h, m, l, v);
+    if (BF2) {
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(mw[j] << 16);
+            v[2 * j + 1] = __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(mw[j] & 0xffff0000u);
+        }
+    } else {
+        const uint4 l = *reinterpret_cast<const uint4 *>(XP + 2 * tc::PLANE_BYTES + off);
+        tc::join3_unpack8(h, m, l, v);
+    }
 }
 __device__ __forceinline__ void store_row8(unsigned char *XP, int row, int c, const float (&v)[8])
 {
-    uint4 h, m, l;
-    tc::split3_pack8(v, h, m, l);
     const uint32_t off = tc::plane_chunk_offset(row, c);
-    *reinterpret_cast<uint4 *>(XP + off) = h;
-    *reinterpret_cast<uint4 *>(XP + tc::PLANE_BYTES + off) = m;
-    *reinterpret_cast<uint4 *>(XP + 2 * tc::PLANE_BYTES + off) = l;
-}
-template <int W>
-__device__ __forceinline__ void split_store(uint32_t ahi, uint32_t alo, const float (&v)[W])
-{
-    float h[W], l[W];
+    if (BF2) {
+        uint32_t hb[8], mb[8];
 #pragma unroll
-    for (int j = 0; j < W; j++) { h[j] = tc::tf32_hi(v[j]); l[j] = v[j] - h[j]; }
-    tc::tmem_st(ahi, h);
-    tc::tmem_st(alo, l);
+        for (int j = 0; j < 8; j++) {
+            hb[j] = bf16_rn_bits(v[j]);
+            mb[j] = bf16_rn_bits(v[j] - __uint_as_float(hb[j]));
+        }
+        *reinterpret_cast<uint4 *>(XP + off) =
+            make_uint4(__byte_perm(hb[0], hb[1], 0x7632), __byte_perm(hb[2], hb[3], 0x7632),
+                       __byte_perm(hb[4], hb[5], 0x7632), __byte_perm(hb[6], hb[7], 0x7632));
+        *reinterpret_cast<uint4 *>(XP + tc::PLANE_BYTES + off) =
+            make_uint4(__byte_perm(mb[0], mb[1], 0x7632), __byte_perm(mb[2], mb[3], 0x7632),
+                       __byte_perm(mb[4], mb[5], 0x7632), __byte_perm(mb[6], mb[7], 0x7632));
+    } else {
+        uint4 h, m, l;
+        tc::split3_pack8(v, h, m, l);
+        *reinterpret_cast<uint4 *>(XP + off) = h;
+        *reinterpret_cast<uint4 *>(XP + tc::PLANE_BYTES + off) = m;
+        *reinterpret_cast<uint4 *>(XP + 2 * tc::PLANE_BYTES + off) = l;
+    }
+}
+// W consecutive fp32 columns [c0, c0 + W) of this thread's row -> the A operand in tensor memory.
+// 3xTF32: hi / lo parts, one 32-bit cell per element.  bf16x2: hi / mid parts as packed bf16
+// pairs (elements 2j, 2j+1 of the row in the low / high half of cell j), so W columns are W / 2 cells.
+template <int W>
+__device__ __forceinline__ void split_store(uint32_t tmem_base, uint32_t lane_base, int c0, const float (&v)[W])
+{
+    if (BF2) {
+        float h[W / 2], m[W / 2];
+#pragma unroll
+        for (int j = 0; j < W / 2; j++) {
+            const uint32_t h0 = bf16_rn_bits(v[2 * j]), h1 = bf16_rn_bits(v[2 * j + 1]);
+            const uint32_t m0 = bf16_rn_bits(v[2 * j] - __uint_as_float(h0));
+            const uint32_t m1 = bf16_rn_bits(v[2 * j + 1] - __uint_as_float(h1));
+            h[j] = __uint_as_float(__byte_perm(h0, h1, 0x7632));
+            m[j] = __uint_as_float(__byte_perm(m0, m1, 0x7632));
+        }
+        tc::tmem_st(tmem_base + TM_AHI + lane_base + (uint32_t)(c0 >> 1), h);
+        tc::tmem_st(tmem_base + TM_ALO + lane_base + (uint32_t)(c0 >> 1), m);
+    } else {
+        float h[W], l[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) { h[j] = tc::tf32_hi(v[j]); l[j] = v[j] - h[j]; }
+        tc::tmem_st(tmem_base + TM_AHI + lane_base + (uint32_t)c0, h);
+        tc::tmem_st(tmem_base + TM_ALO + lane_base + (uint32_t)c0, l);
+    }
 }
 
 // Hand-off to the issuing warp, one arrival per worker warp and per 64-column half: every lane has
@@ -510,8 +681,7 @@ __device__ __forceinline__ void cvt_agg(Misc &ms, uint32_t &done_cnt, uint32_t t
 #pragma unroll
             for (int j = 0; j < CH; j++) v[j] *= scale;
         }
-        split_store(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
-                    tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
+        split_store(tmem_base, lane_base, c0, v);
     });
 }
 
@@ -536,8 +706,7 @@ __device__ __forceinline__ void cvt_self(Misc &ms, uint32_t tmem_base, const uns
 #pragma unroll
                     for (int j = 0; j < 8; j++) v[8 * j8 + j] = xs[j];
                 }
-                split_store(tmem_base + TM_AHI + lane_base + (uint32_t)cc,
-                            tmem_base + TM_ALO + lane_base + (uint32_t)cc, v);
+                split_store(tmem_base, lane_base, cc, v);
             }
         }
         tc::tmem_st_wait();
@@ -563,8 +732,7 @@ __device__ __forceinline__ void epilogue_tmem_t(Misc &ms, uint32_t &done_cnt, ui
             for (int j = 0; j < 4; j++)
                 v[j4 * 4 + j] = in_range ? act_fast<ACT>(act, __uint_as_float(r[j4 * 4 + j]) + bss[j]) : 0.0f;
         }
-        split_store(tmem_base + TM_AHI + lane_base + (uint32_t)c0,
-                    tmem_base + TM_ALO + lane_base + (uint32_t)c0, v);
+        split_store(tmem_base, lane_base, c0, v);
     });
 }
 __device__ __forceinline__ void epilogue_tmem(Misc &ms, uint32_t &done_cnt, uint32_t tmem_base, uint32_t dcol,
@@ -717,7 +885,7 @@ __device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, uint32_t
         for (int c = 0; c < nch; c++) {
             const TLinear &L = p.hl[j][c];
             if (j == 0) {  // A chunk: pending[:, 128c : 128c + K) -> (hi, lo), zero padded
-                const int kp = L.KA * tc::ATOM_K;
+                const int kp = (L.K + 31) & ~31;
                 const float *src = pending + (size_t)row * PLD + c * 128;
 #pragma unroll 1
                 for (int st = 0; st < PASS_STEPS; st++) {
@@ -733,8 +901,7 @@ __device__ __forceinline__ void head_flush(const TcParams &p, Misc &ms, uint32_t
                                     t = __ldcg(reinterpret_cast<const float4 *>(src + cc + j4 * 4));
                                 v[j4 * 4] = t.x; v[j4 * 4 + 1] = t.y; v[j4 * 4 + 2] = t.z; v[j4 * 4 + 3] = t.w;
                             }
-                            split_store(tmem_base + TM_AHI + lane_base + (uint32_t)cc,
-                                        tmem_base + TM_ALO + lane_base + (uint32_t)cc, v);
+                            split_store(tmem_base, lane_base, cc, v);
                         }
                     }
                     tc::tmem_st_wait();
@@ -774,7 +941,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
     unsigned char *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *ADJ = base;
     unsigned char *XP = ADJ + tc::PLANE_BYTES;
-    unsigned char *RING = XP + 3 * tc::PLANE_BYTES;
+    unsigned char *RING = XP + NPLANES * tc::PLANE_BYTES;
     uint32_t *CNT = reinterpret_cast<uint32_t *>(RING + RING_BYTES);
     Misc &ms = *reinterpret_cast<Misc *>(RING + RING_BYTES + CNT_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -809,7 +976,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, ms.tmem_slot, 0);
     const uint32_t adj_addr = __shfl_sync(0xffffffffu, tc::smem_u32(ADJ), 0);
     const uint32_t xp_addr = adj_addr + tc::PLANE_BYTES;
-    const uint32_t ring_addr = adj_addr + 4 * tc::PLANE_BYTES;
+    const uint32_t ring_addr = adj_addr + (1 + NPLANES) * tc::PLANE_BYTES;
     uint32_t done_cnt = 0, cons = 0, dw = 0;   // dw: accumulator buffer of the latest new MMA phase
     const int n_tiles = __shfl_sync(0xffffffffu, __ldg(p.n_tiles_ptr), 0);
 
@@ -910,7 +1077,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
         if (bad && tid == 0) atomicExch(p.error_flag, 1);
         const bool run = ng > 0 && !bad;
         const int r_own = tid & (TM - 1), c_half = tid >> 7;   // staging role: (row, chunk parity)
-        const int kp0 = (p.in_dim + 31) & ~31;
+        const int kp0 = (p.in_dim + 31) & ~31;   // plane columns staged (aggregation K atoms of 32 features)
         if (run) {
             worker_sync();   // the previous tile's pooling has finished reading the planes
             // ---------------------------------------------------------------- stage inputs
@@ -1040,6 +1207,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
         // -------------------------------------------------------------------- conv layers
         for (int l = 0; l < p.num_layers; l++) {
             const int fi = p.fi[l];
+            // A-operand columns the row passes define; the MMAs read whole k-steps of real K only
             const int kp = (fi + 31) & ~31;
             const bool last_layer = l == p.num_layers - 1;
             const bool do_skip = p.skip && l != 0 && !last_layer;  // cpp:269-279
@@ -1179,6 +1347,11 @@ int fused_tc_prepare(gnnb_model *m)
 
     // weight images from the host copies of the parameters (flat reference order: head first)
     std::vector<float> img;
+    auto build_image = [](const float *W, int N, int n_valid, int K, int ld, int col0,
+                          std::vector<float> &out) {
+        if (BF2) build_weight_image_bf2(W, N, n_valid, K, ld, col0, out);
+        else build_weight_image(W, N, n_valid, K, ld, col0, out);
+    };
     struct Pending { size_t off; int K, N; };
     std::vector<Pending> pend;
     size_t idx = 2 * (size_t)d.mlp_num_linear;
@@ -1187,19 +1360,19 @@ int fused_tc_prepare(gnnb_model *m)
         m->layer_dims(k, &fi, &fo);
         if (d.conv_type == GNNB_CONV_GCN) {  // [bias, lin_weight]
             pend.push_back({img.size(), fi, fo});
-            build_weight_image(m->params[idx + 1].host.data(), fo, fo, fi, fi, 0, img);
+            build_image(m->params[idx + 1].host.data(), fo, fo, fi, fi, 0, img);
             idx += 2;
         } else if (d.conv_type == GNNB_CONV_GIN) {  // [w0, b0, w1, b1]
             pend.push_back({img.size(), fi, fo});
-            build_weight_image(m->params[idx].host.data(), fo, fo, fi, fi, 0, img);
+            build_image(m->params[idx].host.data(), fo, fo, fi, fi, 0, img);
             pend.push_back({img.size(), fo, fo});
-            build_weight_image(m->params[idx + 2].host.data(), fo, fo, fo, fo, 0, img);
+            build_image(m->params[idx + 2].host.data(), fo, fo, fo, fo, 0, img);
             idx += 4;
         } else {                                    // SAGE: [lin_l.weight, lin_l.bias, lin_r.weight]
             pend.push_back({img.size(), fi, fo});
-            build_weight_image(m->params[idx].host.data(), fo, fo, fi, fi, 0, img);
+            build_image(m->params[idx].host.data(), fo, fo, fi, fi, 0, img);
             pend.push_back({img.size(), fi, fo});
-            build_weight_image(m->params[idx + 2].host.data(), fo, fo, fi, fi, 0, img);
+            build_image(m->params[idx + 2].host.data(), fo, fo, fi, fi, 0, img);
             idx += 3;
         }
     }
@@ -1219,7 +1392,7 @@ int fused_tc_prepare(gnnb_model *m)
             for (int c = 0; c < h.nch; c++) {
                 h.K[c] = std::min(128, in - 128 * c);
                 h.off[c] = img.size();
-                build_weight_image(W, h.N, out, h.K[c], in, 128 * c, img);
+                build_image(W, h.N, out, h.K[c], in, 128 * c, img);
             }
             h.bias = img.size();
             img.resize(img.size() + h.N, 0.0f);
@@ -1257,7 +1430,7 @@ int fused_tc_prepare(gnnb_model *m)
         auto mk = [&](const Pending &q, const float *bias) {
             TLinear t;
             t.img = base + q.off; t.bias = bias; t.K = q.K; t.N = q.N;
-            t.KA = (q.K + tc::ATOM_K - 1) / tc::ATOM_K;
+            t.KA = (q.K + WATOM_K - 1) / WATOM_K;
             return t;
         };
         p.l0[k] = mk(pend[pi++], L.a.bias);
@@ -1271,11 +1444,11 @@ int fused_tc_prepare(gnnb_model *m)
         for (int c = 0; c < h.nch; c++) {
             TLinear t;
             t.img = base + h.off[c]; t.bias = base + h.bias; t.K = h.K[c]; t.N = h.N;
-            t.KA = (h.K[c] + tc::ATOM_K - 1) / tc::ATOM_K;
+            t.KA = (h.K[c] + WATOM_K - 1) / WATOM_K;
             p.hl[j][c] = t;
         }
     }
-    plan->smem_bytes = 1024 + (size_t)4 * tc::PLANE_BYTES + RING_BYTES + CNT_BYTES + sizeof(Misc);
+    plan->smem_bytes = 1024 + (size_t)(1 + NPLANES) * tc::PLANE_BYTES + RING_BYTES + CNT_BYTES + sizeof(Misc);
     cudaError_t e = cudaFuncSetAttribute(fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)plan->smem_bytes);
     if (e != cudaSuccess) {
