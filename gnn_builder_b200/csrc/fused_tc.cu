@@ -90,7 +90,8 @@ static inline uint32_t bf16_rn_bits_host(float v)
 {
     uint32_t u;
     memcpy(&u, &v, 4);
-    return (u + 0x8000u) & 0xffff0000u;
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc00000u;   // NaN stays NaN
+    return (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u;      // round to nearest even
 }
 // bf16x2 weight image: per K atom (64 columns of K) the N x 128-byte rows of W as bf16 in the
 // canonical K-major SWIZZLE_128B layout, hi part (W rounded to bf16) followed by the mid part
@@ -137,9 +138,11 @@ constexpr int HEAD_G = 128;      // pooled graphs per head call (one 128-row MMA
 constexpr int MAX_HCHUNK = 4;    // 128-wide K chunks of the first head layer (head_in <= 512)
 constexpr int MAX_DIM = 128;
 constexpr int PLD = 520;         // row stride of the pending pooled vectors (>= 512 + 4)
-constexpr int NSLOT = 4;
-constexpr int SLOT_STRIDE = 16384;
-constexpr int RING_BYTES = NSLOT * SLOT_STRIDE;
+// Weight ring: 2^slot_log2 slots of slot_stride bytes (a unit = N x 128 bytes).  4 x 16 KB for
+// N <= 128; PNA (N <= 80, ~130 units per tile) runs 8 x 10 KB so that more bulk copies are in
+// flight: its per-tile weight stream is 1.3 MB and latency-, not bandwidth-, bound.
+constexpr int MAX_NSLOT = 8;
+constexpr int RING_BYTES_DEFAULT = 4 * 16384;
 constexpr int CNT_BYTES = TM * TM;
 constexpr int MAX_NODES_PER_GRAPH = TM;   // a graph must fit one tile
 #ifndef GNNB_TC_BF2
@@ -151,7 +154,10 @@ constexpr int WATOM_K = BF2 ? 64 : 32;          // K elements per 128-byte row o
 constexpr int WMMA_K = BF2 ? 16 : 8;            // K per MMA of the node transform
 constexpr uint32_t TMEM_COLS = 512;
 // A operand: bf16x2 = packed pairs, 64 columns per 128 K for each of hi / mid; 3xTF32 = 128 each
-constexpr uint32_t TM_D0 = 0, TM_AHI = 128, TM_ALO = BF2 ? 192 : 256, TM_D1 = 384;
+//   bf16x2: D0 [0,128) D1 [128,256) A_hi [384,448) A_mid [448,512); PNA lays its accumulators out
+//           in [0,384) itself (pna_layer_workers)
+//   3xTF32: D0 [0,128) A_hi [128,256) A_lo [256,384) D1 [384,512)
+constexpr uint32_t TM_D0 = 0, TM_AHI = BF2 ? 384 : 128, TM_ALO = BF2 ? 448 : 256, TM_D1 = BF2 ? 128 : 384;
 static_assert(!BF2 || GNNB_TC_WORKERS == 256, "bf16x2 packs 32-column chunks into 16 cells: 8 worker warps");
 static_assert(NWARPS == 8 || NWARPS == 16, "row passes: 8 worker warps (two 32-column blocks each) or 16 (one each)");
 constexpr int PASS_STEPS = 2;                // one step per 64-column half
@@ -171,6 +177,23 @@ struct TLinear {
     const float *img;   // weight image: per K atom [hi N x 128 B | lo N x 128 B]
     const float *bias;
     int K, N, KA;
+};
+
+// PNA conv layer (lib:1750-2157) on the tile, factorised as in model.cu (W_pre = [W_self | W_nbr],
+// the three degree scalers as per-row scalars in front of three accumulators):
+//   A_u = X.W_nbr^T, B_v = X.W_self^T + b_pre, S = X.W_post[:, :F]^T            (three GEMMs, one A operand)
+//   stats(v) = max / min / mean / std over in-neighbors u of (A_u + B_v)        (thread per row, shared memory)
+//   D_id += stats.W_id^T, D_amp = stats.W_amp^T, D_att = stats.W_att^T          (per group of 32 features)
+//   y = lin(S + D_id + amp_v D_amp + att_v D_att + b_post)
+constexpr int PNA_LDA = 100;    // row stride (floats) of the A_u rows in shared memory (F_in <= 96, + 4)
+constexpr int MAX_PNA_LAYERS = 4;
+constexpr int MAX_PNA_GROUPS = 3;     // feature groups of 32: F_in <= 96
+struct PnaLayer {
+    TLinear pa, pb, ps;                        // X -> A_u, X -> B_v (bias b_pre), X -> S
+    TLinear gid[MAX_PNA_GROUPS], gamp[MAX_PNA_GROUPS], gatt[MAX_PNA_GROUPS];
+    TLinear pl;                                // final linear (bias b_lin)
+    const float *b_post;
+    int ng, gw[MAX_PNA_GROUPS], fiP, foP;
 };
 
 struct TcParams {
@@ -194,10 +217,15 @@ struct TcParams {
     unsigned long long *timing;
     size_t img_copy_bytes;        // distance between the replicas of the weight images
     int img_copies;
+    int r0_bytes;                 // first shared-memory region: ADJ (32 KB) or PNA's A_u rows
+    int ring_bytes, slot_log2, slot_stride;   // weight ring geometry
+    float pna_delta;
+    PnaLayer pna[MAX_PNA_LAYERS];
 };
 
 struct Misc {
-    uint64_t bar_full[NSLOT], bar_empty[NSLOT];
+    uint64_t bar_full[MAX_NSLOT], bar_empty[MAX_NSLOT];
+    uint32_t slot_log2, slot_stride;
     // MMA <-> row-pass hand-off, per 64-column half h: ready[h] = the workers have written columns
     // [64 h, 64 h + 64) of the next MMA operand (one arrival per worker warp); done[h] = the MMAs
     // producing columns [64 h, +64) of the accumulator have completed (tcgen05.commit).
@@ -321,16 +349,17 @@ __device__ __forceinline__ void produce_linear(Misc &ms, uint32_t ring, uint32_t
                                                const TLinear &L, size_t copy_off, bool leader)
 {
     const uint32_t bytes = (uint32_t)L.N * tc::ROW_BYTES;
+    const uint32_t slot_log2 = ms.slot_log2, slot_stride = ms.slot_stride;
     const unsigned char *hi = reinterpret_cast<const unsigned char *>(L.img) + copy_off;
     const unsigned char *lo = hi + bytes;
     for (int part = 0; part < 2; part++) {
         const unsigned char *src = part ? lo : hi;
         for (int ka = 0; ka < L.KA; ka++) {
-            const uint32_t s = prod & (NSLOT - 1), use = prod / NSLOT;
+            const uint32_t s = prod & ((1u << slot_log2) - 1u), use = prod >> slot_log2;
             if (use > 0) tc::mbar_wait(&ms.bar_empty[s], (use - 1) & 1);
             if (leader) {
                 tc::mbar_expect_tx(&ms.bar_full[s], bytes);
-                tc::bulk_g2s_addr(ring + s * SLOT_STRIDE, src, bytes, &ms.bar_full[s]);
+                tc::bulk_g2s_addr(ring + s * slot_stride, src, bytes, &ms.bar_full[s]);
             }
             src += 2 * (size_t)bytes;
             prod++;
@@ -346,27 +375,33 @@ __device__ __forceinline__ void produce_linear(Misc &ms, uint32_t ring, uint32_t
 // packed TMEM columns per part), 4 k-steps of K = 16; hi atoms feed A_hi.W_hi and A_mid.W_hi, the
 // mid atoms A_hi.W_mid.  Only the k-steps that cover real K columns are issued (layer 0 of the
 // QM9 model has K = 11: one k-step).
+// wait_ready = false: the A operand is the one the previous GEMM used (several GEMMs off one row
+// pass); commit_done = false: more GEMMs of the same phase follow before the workers are told.
 __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &cons, uint32_t tmem_base,
                                            uint32_t dcol, const TLinear &L, bool accumulate,
-                                           uint32_t &ready_cnt)
+                                           uint32_t &ready_cnt, bool wait_ready = true,
+                                           bool commit_done = true)
 {
     const bool leader = tc::elect_one();
+    const uint32_t slot_log2 = ms.slot_log2, slot_stride = ms.slot_stride;
     const int KA = L.KA;
     const uint32_t idesc = tc::make_idesc_bf16(TM, L.N, 0);
     const uint32_t tmem_d = tmem_base + dcol, ahi = tmem_base + TM_AHI, amid = tmem_base + TM_ALO;
-    tc::mbar_wait(&ms.bar_ready[0], ready_cnt & 1);
-    tc::tc_fence_after();
+    if (wait_ready) {
+        tc::mbar_wait(&ms.bar_ready[0], ready_cnt & 1);
+        tc::tc_fence_after();
+    }
     for (int ka = 0; ka < KA; ka++) {   // hi atoms
-        if (ka == 1) {
+        if (ka == 1 && wait_ready) {
             tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1);
             tc::tc_fence_after();
         }
-        const uint32_t s = cons & (NSLOT - 1);
-        tc::mbar_wait(&ms.bar_full[s], (cons / NSLOT) & 1);
+        const uint32_t s = cons & ((1u << slot_log2) - 1u);
+        tc::mbar_wait(&ms.bar_full[s], (cons >> slot_log2) & 1);
         tc::tc_fence_after();
         const uint32_t col = (uint32_t)(ka * 32);
         const int nk = min(4, (L.K - ka * 64 + 15) >> 4);
-        const uint64_t bd = tc::make_desc(ring + s * SLOT_STRIDE);
+        const uint64_t bd = tc::make_desc(ring + s * slot_stride);
         const uint32_t first = (ka == 0 && !accumulate) ? 0u : 1u;
         if (leader) {
 #pragma unroll
@@ -382,18 +417,20 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &co
         }
         cons++;
     }
-    if (KA <= 1) {
-        tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1);
-        tc::tc_fence_after();
+    if (wait_ready) {
+        if (KA <= 1) {
+            tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1);
+            tc::tc_fence_after();
+        }
+        ready_cnt++;
     }
-    ready_cnt++;
     for (int ka = 0; ka < KA; ka++) {   // mid atoms
-        const uint32_t s = cons & (NSLOT - 1);
-        tc::mbar_wait(&ms.bar_full[s], (cons / NSLOT) & 1);
+        const uint32_t s = cons & ((1u << slot_log2) - 1u);
+        tc::mbar_wait(&ms.bar_full[s], (cons >> slot_log2) & 1);
         tc::tc_fence_after();
         const uint32_t col = (uint32_t)(ka * 32);
         const int nk = min(4, (L.K - ka * 64 + 15) >> 4);
-        const uint64_t bd = tc::make_desc(ring + s * SLOT_STRIDE);
+        const uint64_t bd = tc::make_desc(ring + s * slot_stride);
         if (leader) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; k4++)
@@ -403,7 +440,7 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &co
         }
         cons++;
     }
-    if (leader) {
+    if (leader && commit_done) {
         tc::mma_commit(&ms.bar_done[0]);
         tc::mma_commit(&ms.bar_done[1]);
     }
@@ -414,6 +451,7 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &co
                                            uint32_t &ready_cnt)
 {
     const bool leader = tc::elect_one();
+    const uint32_t slot_log2 = ms.slot_log2, slot_stride = ms.slot_stride;
     const int KA = L.KA;
     const int KA0 = KA < 2 ? KA : 2;   // atoms inside the first 64 columns
     const uint32_t idesc = tc::make_idesc_tf32(TM, L.N);
@@ -425,11 +463,11 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &co
             tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1);
             tc::tc_fence_after();
         }
-        const uint32_t s = cons & (NSLOT - 1);
-        tc::mbar_wait(&ms.bar_full[s], (cons / NSLOT) & 1);
+        const uint32_t s = cons & ((1u << slot_log2) - 1u);
+        tc::mbar_wait(&ms.bar_full[s], (cons >> slot_log2) & 1);
         tc::tc_fence_after();
         const uint32_t col = (uint32_t)(ka * tc::ATOM_K);
-        const uint64_t bd = tc::make_desc(ring + s * SLOT_STRIDE);
+        const uint64_t bd = tc::make_desc(ring + s * slot_stride);
         const uint32_t first = (ka == 0 && !accumulate) ? 0u : 1u;
         if (leader) {
 #pragma unroll
@@ -449,11 +487,11 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &co
     }
     ready_cnt++;
     for (int ka = 0; ka < KA; ka++) {   // lo atoms
-        const uint32_t s = cons & (NSLOT - 1);
-        tc::mbar_wait(&ms.bar_full[s], (cons / NSLOT) & 1);
+        const uint32_t s = cons & ((1u << slot_log2) - 1u);
+        tc::mbar_wait(&ms.bar_full[s], (cons >> slot_log2) & 1);
         tc::tc_fence_after();
         const uint32_t col = (uint32_t)(ka * tc::ATOM_K);
-        const uint64_t bd = tc::make_desc(ring + s * SLOT_STRIDE);
+        const uint64_t bd = tc::make_desc(ring + s * slot_stride);
         if (leader) {
 #pragma unroll
             for (int k8 = 0; k8 < tc::ATOM_K / tc::MMA_K; k8++)
@@ -508,10 +546,21 @@ __device__ __forceinline__ void agg_issue(Misc &ms, uint32_t tmem_d, uint32_t ad
 // ---------------------------------------------------------------------------------------
 // Thread-per-row helpers.  Warp w owns TMEM lanes [32 (w & 3), +32) and the column blocks
 // c0 = 32 (w >> 2), +64, ...
-// bf16 rounded to nearest (ties away from zero), as an fp32 bit pattern with a zero low half
-__device__ __forceinline__ uint32_t bf16_rn_bits(float v)
+// two fp32 values -> one packed bf16 pair (lo in the low half), round to nearest even, NaN kept:
+// one cvt.rn.bf16x2.f32.  (An integer add-and-mask rounding turns CUDA's canonical NaN 0x7fffffff
+// into -0.0: a zero-in-degree PNA row must stay NaN like the reference's, lib:702.)
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi)
 {
-    return (__float_as_uint(v) + 0x8000u) & 0xffff0000u;
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// hi / mid bf16 pairs of two fp32 values: v ~= hi + mid, both rounded to nearest
+__device__ __forceinline__ void split2_pair(float v0, float v1, uint32_t &hp, uint32_t &mp)
+{
+    hp = pack_bf16x2_rn(v0, v1);
+    const float r0 = v0 - __uint_as_float(hp << 16), r1 = v1 - __uint_as_float(hp & 0xffff0000u);
+    mp = pack_bf16x2_rn(r0, r1);
 }
 __device__ __forceinline__ void load_row8(const unsigned char *XP, int row, int c, float (&v)[8])
 {
@@ -534,18 +583,11 @@ __device__ __forceinline__ void store_row8(unsigned char *XP, int row, int c, co
 {
     const uint32_t off = tc::plane_chunk_offset(row, c);
     if (BF2) {
-        uint32_t hb[8], mb[8];
+        uint32_t hp[4], mp[4];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            hb[j] = bf16_rn_bits(v[j]);
-            mb[j] = bf16_rn_bits(v[j] - __uint_as_float(hb[j]));
-        }
-        *reinterpret_cast<uint4 *>(XP + off) =
-            make_uint4(__byte_perm(hb[0], hb[1], 0x7632), __byte_perm(hb[2], hb[3], 0x7632),
-                       __byte_perm(hb[4], hb[5], 0x7632), __byte_perm(hb[6], hb[7], 0x7632));
-        *reinterpret_cast<uint4 *>(XP + tc::PLANE_BYTES + off) =
-            make_uint4(__byte_perm(mb[0], mb[1], 0x7632), __byte_perm(mb[2], mb[3], 0x7632),
-                       __byte_perm(mb[4], mb[5], 0x7632), __byte_perm(mb[6], mb[7], 0x7632));
+        for (int j = 0; j < 4; j++) split2_pair(v[2 * j], v[2 * j + 1], hp[j], mp[j]);
+        *reinterpret_cast<uint4 *>(XP + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4 *>(XP + tc::PLANE_BYTES + off) = make_uint4(mp[0], mp[1], mp[2], mp[3]);
     } else {
         uint4 h, m, l;
         tc::split3_pack8(v, h, m, l);
@@ -564,11 +606,10 @@ __device__ __forceinline__ void split_store(uint32_t tmem_base, uint32_t lane_ba
         float h[W / 2], m[W / 2];
 #pragma unroll
         for (int j = 0; j < W / 2; j++) {
-            const uint32_t h0 = bf16_rn_bits(v[2 * j]), h1 = bf16_rn_bits(v[2 * j + 1]);
-            const uint32_t m0 = bf16_rn_bits(v[2 * j] - __uint_as_float(h0));
-            const uint32_t m1 = bf16_rn_bits(v[2 * j + 1] - __uint_as_float(h1));
-            h[j] = __uint_as_float(__byte_perm(h0, h1, 0x7632));
-            m[j] = __uint_as_float(__byte_perm(m0, m1, 0x7632));
+            uint32_t hp, mp;
+            split2_pair(v[2 * j], v[2 * j + 1], hp, mp);
+            h[j] = __uint_as_float(hp);
+            m[j] = __uint_as_float(mp);
         }
         tc::tmem_st(tmem_base + TM_AHI + lane_base + (uint32_t)(c0 >> 1), h);
         tc::tmem_st(tmem_base + TM_ALO + lane_base + (uint32_t)(c0 >> 1), m);
@@ -747,7 +788,7 @@ __device__ __forceinline__ void epilogue_tmem(Misc &ms, uint32_t &done_cnt, uint
 // skip: add the row's current plane content times skip_unscale (cpp:269-279).  Returns nonzero if
 // a non-finite value was written (chk accumulates t * 0, which is NaN exactly then).  Columns
 // [N, round_up(N, 32)) are zero filled.
-template <int ACT, bool SKIP, bool SCALE>
+template <int ACT, bool SKIP, bool SCALE, int HK = 2>
 __device__ __forceinline__ int epilogue_planes_t(Misc &ms, uint32_t &done_cnt, uint32_t tmem_d,
                                                  unsigned char *XP, int N,
                                                  const float *__restrict__ bias, int act,
@@ -755,7 +796,7 @@ __device__ __forceinline__ int epilogue_planes_t(Misc &ms, uint32_t &done_cnt, u
 {
     const int row = 32 * ((threadIdx.x >> 5) & 3) + (threadIdx.x & 31);
     float chk = 0.0f;
-    row_pass<2>(ms, done_cnt, tmem_d, (N + 31) & ~31, [&](int c0, uint32_t, const uint32_t (&r)[CH]) {
+    row_pass<HK>(ms, done_cnt, tmem_d, (N + 31) & ~31, [&](int c0, uint32_t, const uint32_t (&r)[CH]) {
 #pragma unroll
         for (int j8 = 0; j8 < CH / 8; j8++) {
             const int c = c0 + 8 * j8;
@@ -866,6 +907,285 @@ __device__ __forceinline__ void epilogue_global(uint32_t tmem_d, int N, const fl
 // barrier over the 256 worker threads (the producer warp never joins it)
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(NTHREADS) : "memory"); }
 
+#if GNNB_TC_BF2
+// ---------------------------------------------------------------------------------------
+// PNA (lib:1750-2157) inside the fused kernel.  Tensor memory of a PNA layer (foP = F_out rounded
+// to 16, <= 96): D_id [0, foP) | D_amp [foP, 2 foP) | D_att [2 foP, 3 foP) (the A_u accumulator of
+// the pre-transform aliases D_att until its rows have been copied to shared memory) | B_v, later the
+// final linear's accumulator, at [3 foP, ...) | A operand at [384, 512).
+__device__ __forceinline__ uint32_t pna_col_att(const PnaLayer &P) { return 2u * (uint32_t)P.foP; }
+__device__ __forceinline__ uint32_t pna_col_b(const PnaLayer &P) { return 3u * (uint32_t)P.foP; }
+
+// The in-neighbors of a row, extracted ONCE per tile from the u8 multiplicity counters into
+// registers: up to 8 entries (source | multiplicity << 8, 16 bits each, ascending source order =
+// deterministic).  Walking the counters inside every statistics pass instead made a warp execute
+// the gather body once per (word, byte) position ANY of its lanes had a neighbor at (~27 times per
+// pass, ncu: 3.2 k instructions per step); with the lists it runs max-degree-in-warp times (~4).
+// n = 9 marks a row with more than 8 distinct in-neighbors: those walk the counters as before.
+struct PnaNbr {
+    unsigned long long lo, hi;
+    int n;
+};
+__device__ __forceinline__ void pna_build_nbr(const uint32_t *CNT, int row, int g_r0, int g_r1, PnaNbr &nb)
+{
+    nb.lo = 0ull; nb.hi = 0ull; nb.n = 0;
+    const uint32_t *cw = CNT + row * (TM / 4);
+    for (int w = g_r0 >> 2; w < (g_r1 + 3) >> 2; w++) {
+        const uint32_t word = cw[w];
+        if (word == 0u) continue;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t m = (word >> (8 * b)) & 0xffu;
+            if (m) {
+                const unsigned long long e = (unsigned long long)((uint32_t)(4 * w + b) | (m << 8));
+                if (nb.n < 4) nb.lo |= e << (16 * nb.n);
+                else if (nb.n < 8) nb.hi |= e << (16 * (nb.n - 4));
+                nb.n = nb.n < 9 ? nb.n + 1 : 9;
+            }
+        }
+    }
+}
+template <class F>
+__device__ __forceinline__ void pna_for_each_neighbor(const PnaNbr &nb, const uint32_t *CNT, int row,
+                                                      int g_r0, int g_r1, F &&f)
+{
+    if (nb.n <= 8) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (i < nb.n) {
+                const uint32_t e = (uint32_t)((i < 4 ? nb.lo : nb.hi) >> (16 * (i & 3))) & 0xffffu;
+                f((int)(e & 0xffu), (int)(e >> 8));
+            }
+        }
+        return;
+    }
+    const uint32_t *cw = CNT + row * (TM / 4);
+    for (int w = g_r0 >> 2; w < (g_r1 + 3) >> 2; w++) {
+        uint32_t word = cw[w];
+        if (word == 0u) continue;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int m = (int)((word >> (8 * b)) & 0xffu);
+            if (m) f(4 * w + b, m);
+        }
+    }
+}
+
+// One PNA conv layer, worker side.  Thread (row, hh): row = TMEM lane, hh = warp >> 2 picks the
+// column block inside a 64-column half like every other row pass.
+__device__ __forceinline__ int pna_layer_workers(const TcParams &p, Misc &ms, int l, uint32_t tmem_base,
+                                                 unsigned char *XP, float *AROWS, const uint32_t *CNT,
+                                                 uint32_t &done_cnt, int my_deg, const PnaNbr &nb, int g_r0,
+                                                 int g_r1, bool last_layer, bool do_skip, long long &t_prev)
+{
+    // GNNB_FUSED_TIMING: thread 0's cycles per phase -> timing[8 ..]
+#define PNA_PHASE(idx)                                                              \
+    if (p.timing != nullptr && threadIdx.x == 0) {                                  \
+        const long long t_now = clock64();                                          \
+        atomicAdd(p.timing + (idx), (unsigned long long)(t_now - t_prev));          \
+        t_prev = t_now;                                                             \
+    }
+    const PnaLayer &P = p.pna[l];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = 32 * (warp & 3) + lane, hh = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    const int fi = p.fi[l], kp = (fi + 31) & ~31;
+    // ---- phase A: X rows -> A operand; the issuer runs the three GEMMs off it
+    cvt_self(ms, tmem_base, XP, kp);
+    PNA_PHASE(8)
+    wait_done_both(ms, done_cnt);
+    PNA_PHASE(9)
+    // ---- phase B: A_u rows (fp32) -> shared memory, where every row's thread can gather them
+    for (int c = 16 * hh; c < P.fiP; c += 32) {
+        uint32_t r[16];
+        tc::tmem_ld_nowait(tmem_base + pna_col_att(P) + lane_base + (uint32_t)c, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 4; j4++)
+            *reinterpret_cast<uint4 *>(AROWS + row * PNA_LDA + c + 4 * j4) =
+                make_uint4(r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
+    }
+    tc::tc_fence_before();
+    worker_sync();
+    tc::tc_fence_after();
+    PNA_PHASE(10)
+    // ---- phase C: per group of 32 features, per sub-block h of 16: (max, min) by the hh = 0 thread
+    // of the row, (mean, std) by the hh = 1 thread, over the row's in-neighbors; the 32 results are
+    // A-operand columns [64 h + 32 hh, +32) of the group's GEMMs (the weight images are permuted to
+    // that order: K' = 64 h + 16 q + j  <->  statistic q of feature 32 g + 16 h + j)
+    const float degf = (float)my_deg;
+    for (int g = 0; g < P.ng; g++) {
+        const int gw = P.gw[g];
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const int f0 = 32 * g + 16 * h;
+            if (16 * h < gw) {
+                float bv[16], s0[16], s1[16];
+                {   // B_v + b_pre of this row (tensor memory) for the 16 features
+                    uint32_t r[16];
+                    tc::tmem_ld_nowait(tmem_base + pna_col_b(P) + lane_base + (uint32_t)f0, r);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; j++) bv[j] = __uint_as_float(r[j]) + __ldg(P.pb.bias + f0 + j);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j++) { s0[j] = 0.0f; s1[j] = 0.0f; }
+                if (hh == 0) {   // max / min with the reference's first-sample rule (lib:748-795)
+                    bool first = true;
+                    pna_for_each_neighbor(nb, CNT, row, g_r0, g_r1, [&](int u, int) {
+                        const float *au = AROWS + u * PNA_LDA + f0;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; j4++) {
+                            const float4 a = *reinterpret_cast<const float4 *>(au + 4 * j4);
+                            const float t[4] = {a.x + bv[4 * j4], a.y + bv[4 * j4 + 1], a.z + bv[4 * j4 + 2],
+                                                a.w + bv[4 * j4 + 3]};
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                s0[4 * j4 + j] = (first || t[j] > s0[4 * j4 + j]) ? t[j] : s0[4 * j4 + j];
+                                s1[4 * j4 + j] = (first || t[j] < s1[4 * j4 + j]) ? t[j] : s1[4 * j4 + j];
+                            }
+                        }
+                        first = false;
+                    });
+                } else {         // mean, then the population variance around it; std = sqrt(var + 1e-5)
+                    pna_for_each_neighbor(nb, CNT, row, g_r0, g_r1, [&](int u, int m) {
+                        const float *au = AROWS + u * PNA_LDA + f0;
+                        const float mf = (float)m;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; j4++) {
+                            const float4 a = *reinterpret_cast<const float4 *>(au + 4 * j4);
+                            s0[4 * j4] = fmaf(mf, a.x + bv[4 * j4], s0[4 * j4]);
+                            s0[4 * j4 + 1] = fmaf(mf, a.y + bv[4 * j4 + 1], s0[4 * j4 + 1]);
+                            s0[4 * j4 + 2] = fmaf(mf, a.z + bv[4 * j4 + 2], s0[4 * j4 + 2]);
+                            s0[4 * j4 + 3] = fmaf(mf, a.w + bv[4 * j4 + 3], s0[4 * j4 + 3]);
+                        }
+                    });
+                    if (my_deg > 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) s0[j] = s0[j] / degf;      // lib:661
+                    }
+                    pna_for_each_neighbor(nb, CNT, row, g_r0, g_r1, [&](int u, int m) {
+                        const float *au = AROWS + u * PNA_LDA + f0;
+                        const float mf = (float)m;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; j4++) {
+                            const float4 a = *reinterpret_cast<const float4 *>(au + 4 * j4);
+                            const float t[4] = {a.x + bv[4 * j4], a.y + bv[4 * j4 + 1], a.z + bv[4 * j4 + 2],
+                                                a.w + bv[4 * j4 + 3]};
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const float d = t[j] - s0[4 * j4 + j];
+                                s1[4 * j4 + j] = fmaf(mf * d, d, s1[4 * j4 + j]);
+                            }
+                        }
+                    });
+#pragma unroll
+                    for (int j = 0; j < 16; j++)     // in-degree 0: 0 / 0 = NaN like the reference (lib:702)
+                        s1[j] = sqrtf(s1[j] / degf + 1e-5f);
+                }
+                PNA_PHASE(11)
+                // the previous group's GEMMs must have finished reading the A operand
+                if (g > 0 && h == 0) wait_done_both(ms, done_cnt);
+                PNA_PHASE(12)
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 16; j++) { v[j] = s0[j]; v[16 + j] = s1[j]; }
+                split_store(tmem_base, lane_base, 64 * h + 32 * hh, v);
+                tc::tmem_st_wait();
+            } else if (g > 0 && h == 0) {
+                wait_done_both(ms, done_cnt);
+            }
+            handoff_half(ms, h);
+            PNA_PHASE(13)
+        }
+    }
+    wait_done_both(ms, done_cnt);
+    PNA_PHASE(12)
+    // ---- phase D: S + D_id + amp_v D_amp + att_v D_att + b_post -> A operand of the final linear
+    {
+        const float lg = logf((float)(my_deg < 1 ? 1 : my_deg) + 1.0f);      // lib:1973-1984
+        const float amp = lg / p.pna_delta, att = p.pna_delta / lg;
+        const int fo = p.fo[l], npad = (fo + 31) & ~31;
+#pragma unroll 1
+        for (int st = 0; st < PASS_STEPS; st++) {
+            const int c0 = 64 * st + 32 * hh;
+            if (c0 < npad) {
+                float v[32];
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int c = c0 + 16 * q;
+                    if (c < fo) {   // fo % 16 == 0
+                        uint32_t a[16], b[16], d[16];
+                        tc::tmem_ld_nowait(tmem_base + lane_base + (uint32_t)c, a);
+                        tc::tmem_ld_nowait(tmem_base + (uint32_t)P.foP + lane_base + (uint32_t)c, b);
+                        tc::tmem_ld_nowait(tmem_base + pna_col_att(P) + lane_base + (uint32_t)c, d);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++)
+                            v[16 * q + j] = fmaf(att, __uint_as_float(d[j]),
+                                                 fmaf(amp, __uint_as_float(b[j]),
+                                                      __uint_as_float(a[j]) + __ldg(P.b_post + c + j)));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[16 * q + j] = 0.0f;
+                    }
+                }
+                split_store(tmem_base, lane_base, c0, v);
+            }
+            tc::tmem_st_wait();
+            handoff_half(ms, st);
+        }
+    }
+    PNA_PHASE(14)
+    // ---- phase E: final linear's accumulator -> (+bias, skip, activation) -> next layer / pooling
+    const uint32_t tmem_d = tmem_base + pna_col_b(P);
+    if (last_layer) {
+        epilogue_rows(ms, done_cnt, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act);
+        return 0;
+    }
+    // no hand-off: the next layer starts with its own row pass over the planes (generic-proxy
+    // reads of the columns this very thread wrote)
+    if (p.gnn_act == GNNB_ACT_RELU)
+        return do_skip ? epilogue_planes_t<1, true, false, 0>(ms, done_cnt, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act, 1.0f, 1.0f)
+                       : epilogue_planes_t<1, false, false, 0>(ms, done_cnt, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act, 1.0f, 1.0f);
+    return do_skip ? epilogue_planes_t<2, true, false, 0>(ms, done_cnt, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act, 1.0f, 1.0f)
+                   : epilogue_planes_t<2, false, false, 0>(ms, done_cnt, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act, 1.0f, 1.0f);
+#undef PNA_PHASE
+}
+
+// the same layer on the MMA-issuing warp
+__device__ __forceinline__ void pna_layer_issue(const TcParams &p, Misc &ms, int l, uint32_t ring,
+                                                uint32_t &cons, uint32_t tmem_base, uint32_t &ready_cnt)
+{
+    const PnaLayer &P = p.pna[l];
+    const uint32_t c_att = 2u * (uint32_t)P.foP, c_b = 3u * (uint32_t)P.foP;
+    gemm_issue(ms, ring, cons, tmem_base, c_att, P.pa, false, ready_cnt, true, false);
+    gemm_issue(ms, ring, cons, tmem_base, c_b, P.pb, false, ready_cnt, false, false);
+    gemm_issue(ms, ring, cons, tmem_base, 0u, P.ps, false, ready_cnt, false, true);
+    for (int g = 0; g < P.ng; g++) {
+        gemm_issue(ms, ring, cons, tmem_base, 0u, P.gid[g], true, ready_cnt, true, false);
+        gemm_issue(ms, ring, cons, tmem_base, (uint32_t)P.foP, P.gamp[g], g > 0, ready_cnt, false, false);
+        gemm_issue(ms, ring, cons, tmem_base, c_att, P.gatt[g], g > 0, ready_cnt, false, true);
+    }
+    gemm_issue(ms, ring, cons, tmem_base, c_b, P.pl, false, ready_cnt);
+}
+// ... and the weight units it consumes, in the same order (producer warp)
+__device__ __forceinline__ void pna_layer_produce(const TcParams &p, Misc &ms, int l, uint32_t ring,
+                                                  uint32_t &prod, size_t copy_off, bool leader)
+{
+    const PnaLayer &P = p.pna[l];
+    produce_linear(ms, ring, prod, P.pa, copy_off, leader);
+    produce_linear(ms, ring, prod, P.pb, copy_off, leader);
+    produce_linear(ms, ring, prod, P.ps, copy_off, leader);
+    for (int g = 0; g < P.ng; g++) {
+        produce_linear(ms, ring, prod, P.gid[g], copy_off, leader);
+        produce_linear(ms, ring, prod, P.gamp[g], copy_off, leader);
+        produce_linear(ms, ring, prod, P.gatt[g], copy_off, leader);
+    }
+    produce_linear(ms, ring, prod, P.pl, copy_off, leader);
+}
+#endif   // GNNB_TC_BF2
+
 // MLP head (cpp:454-530) for up to 128 pending graphs: the pooled vectors [128][head_in] go from the
 // per-CTA pending buffer (L2) to tensor memory in 128-wide K chunks that accumulate into the same
 // accumulator; later head layers take their A operand from the previous epilogue like GIN's hidden
@@ -939,11 +1259,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char *ADJ = base;
-    unsigned char *XP = ADJ + tc::PLANE_BYTES;
+    unsigned char *ADJ = base;                   // (PNA: the A_u rows, fp32 [128][PNA_LDA])
+    unsigned char *XP = ADJ + p.r0_bytes;
     unsigned char *RING = XP + NPLANES * tc::PLANE_BYTES;
-    uint32_t *CNT = reinterpret_cast<uint32_t *>(RING + RING_BYTES);
-    Misc &ms = *reinterpret_cast<Misc *>(RING + RING_BYTES + CNT_BYTES);
+    uint32_t *CNT = reinterpret_cast<uint32_t *>(RING + p.ring_bytes);
+    Misc &ms = *reinterpret_cast<Misc *>(RING + p.ring_bytes + CNT_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long t_prev = clock64();
 #define GNNB_PHASE(idx)                                                             \
@@ -955,7 +1275,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
 
     if (warp == 0) tc::tmem_alloc(&ms.tmem_slot, TMEM_COLS);
     if (tid == 0) {
-        for (int i = 0; i < NSLOT; i++) {
+        ms.slot_log2 = (uint32_t)p.slot_log2;
+        ms.slot_stride = (uint32_t)p.slot_stride;
+        for (int i = 0; i < MAX_NSLOT; i++) {
             tc::mbar_init(&ms.bar_full[i], 1);
             tc::mbar_init(&ms.bar_empty[i], 1);
         }
@@ -975,8 +1297,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, ms.tmem_slot, 0);
     const uint32_t adj_addr = __shfl_sync(0xffffffffu, tc::smem_u32(ADJ), 0);
-    const uint32_t xp_addr = adj_addr + tc::PLANE_BYTES;
-    const uint32_t ring_addr = adj_addr + (1 + NPLANES) * tc::PLANE_BYTES;
+    const uint32_t xp_addr = adj_addr + (uint32_t)p.r0_bytes;
+    const uint32_t ring_addr = xp_addr + NPLANES * tc::PLANE_BYTES;
     uint32_t done_cnt = 0, cons = 0, dw = 0;   // dw: accumulator buffer of the latest new MMA phase
     const int n_tiles = __shfl_sync(0xffffffffu, __ldg(p.n_tiles_ptr), 0);
 
@@ -996,6 +1318,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             const int64_t trows = __ldg(p.node_ptr + tg1) - __ldg(p.node_ptr + tg0);
             if (tng <= 0 || trows > TM || tng > TM) continue;
             for (int l = 0; l < p.num_layers; l++) {
+#if GNNB_TC_BF2
+                if (p.conv_type == GNNB_CONV_PNA) {
+                    pna_layer_produce(p, ms, l, ring_addr, prod, copy_off, leader);
+                    continue;
+                }
+#endif
                 produce_linear(ms, ring_addr, prod, p.l0[l], copy_off, leader);
                 if (p.conv_type != GNNB_CONV_GCN) produce_linear(ms, ring_addr, prod, p.l1[l], copy_off, leader);
             }
@@ -1024,6 +1352,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             const int64_t trows = __ldg(p.node_ptr + tg1) - __ldg(p.node_ptr + tg0);
             if (tng <= 0 || trows > TM || tng > TM) continue;
             for (int l = 0; l < p.num_layers; l++) {
+#if GNNB_TC_BF2
+                if (p.conv_type == GNNB_CONV_PNA) {
+                    pna_layer_issue(p, ms, l, ring_addr, cons, tmem_base, ready_cnt);
+                    continue;
+                }
+#endif
                 dw ^= 1u;
                 agg_issue(ms, tmem_base + dcol_of(dw), adj_addr, xp_addr, (p.fi[l] + 31) & ~31, (int)trows,
                           ready_cnt);
@@ -1126,7 +1460,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             worker_sync();
             GNNB_PHASE(0)
             // ---------------------------------------------------------------- ADJ, planes
-            for (int idx = tid; idx < TM * 8; idx += NTHREADS) {   // 16 sources per iteration
+            // (PNA gathers over the multiplicity counters themselves: no ADJ, counters kept)
+            for (int idx = tid; idx < (conv == GNNB_CONV_PNA ? 0 : TM * 8); idx += NTHREADS) {   // 16 sources per iteration
                 const int d = idx >> 3, s0 = (idx & 7) * 16;
                 uint4 *cp = reinterpret_cast<uint4 *>(CNT) + idx;
                 const uint4 cw = *cp;
@@ -1182,9 +1517,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
                     store_row8(XP, r_own, c, o);
                 }
             }
-            tc::fence_async_smem();
-            handoff_both(ms);    // ADJ + planes are ready: layer 0's aggregation may start
-            dw ^= 1u;
+            if (conv == GNNB_CONV_PNA) {
+                bad_values = 0;      // PNA never mixes the graphs of a tile: NaN / Inf stay in their graph
+                worker_sync();       // layer 0's row pass reads plane chunks other threads staged
+            } else {
+                tc::fence_async_smem();
+                handoff_both(ms);    // ADJ + planes are ready: layer 0's aggregation may start
+                dw ^= 1u;
+            }
             GNNB_PHASE(1)
         }
         // second half of the next tile's geometry (the bounds have arrived by now), and a hint to
@@ -1205,6 +1545,33 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
         const float my_dinv = 1.0f / sqrtf(1.0f + (float)my_deg);
 
         // -------------------------------------------------------------------- conv layers
+#if GNNB_TC_BF2
+        if (conv == GNNB_CONV_PNA) {
+            // the row range of this thread's graph (rows beyond the tile's graphs: empty range)
+            const int my_row = 32 * (warp & 3) + lane;
+            int g_r0 = 0, g_r1 = 0;
+            if (my_row < rows) {
+                int lo = 0, hi = ng;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (ms.grow[mid] <= my_row) lo = mid; else hi = mid;
+                }
+                g_r0 = ms.grow[lo];
+                g_r1 = ms.grow[lo + 1];
+            }
+            PnaNbr nb;
+            pna_build_nbr(CNT, my_row, g_r0, g_r1, nb);
+            for (int l = 0; l < p.num_layers; l++) {
+                const bool last_layer = l == p.num_layers - 1;
+                pna_layer_workers(p, ms, l, tmem_base, XP, reinterpret_cast<float *>(ADJ), CNT, done_cnt,
+                                  my_deg, nb, g_r0, g_r1, last_layer, p.skip && l != 0 && !last_layer, t_prev);
+                GNNB_PHASE(7)
+            }
+            worker_sync();           // pooling reads the other threads' rows; the counters are dead
+            for (int i = tid; i < CNT_BYTES / 16; i += NTHREADS)
+                reinterpret_cast<uint4 *>(CNT)[i] = make_uint4(0u, 0u, 0u, 0u);
+        } else
+#endif
         for (int l = 0; l < p.num_layers; l++) {
             const int fi = p.fi[l];
             // A-operand columns the row passes define; the MMAs read whole k-steps of real K only
@@ -1324,8 +1691,9 @@ int fused_tc_prepare(gnnb_model *m)
     m->fused_tc = nullptr;
     const gnnb_model_desc &d = m->d;
     if (getenv("GNNB_DISABLE_TC") != nullptr) return GNNB_OK;
+    const bool is_pna = d.conv_type == GNNB_CONV_PNA;
     const bool conv_ok = d.conv_type == GNNB_CONV_GCN || d.conv_type == GNNB_CONV_GIN ||
-                         d.conv_type == GNNB_CONV_SAGE;
+                         d.conv_type == GNNB_CONV_SAGE || (is_pna && BF2);
     const int head_in = m->emb_dim() * d.num_pools;
     bool dims_ok = d.num_layers >= 1 && d.num_layers <= MAX_LAYERS && d.mlp_num_linear >= 1 &&
                    d.mlp_num_linear <= MAX_HEAD && d.in_dim <= MAX_DIM && d.mlp_hidden <= MAX_DIM &&
@@ -1334,6 +1702,12 @@ int fused_tc_prepare(gnnb_model *m)
         int fi, fo;
         m->layer_dims(k, &fi, &fo);
         dims_ok = fo % 16 == 0 && fo >= 16 && fo <= MAX_DIM && fi <= MAX_DIM;
+        if (is_pna) {   // tensor-memory budget of a PNA layer: 3 foP + max(fiP, foP) <= 384 columns
+            const int fiP = (fi + 15) / 16 * 16;
+            // (the A_u accumulator of the pre-transform aliases D_att: F_in may not exceed F_out)
+            dims_ok = dims_ok && fo <= 96 && fiP <= fo && 4 * fo <= 384 &&
+                      d.num_layers <= MAX_PNA_LAYERS && d.pna_delta > 0.0f;
+        }
     }
     if (!conv_ok || !dims_ok) return GNNB_OK;
 
@@ -1354,6 +1728,13 @@ int fused_tc_prepare(gnnb_model *m)
     };
     struct Pending { size_t off; int K, N; };
     std::vector<Pending> pend;
+    struct PnaPending {
+        struct Lin { size_t off; int K, N; size_t bias; bool has_bias; };
+        Lin pa, pb, ps, gid[MAX_PNA_GROUPS], gamp[MAX_PNA_GROUPS], gatt[MAX_PNA_GROUPS], pl;
+        size_t b_post;
+        int ng, gw[MAX_PNA_GROUPS], fiP, foP;
+    };
+    std::vector<PnaPending> pna_pend;
     size_t idx = 2 * (size_t)d.mlp_num_linear;
     for (int k = 0; k < d.num_layers; k++) {
         int fi, fo;
@@ -1368,12 +1749,64 @@ int fused_tc_prepare(gnnb_model *m)
             pend.push_back({img.size(), fo, fo});
             build_image(m->params[idx + 2].host.data(), fo, fo, fo, fo, 0, img);
             idx += 4;
-        } else {                                    // SAGE: [lin_l.weight, lin_l.bias, lin_r.weight]
+        } else if (d.conv_type == GNNB_CONV_SAGE) { // [lin_l.weight, lin_l.bias, lin_r.weight]
             pend.push_back({img.size(), fi, fo});
             build_image(m->params[idx].host.data(), fo, fo, fi, fi, 0, img);
             pend.push_back({img.size(), fi, fo});
             build_image(m->params[idx + 2].host.data(), fo, fo, fi, fi, 0, img);
             idx += 3;
+        } else {
+            // PNA: [pre_w (fi x 2fi), pre_b, post_w (fo x 13fi), post_b, lin_w (fo x fo), lin_b]
+            const float *pre_w = m->params[idx].host.data(), *pre_b = m->params[idx + 1].host.data();
+            const float *post_w = m->params[idx + 2].host.data(), *post_b = m->params[idx + 3].host.data();
+            const float *lin_w = m->params[idx + 4].host.data(), *lin_b = m->params[idx + 5].host.data();
+            const int fiP = (fi + 15) / 16 * 16;
+            PnaPending q{};
+            q.fiP = fiP; q.foP = fo;
+            auto add = [&](const float *W, int N, int n_valid, int K, int ld, int col0) {
+                PnaPending::Lin l{img.size(), K, N, 0, false};
+                build_image(W, N, n_valid, K, ld, col0, img);
+                return l;
+            };
+            auto add_bias = [&](PnaPending::Lin &l, const float *b, int n, int n_pad) {
+                l.bias = img.size();
+                l.has_bias = true;
+                img.resize(img.size() + n_pad, 0.0f);
+                for (int i = 0; i < n; i++) img[l.bias + i] = b[i];
+            };
+            q.pa = add(pre_w, fiP, fi, fi, 2 * fi, fi);        // W_nbr  = W_pre[:, fi:2fi]
+            q.pb = add(pre_w, fiP, fi, fi, 2 * fi, 0);         // W_self = W_pre[:, 0:fi]
+            add_bias(q.pb, pre_b, fi, fiP);
+            q.ps = add(post_w, fo, fo, fi, 13 * fi, 0);        // self block of post_nn
+            q.ng = (fi + 31) / 32;
+            for (int g = 0; g < q.ng; g++) {
+                const int gw = std::min(32, (fi - 32 * g + 15) / 16 * 16);
+                q.gw[g] = gw;
+                const int Kg = 4 * gw;
+                // K' = 64 h + 16 q + j  <->  statistic q of feature 32 g + 16 h + j (lib:1857-1875: the
+                // 12F block is [identity | amplification | attenuation] x [max | min | mean | std] x F)
+                for (int sc = 0; sc < 3; sc++) {
+                    std::vector<float> Wg((size_t)fo * Kg, 0.0f);
+                    for (int o = 0; o < fo; o++)
+                        for (int h = 0; h < gw / 16; h++)
+                            for (int st = 0; st < 4; st++)
+                                for (int j = 0; j < 16; j++) {
+                                    const int f = 32 * g + 16 * h + j;
+                                    if (f < fi)
+                                        Wg[(size_t)o * Kg + 64 * h + 16 * st + j] =
+                                            post_w[(size_t)o * 13 * fi + fi + (size_t)(sc * 4 + st) * fi + f];
+                                }
+                    PnaPending::Lin l = add(Wg.data(), fo, fo, Kg, Kg, 0);
+                    (sc == 0 ? q.gid : sc == 1 ? q.gamp : q.gatt)[g] = l;
+                }
+            }
+            q.pl = add(lin_w, fo, fo, fo, fo, 0);
+            add_bias(q.pl, lin_b, fo, fo);
+            q.b_post = img.size();
+            img.resize(img.size() + fo, 0.0f);
+            for (int i = 0; i < fo; i++) img[q.b_post + i] = post_b[i];
+            pna_pend.push_back(q);
+            idx += 6;
         }
     }
     // MLP head: N padded to a multiple of 16, K cut into 128-wide chunks, bias zero padded
@@ -1433,10 +1866,31 @@ int fused_tc_prepare(gnnb_model *m)
             t.KA = (q.K + WATOM_K - 1) / WATOM_K;
             return t;
         };
+        if (is_pna) {
+            const PnaPending &q = pna_pend[k];
+            auto mkp = [&](const PnaPending::Lin &l) {
+                TLinear t;
+                t.img = base + l.off; t.bias = l.has_bias ? base + l.bias : nullptr; t.K = l.K; t.N = l.N;
+                t.KA = (l.K + WATOM_K - 1) / WATOM_K;
+                return t;
+            };
+            PnaLayer &P = p.pna[k];
+            P.pa = mkp(q.pa); P.pb = mkp(q.pb); P.ps = mkp(q.ps); P.pl = mkp(q.pl);
+            for (int g = 0; g < q.ng; g++) {
+                P.gid[g] = mkp(q.gid[g]); P.gamp[g] = mkp(q.gamp[g]); P.gatt[g] = mkp(q.gatt[g]);
+                P.gw[g] = q.gw[g];
+            }
+            P.b_post = base + q.b_post;
+            P.ng = q.ng; P.fiP = q.fiP; P.foP = q.foP;
+            continue;
+        }
         p.l0[k] = mk(pend[pi++], L.a.bias);
         if (d.conv_type == GNNB_CONV_GIN) p.l1[k] = mk(pend[pi++], L.b.bias);
         else if (d.conv_type == GNNB_CONV_SAGE) p.l1[k] = mk(pend[pi++], nullptr);
     }
+    p.pna_delta = d.pna_delta;
+    // first shared-memory region: the bf16 ADJ tile, or PNA's fp32 A_u rows [128][PNA_LDA]
+    p.r0_bytes = is_pna ? (int)((TM * PNA_LDA * sizeof(float) + 1023) / 1024 * 1024) : tc::PLANE_BYTES;
     for (int j = 0; j < d.mlp_num_linear; j++) {
         const HeadPending &h = hpend[j];
         p.hchunks[j] = h.nch;
@@ -1448,7 +1902,17 @@ int fused_tc_prepare(gnnb_model *m)
             p.hl[j][c] = t;
         }
     }
-    plan->smem_bytes = 1024 + (size_t)(1 + NPLANES) * tc::PLANE_BYTES + RING_BYTES + CNT_BYTES + sizeof(Misc);
+    // weight ring: 4 x 16 KB, or for PNA with N <= 80 (10 KB units, ~130 of them per tile) 8 x 10 KB
+    p.slot_log2 = 2; p.slot_stride = 16384;
+    if (is_pna && m->emb_dim() <= 80 && d.hidden_dim <= 80) { p.slot_log2 = 3; p.slot_stride = 80 * tc::ROW_BYTES; }
+    if (const char *e = getenv("GNNB_TC_RING_SLOTS_LOG2")) {   // tuning hook (2 or 3)
+        const int v = atoi(e);
+        if (v == 2 || (v == 3 && p.slot_stride <= 10240)) p.slot_log2 = v;
+    }
+    p.ring_bytes = (p.slot_stride << p.slot_log2);
+    plan->smem_bytes = 1024 + (size_t)p.r0_bytes + (size_t)NPLANES * tc::PLANE_BYTES + p.ring_bytes + CNT_BYTES +
+                       sizeof(Misc);
+    if (plan->smem_bytes > 232448) { delete plan; return GNNB_OK; }   // (cannot happen with the limits above)
     cudaError_t e = cudaFuncSetAttribute(fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)plan->smem_bytes);
     if (e != cudaSuccess) {
@@ -1525,13 +1989,14 @@ int fused_tc_status(gnnb_model *m, int *status)
         GNNB_CUDA(cudaMemcpy(t, plan->timing.ptr, sizeof(t), cudaMemcpyDeviceToHost));
         GNNB_CUDA(cudaMemset(plan->timing.ptr, 0, sizeof(t)));
         // (the row passes include their waits for the MMAs of the phase they read)
-        const char *names[8] = {"stage", "adj+planes", "agg->A pass", "hidden/self pass", "pool", "head",
-                                "-", "output pass"};
+        const char *names[16] = {"stage", "adj+planes", "agg->A pass", "hidden/self pass", "pool", "head",
+                                 "-", "output pass", "pna:x->A", "pna:wait pre", "pna:A_u->smem",
+                                 "pna:stats", "pna:wait MMA", "pna:store+handoff", "pna:combine", "-"};
         unsigned long long tot = 0;
-        for (int i = 0; i < 8; i++) tot += t[i];
+        for (int i = 0; i < 16; i++) tot += t[i];
         fprintf(stderr, "[gnnb fused-tc phases]");
-        for (int i = 0; i < 8; i++)
-            if (i != 6)
+        for (int i = 0; i < 16; i++)
+            if (t[i])
                 fprintf(stderr, " %s %.1f%%", names[i], tot ? 100.0 * (double)t[i] / (double)tot : 0.0);
         fprintf(stderr, " (total %.3g cycles over all CTAs)\n", (double)tot);
 #ifdef GNNB_TC_SUBTIMING

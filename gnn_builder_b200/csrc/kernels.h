@@ -185,7 +185,7 @@ int launch_transpose_weight(const float *W, float *Wt, int out_size, int in_size
 // pooled[g][p*F + f] for pools[p] over rows node_ptr[g]..node_ptr[g+1]
 int launch_pool(const float *x, int ldx, int F, const int64_t *node_ptr, int64_t node_base,
                 int n_graphs, int64_t total_nodes, const int *pools, int num_pools, float *pooled,
-                DeviceBuf &tmp, cudaStream_t s, int *launches);
+                DeviceBuf &tmp, cudaStream_t s, int *launches, bool single_pass = false);
 int launch_activation(int act, const float *x, float *y, size_t n, cudaStream_t s, int *launches);
 
 }  // namespace gnnb

@@ -602,7 +602,7 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
     {
         ProfScope ps(m->prof, PROF_POOL, s);
         GNNB_TRY(launch_pool(cur, cur_ld, emb, node_ptr, node_base, n_graphs, T64, d.pools,
-                             d.num_pools, h_in, m->pool_tmp, s, launches));
+                             d.num_pools, h_in, m->pool_tmp, s, launches, strict));
     }
     // launch_pool writes rows of stride num_pools*emb; keep that as the leading dimension
     h_ld = head_in;

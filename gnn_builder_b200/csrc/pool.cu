@@ -47,12 +47,15 @@ __global__ void __launch_bounds__(128) pool_kernel(const PoolArgs a)
         const int64_t r0 = n0 + split * per;
         const int64_t r1 = (r0 + per < n1) ? r0 + per : n1;
         for (int f = threadIdx.x; f < a.F; f += blockDim.x) {
-            float sum = 0.0f, mx = 0.0f;
-            bool first = true;
+            float sum = 0.0f, mx = split == 0 ? 0.0f : -INFINITY;
+            // lib:748-759: the first sample of the GRAPH initialises the maximum (a NaN there
+            // sticks), every later sample only replaces it when it compares greater (a NaN never
+            // does).  Only range 0 holds the graph's first sample.
+            bool first = split == 0;
             for (int64_t r = r0; r < r1; r++) {
                 const float v = __ldg(a.x + (size_t)r * a.ldx + f);
                 sum = __fadd_rn(sum, v);
-                mx = (first || v > mx) ? v : mx;  // lib:748-759 (a NaN first sample sticks)
+                mx = (first || v > mx) ? v : mx;
                 first = false;
             }
             if (a.splits == 1) {
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(128) pool_kernel(const PoolArgs a)
             } else {
                 float *p = a.partial + ((size_t)g * a.splits + split) * 2 * a.F;
                 p[f] = sum;
-                p[a.F + f] = first ? -INFINITY : mx;
+                p[a.F + f] = (split == 0 && r1 <= r0) ? -INFINITY : mx;
             }
         }
     }
@@ -83,7 +86,8 @@ __global__ void __launch_bounds__(128 * COMBINE_GROUPS) pool_combine_kernel(cons
                 for (int sp = grp; sp < a.splits; sp += COMBINE_GROUPS) {
                     const float *p = a.partial + ((size_t)g * a.splits + sp) * 2 * a.F;
                     sum += p[f];
-                    mx = fmaxf(mx, p[a.F + f]);
+                    const float v = p[a.F + f];
+                    mx = v > mx ? v : mx;
                 }
             }
             s_sum[grp][fl] = sum;
@@ -94,8 +98,11 @@ __global__ void __launch_bounds__(128 * COMBINE_GROUPS) pool_combine_kernel(cons
 #pragma unroll
                 for (int q = 0; q < COMBINE_GROUPS; q++) {
                     ts += s_sum[q][fl];
-                    tm = fmaxf(tm, s_max[q][fl]);
+                    tm = s_max[q][fl] > tm ? s_max[q][fl] : tm;
                 }
+                // a NaN in the graph's first row sticks, exactly like the single-pass rule
+                const float p0 = a.partial[((size_t)g * a.splits) * 2 * a.F + a.F + f];
+                if (p0 != p0) tm = p0;
                 write_pools(a, g, f, ts, tm, n);
             }
             __syncthreads();
@@ -115,7 +122,7 @@ __global__ void activation_kernel(int act, const float *__restrict__ x, float *_
 
 int launch_pool(const float *x, int ldx, int F, const int64_t *node_ptr, int64_t node_base,
                 int n_graphs, int64_t total_nodes, const int *pools, int num_pools, float *pooled,
-                DeviceBuf &tmp, cudaStream_t s, int *launches)
+                DeviceBuf &tmp, cudaStream_t s, int *launches, bool single_pass)
 {
     if (n_graphs <= 0 || F <= 0) return GNNB_OK;
     GNNB_REQUIRE(num_pools >= 1 && num_pools <= 4, "pooling: 1..4 aggregations");
@@ -128,7 +135,7 @@ int launch_pool(const float *x, int ldx, int F, const int64_t *node_ptr, int64_t
     // cut graphs that are much larger than the machine into row ranges
     int64_t avg = total_nodes / n_graphs;
     int splits = 1;
-    if (avg > 8192) {
+    if (avg > 8192 && !single_pass) {   // (STRICT math: one range, the reference's sum order)
         int64_t want = avg / 2048;
         int64_t room = (int64_t)kNumSMs * 16 / n_graphs;
         if (room < 1) room = 1;

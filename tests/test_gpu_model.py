@@ -84,8 +84,8 @@ def test_batch_vs_oracle(gnnb, orc, name):
         kernel = outs.pop("forced-kernel", None)
         for path, out in outs.items():
             assert rel_err(out, ref) < TOL, (name, path, rel_err(out, ref))
-        # which kernel AUTO must have picked: tcgen05 fused for GCN/GIN/SAGE, layerwise for PNA
-        assert ("fused" in outs) == (name != "c4_pna_lipo"), (name, list(outs), kernel)
+        # AUTO picks the tcgen05 fused kernel for all four BASELINE convs (PNA since round 2)
+        assert "fused" in outs and kernel == "fused-tcgen05", (name, list(outs), kernel)
 
 
 def test_edge_cases(gnnb, orc):
@@ -296,6 +296,69 @@ def test_non_finite_inputs_do_not_leak_between_graphs(gnnb, orc):
         assert eng.last_kernel == "fused-tcgen05"
 
 
+PNA_VARIANTS = {
+    # tensor-memory budget edge (hidden 96), two feature groups of different width (in_dim 40:
+    # 32 + 16 features), one group of 16, four layers, non-ReLU activation, no skip, single pool
+    "pna_96": dict(hidden_dim=96),
+    "pna_wide_input_48": dict(hidden_dim=48, in_dim=40, mlp_hidden_dim=32),
+    "pna_16_4layers_tanh": dict(hidden_dim=16, num_layers=4, activation="tanh"),
+    "pna_64_noskip_sigmoid_maxpool": dict(hidden_dim=64, skip=False, activation="sigmoid", pools=["max"]),
+    "pna_one_layer": dict(num_layers=1, hidden_dim=80),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(PNA_VARIANTS))
+def test_fused_tc_pna_variants(gnnb, orc, variant):
+    """PNA in the fused tcgen05 kernel (gather statistics in shared memory, three accumulators for
+    the degree scalers) against the oracle"""
+    import dataclasses
+
+    from conftest import workload_by_name
+    from gnn_builder_b200.models import build_model
+
+    w = dataclasses.replace(workload_by_name("c4_pna_lipo"), **PNA_VARIANTS[variant])
+    model = build_model(w, pna_delta=w.pna_delta, seed=11)
+    params = model.named_parameter_arrays()
+    batch = gnnb.make_molecular_batch(700, w.mu_nodes, w.mu_edges, w.in_dim, seed=5)
+    ref = orc.model_forward_batch(model.describe(), list(params.values()), batch)
+    with gnnb.Engine(model) as eng:
+        out = eng.run(batch)
+        assert eng.last_kernel == "fused-tcgen05", (variant, eng.last_kernel)
+        assert rel_err(out, ref) < TOL, (variant, rel_err(out, ref))
+
+
+def test_fused_pna_zero_in_degree_and_multi_edges(gnnb, orc):
+    """the fused PNA path keeps the reference's semantics per graph: std = NaN for in-degree 0
+    (0/0, lib:702) -- which ReLU turns into 0 and sigmoid keeps --, duplicate edges count twice in
+    mean / std, and a NaN graph does not touch its tile neighbours (PNA never mixes graphs)"""
+    import dataclasses
+
+    from conftest import workload_by_name
+    from gnn_builder_b200.models import build_model
+
+    for act in ("relu", "sigmoid"):
+        w = dataclasses.replace(workload_by_name("c4_pna_lipo"), activation=act)
+        model = build_model(w, pna_delta=w.pna_delta, seed=3)
+        params = model.named_parameter_arrays()
+        rng = np.random.default_rng(2)
+        mol = gnnb.make_molecular_batch(40, w.mu_nodes, w.mu_edges, w.in_dim, seed=9)
+        graphs = [mol.graph(g) for g in range(mol.n_graphs)]
+        graphs.insert(3, (rng.uniform(-1, 1, (4, w.in_dim)).astype(np.float32),
+                          np.array([[0, 1], [1, 2], [2, 1], [0, 1], [0, 1]], np.int32)))   # nodes 0, 3: no in-edges
+        graphs.insert(17, (rng.uniform(-1, 1, (1, w.in_dim)).astype(np.float32), np.zeros((0, 2), np.int32)))
+        star = np.stack([np.arange(1, 14), np.zeros(13, np.int64)], 1)         # node 0: 13 distinct in-neighbors
+        graphs.insert(25, (rng.uniform(-1, 1, (14, w.in_dim)).astype(np.float32),
+                           np.concatenate([star, star[:, ::-1], star[:3]]).astype(np.int32)))
+        batch = gnnb.GraphBatch.from_graphs(graphs)
+        ref = orc.model_forward_batch(model.describe(), list(params.values()), batch)
+        with gnnb.Engine(model) as eng:
+            out = eng.run(batch)
+            assert eng.last_kernel == "fused-tcgen05"
+        assert np.array_equal(np.isnan(out), np.isnan(ref)), act
+        assert rel_err(np.nan_to_num(out), np.nan_to_num(ref)) < TOL, act
+        assert np.isfinite(ref[[0, 1, 2, 4, 5]]).all()     # (the head's ReLU maps a NaN pooled vector to 0)
+
+
 VARIANTS = {
     # (base workload, overrides): shapes and options the BASELINE configs do not reach
     "gin_eps": ("c2_gin_qm9", dict(gin_eps=0.25)),                        # eps * x_v added in registers
@@ -367,7 +430,7 @@ def test_two_handles_from_two_host_threads(gnnb, orc):
 
 
 
-@pytest.mark.parametrize("name", ["c1_gcn_esol", "c2_gin_qm9", "c3_sage_hiv"])
+@pytest.mark.parametrize("name", ["c1_gcn_esol", "c2_gin_qm9", "c3_sage_hiv", "c4_pna_lipo"])
 def test_fused_tcgen05_run_to_run_bit_identity(gnnb, name):
     """the same batch 20 times through the tcgen05 fused kernel gives the same bits every time:
     every hand-off between the row passes and the MMAs is ordered by mbarriers, so no result

@@ -14,11 +14,12 @@ sys.path.insert(0, str(ROOT / "tests"))
 import gnn_builder_b200 as gnnb  # noqa: E402
 from conftest import rel_err, workload_by_name  # noqa: E402
 from oracle import Oracle  # noqa: E402
-from test_gpu_model import VARIANTS  # noqa: E402
+from test_gpu_model import PNA_VARIANTS, VARIANTS  # noqa: E402
 
 orc = Oracle()
-cases = [(n, n, {}) for n in ("c1_gcn_esol", "c2_gin_qm9", "c3_sage_hiv")]
+cases = [(n, n, {}) for n in ("c1_gcn_esol", "c2_gin_qm9", "c3_sage_hiv", "c4_pna_lipo")]
 cases += [(k, b, o) for k, (b, o) in sorted(VARIANTS.items())]
+cases += [(k, "c4_pna_lipo", o) for k, o in sorted(PNA_VARIANTS.items())]
 worst = 0.0
 for label, base, over in cases:
     w = dataclasses.replace(workload_by_name(base), **over)
