@@ -226,6 +226,7 @@ struct TcParams {
 struct Misc {
     uint64_t bar_full[MAX_NSLOT], bar_empty[MAX_NSLOT];
     uint32_t slot_log2, slot_stride;
+    unsigned long long *timing;      // GNNB_FUSED_TIMING: per-phase cycle counters, else null
     // MMA <-> row-pass hand-off, per 64-column half h: ready[h] = the workers have written columns
     // [64 h, 64 h + 64) of the next MMA operand (one arrival per worker warp); done[h] = the MMAs
     // producing columns [64 h, +64) of the accumulator have completed (tcgen05.commit).
@@ -387,17 +388,23 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &co
     const int KA = L.KA;
     const uint32_t idesc = tc::make_idesc_bf16(TM, L.N, 0);
     const uint32_t tmem_d = tmem_base + dcol, ahi = tmem_base + TM_AHI, amid = tmem_base + TM_ALO;
+    // GNNB_FUSED_TIMING: the issuing warp's cycles waiting for the A operand (timing[16]), waiting
+    // for weight units (timing[17]) and inside this function in total (timing[18])
+    unsigned long long *const timing = ms.timing;
+    long long t_enter = 0, t_w = 0, t_ready = 0, t_full = 0;
+    if (timing != nullptr) t_enter = clock64();
+#define GNNB_TWAIT(acc, expr) do { if (timing != nullptr) t_w = clock64(); expr; if (timing != nullptr) acc += clock64() - t_w; } while (0)
     if (wait_ready) {
-        tc::mbar_wait(&ms.bar_ready[0], ready_cnt & 1);
+        GNNB_TWAIT(t_ready, tc::mbar_wait(&ms.bar_ready[0], ready_cnt & 1));
         tc::tc_fence_after();
     }
     for (int ka = 0; ka < KA; ka++) {   // hi atoms
         if (ka == 1 && wait_ready) {
-            tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1);
+            GNNB_TWAIT(t_ready, tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1));
             tc::tc_fence_after();
         }
         const uint32_t s = cons & ((1u << slot_log2) - 1u);
-        tc::mbar_wait(&ms.bar_full[s], (cons >> slot_log2) & 1);
+        GNNB_TWAIT(t_full, tc::mbar_wait(&ms.bar_full[s], (cons >> slot_log2) & 1));
         tc::tc_fence_after();
         const uint32_t col = (uint32_t)(ka * 32);
         const int nk = min(4, (L.K - ka * 64 + 15) >> 4);
@@ -419,14 +426,14 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &co
     }
     if (wait_ready) {
         if (KA <= 1) {
-            tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1);
+            GNNB_TWAIT(t_ready, tc::mbar_wait(&ms.bar_ready[1], ready_cnt & 1));
             tc::tc_fence_after();
         }
         ready_cnt++;
     }
     for (int ka = 0; ka < KA; ka++) {   // mid atoms
         const uint32_t s = cons & ((1u << slot_log2) - 1u);
-        tc::mbar_wait(&ms.bar_full[s], (cons >> slot_log2) & 1);
+        GNNB_TWAIT(t_full, tc::mbar_wait(&ms.bar_full[s], (cons >> slot_log2) & 1));
         tc::tc_fence_after();
         const uint32_t col = (uint32_t)(ka * 32);
         const int nk = min(4, (L.K - ka * 64 + 15) >> 4);
@@ -443,6 +450,13 @@ __device__ __forceinline__ void gemm_issue(Misc &ms, uint32_t ring, uint32_t &co
     if (leader && commit_done) {
         tc::mma_commit(&ms.bar_done[0]);
         tc::mma_commit(&ms.bar_done[1]);
+    }
+#undef GNNB_TWAIT
+    if (timing != nullptr && leader) {
+        atomicAdd(timing + 16, (unsigned long long)t_ready);
+        atomicAdd(timing + 17, (unsigned long long)t_full);
+        atomicAdd(timing + 18, (unsigned long long)(clock64() - t_enter));
+        atomicAdd(timing + 19, 1ull);
     }
 }
 #else
@@ -825,6 +839,54 @@ __device__ __forceinline__ int epilogue_planes_t(Misc &ms, uint32_t &done_cnt, u
     });
     return chk == 0.0f ? 0 : 1;
 }
+#if GNNB_TC_BF2
+// PNA: the same pass writes the planes (the next layer's skip source) AND the next layer's A operand
+// -- the packed bf16 pairs are identical -- and hands the A operand off, so the next layer's three
+// pre-transform GEMMs start without another pass over the planes.
+template <int ACT, bool SKIP>
+__device__ __forceinline__ void epilogue_planes_a_t(Misc &ms, uint32_t &done_cnt, uint32_t tmem_base,
+                                                    uint32_t tmem_d, unsigned char *XP, int N,
+                                                    const float *__restrict__ bias, int act)
+{
+    const int row = 32 * ((threadIdx.x >> 5) & 3) + (threadIdx.x & 31);
+    row_pass<1>(ms, done_cnt, tmem_d, (N + 31) & ~31, [&](int c0, uint32_t lane_base, const uint32_t (&r)[CH]) {
+        float hc[CH / 2], mc[CH / 2];
+#pragma unroll
+        for (int j8 = 0; j8 < CH / 8; j8++) {
+            const int c = c0 + 8 * j8;
+            float o[8];
+            if (c < N) {   // N % 8 == 0
+                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + c));
+                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + c + 4));
+                const float bss[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float xs[8];
+                if (SKIP) load_row8(XP, row, c, xs);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    float t = __uint_as_float(r[8 * j8 + j]) + bss[j];
+                    if (SKIP) t += xs[j];
+                    o[j] = act_fast<ACT>(act, t);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) o[j] = 0.0f;
+            }
+            uint32_t hp[4], mp[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                split2_pair(o[2 * j], o[2 * j + 1], hp[j], mp[j]);
+                hc[4 * j8 + j] = __uint_as_float(hp[j]);
+                mc[4 * j8 + j] = __uint_as_float(mp[j]);
+            }
+            const uint32_t off = tc::plane_chunk_offset(row, c);
+            *reinterpret_cast<uint4 *>(XP + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            *reinterpret_cast<uint4 *>(XP + tc::PLANE_BYTES + off) = make_uint4(mp[0], mp[1], mp[2], mp[3]);
+        }
+        tc::tmem_st(tmem_base + TM_AHI + lane_base + (uint32_t)(c0 >> 1), hc);
+        tc::tmem_st(tmem_base + TM_ALO + lane_base + (uint32_t)(c0 >> 1), mc);
+    });
+}
+#endif
 // SCALE (GCN only): skip_unscale undoes the dinv factor stored in the planes, out_scale applies the
 // next layer's.  The common cases (ReLU / identity, with and without skip) get lean instantiations.
 __device__ __forceinline__ int epilogue_planes(Misc &ms, uint32_t &done_cnt, uint32_t tmem_d,
@@ -976,7 +1038,8 @@ __device__ __forceinline__ void pna_for_each_neighbor(const PnaNbr &nb, const ui
 __device__ __forceinline__ int pna_layer_workers(const TcParams &p, Misc &ms, int l, uint32_t tmem_base,
                                                  unsigned char *XP, float *AROWS, const uint32_t *CNT,
                                                  uint32_t &done_cnt, int my_deg, const PnaNbr &nb, int g_r0,
-                                                 int g_r1, bool last_layer, bool do_skip, long long &t_prev)
+                                                 int g_r1, bool last_layer, bool do_skip, bool next_skip,
+                                                 long long &t_prev)
 {
     // GNNB_FUSED_TIMING: thread 0's cycles per phase -> timing[8 ..]
 #define PNA_PHASE(idx)                                                              \
@@ -990,8 +1053,9 @@ __device__ __forceinline__ int pna_layer_workers(const TcParams &p, Misc &ms, in
     const int row = 32 * (warp & 3) + lane, hh = warp >> 2;
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     const int fi = p.fi[l], kp = (fi + 31) & ~31;
-    // ---- phase A: X rows -> A operand; the issuer runs the three GEMMs off it
-    cvt_self(ms, tmem_base, XP, kp);
+    // ---- phase A: X rows -> A operand; the issuer runs the three GEMMs off it.  (From layer 1 on
+    // the previous layer's output pass has written and handed off the A operand already.)
+    if (l == 0) cvt_self(ms, tmem_base, XP, kp);
     PNA_PHASE(8)
     wait_done_both(ms, done_cnt);
     PNA_PHASE(9)
@@ -1009,87 +1073,79 @@ __device__ __forceinline__ int pna_layer_workers(const TcParams &p, Misc &ms, in
     worker_sync();
     tc::tc_fence_after();
     PNA_PHASE(10)
-    // ---- phase C: per group of 32 features, per sub-block h of 16: (max, min) by the hh = 0 thread
-    // of the row, (mean, std) by the hh = 1 thread, over the row's in-neighbors; the 32 results are
-    // A-operand columns [64 h + 32 hh, +32) of the group's GEMMs (the weight images are permuted to
-    // that order: K' = 64 h + 16 q + j  <->  statistic q of feature 32 g + 16 h + j)
+    // ---- phase C: per group of 32 features, per sub-block h of 16 features: the two threads of a
+    // row take 8 features each and compute all four statistics over the row's in-neighbors (one
+    // gather for max / min / sum, a second one for the variance around the mean); the 32 results
+    // are A-operand columns [64 h + 32 hh, +32) of the group's GEMMs.  The weight images are
+    // permuted to that order: K' = 64 h + 32 hh + 8 q + j  <->  statistic q (max, min, mean, std)
+    // of feature 32 g + 16 h + 8 hh + j.
     const float degf = (float)my_deg;
+    const float inv_deg = 1.0f / degf;        // (in-degree 0: inf, so the variance becomes 0 * inf = NaN, lib:702)
     for (int g = 0; g < P.ng; g++) {
         const int gw = P.gw[g];
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
-            const int f0 = 32 * g + 16 * h;
+            const int f0 = 32 * g + 16 * h + 8 * hh;
             if (16 * h < gw) {
-                float bv[16], s0[16], s1[16];
-                {   // B_v + b_pre of this row (tensor memory) for the 16 features
-                    uint32_t r[16];
-                    tc::tmem_ld_nowait(tmem_base + pna_col_b(P) + lane_base + (uint32_t)f0, r);
+                float bv[8], vmax[8], vmin[8], vsum[8], vm2[8];
+                {   // B_v + b_pre of this row (tensor memory) for its 8 features
+                    uint32_t r[8];
+                    tc::tmem_ld8_nowait(tmem_base + pna_col_b(P) + lane_base + (uint32_t)f0, r);
                     tc::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; j++) bv[j] = __uint_as_float(r[j]) + __ldg(P.pb.bias + f0 + j);
+                    for (int j = 0; j < 8; j++) bv[j] = __uint_as_float(r[j]) + __ldg(P.pb.bias + f0 + j);
                 }
 #pragma unroll
-                for (int j = 0; j < 16; j++) { s0[j] = 0.0f; s1[j] = 0.0f; }
-                if (hh == 0) {   // max / min with the reference's first-sample rule (lib:748-795)
-                    bool first = true;
-                    pna_for_each_neighbor(nb, CNT, row, g_r0, g_r1, [&](int u, int) {
-                        const float *au = AROWS + u * PNA_LDA + f0;
+                for (int j = 0; j < 8; j++) { vmax[j] = 0.0f; vmin[j] = 0.0f; vsum[j] = 0.0f; vm2[j] = 0.0f; }
+                // max / min: the reference's first-sample rule (lib:748-795) differs from fmaxf / fminf
+                // only when a sample is NaN -- and then the mean, hence the whole output row, is NaN
+                // either way -- so the running extrema start from -inf / +inf (0 for no samples)
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; j4++) {
-                            const float4 a = *reinterpret_cast<const float4 *>(au + 4 * j4);
-                            const float t[4] = {a.x + bv[4 * j4], a.y + bv[4 * j4 + 1], a.z + bv[4 * j4 + 2],
-                                                a.w + bv[4 * j4 + 3]};
+                for (int j = 0; j < 8; j++) { vmax[j] = -INFINITY; vmin[j] = INFINITY; }
+                pna_for_each_neighbor(nb, CNT, row, g_r0, g_r1, [&](int u, int m) {
+                    const float *au = AROWS + u * PNA_LDA + f0;
+                    const float4 a0 = *reinterpret_cast<const float4 *>(au);
+                    const float4 a1 = *reinterpret_cast<const float4 *>(au + 4);
+                    const float t[8] = {a0.x + bv[0], a0.y + bv[1], a0.z + bv[2], a0.w + bv[3],
+                                        a1.x + bv[4], a1.y + bv[5], a1.z + bv[6], a1.w + bv[7]};
+                    const float mf = (float)m;
 #pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                s0[4 * j4 + j] = (first || t[j] > s0[4 * j4 + j]) ? t[j] : s0[4 * j4 + j];
-                                s1[4 * j4 + j] = (first || t[j] < s1[4 * j4 + j]) ? t[j] : s1[4 * j4 + j];
-                            }
-                        }
-                        first = false;
-                    });
-                } else {         // mean, then the population variance around it; std = sqrt(var + 1e-5)
-                    pna_for_each_neighbor(nb, CNT, row, g_r0, g_r1, [&](int u, int m) {
-                        const float *au = AROWS + u * PNA_LDA + f0;
-                        const float mf = (float)m;
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; j4++) {
-                            const float4 a = *reinterpret_cast<const float4 *>(au + 4 * j4);
-                            s0[4 * j4] = fmaf(mf, a.x + bv[4 * j4], s0[4 * j4]);
-                            s0[4 * j4 + 1] = fmaf(mf, a.y + bv[4 * j4 + 1], s0[4 * j4 + 1]);
-                            s0[4 * j4 + 2] = fmaf(mf, a.z + bv[4 * j4 + 2], s0[4 * j4 + 2]);
-                            s0[4 * j4 + 3] = fmaf(mf, a.w + bv[4 * j4 + 3], s0[4 * j4 + 3]);
-                        }
-                    });
-                    if (my_deg > 0) {
-#pragma unroll
-                        for (int j = 0; j < 16; j++) s0[j] = s0[j] / degf;      // lib:661
+                    for (int j = 0; j < 8; j++) {
+                        vmax[j] = fmaxf(vmax[j], t[j]);
+                        vmin[j] = fminf(vmin[j], t[j]);
+                        vsum[j] = fmaf(mf, t[j], vsum[j]);
                     }
-                    pna_for_each_neighbor(nb, CNT, row, g_r0, g_r1, [&](int u, int m) {
-                        const float *au = AROWS + u * PNA_LDA + f0;
-                        const float mf = (float)m;
+                });
+                if (my_deg == 0) {
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; j4++) {
-                            const float4 a = *reinterpret_cast<const float4 *>(au + 4 * j4);
-                            const float t[4] = {a.x + bv[4 * j4], a.y + bv[4 * j4 + 1], a.z + bv[4 * j4 + 2],
-                                                a.w + bv[4 * j4 + 3]};
+                    for (int j = 0; j < 8; j++) { vmax[j] = 0.0f; vmin[j] = 0.0f; }
+                }
 #pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const float d = t[j] - s0[4 * j4 + j];
-                                s1[4 * j4 + j] = fmaf(mf * d, d, s1[4 * j4 + j]);
-                            }
-                        }
-                    });
+                for (int j = 0; j < 8; j++) vsum[j] = my_deg > 0 ? vsum[j] * inv_deg : 0.0f;   // mean (lib:661)
+                pna_for_each_neighbor(nb, CNT, row, g_r0, g_r1, [&](int u, int m) {
+                    const float *au = AROWS + u * PNA_LDA + f0;
+                    const float4 a0 = *reinterpret_cast<const float4 *>(au);
+                    const float4 a1 = *reinterpret_cast<const float4 *>(au + 4);
+                    const float t[8] = {a0.x + bv[0], a0.y + bv[1], a0.z + bv[2], a0.w + bv[3],
+                                        a1.x + bv[4], a1.y + bv[5], a1.z + bv[6], a1.w + bv[7]};
+                    const float mf = (float)m;
 #pragma unroll
-                    for (int j = 0; j < 16; j++)     // in-degree 0: 0 / 0 = NaN like the reference (lib:702)
-                        s1[j] = sqrtf(s1[j] / degf + 1e-5f);
+                    for (int j = 0; j < 8; j++) {
+                        const float d = t[j] - vsum[j];
+                        vm2[j] = fmaf(mf * d, d, vm2[j]);
+                    }
+                });
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float var = vm2[j] * inv_deg + 1e-5f;      // population variance (lib:702-703)
+                    v[j] = vmax[j]; v[8 + j] = vmin[j]; v[16 + j] = vsum[j];
+                    v[24 + j] = var * rsqrtf(var);                    // sqrt(var), 2 ulp; NaN for in-degree 0
                 }
                 PNA_PHASE(11)
                 // the previous group's GEMMs must have finished reading the A operand
                 if (g > 0 && h == 0) wait_done_both(ms, done_cnt);
                 PNA_PHASE(12)
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 16; j++) { v[j] = s0[j]; v[16 + j] = s1[j]; }
                 split_store(tmem_base, lane_base, 64 * h + 32 * hh, v);
                 tc::tmem_st_wait();
             } else if (g > 0 && h == 0) {
@@ -1143,13 +1199,17 @@ __device__ __forceinline__ int pna_layer_workers(const TcParams &p, Misc &ms, in
         epilogue_rows(ms, done_cnt, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act);
         return 0;
     }
-    // no hand-off: the next layer starts with its own row pass over the planes (generic-proxy
-    // reads of the columns this very thread wrote)
-    if (p.gnn_act == GNNB_ACT_RELU)
-        return do_skip ? epilogue_planes_t<1, true, false, 0>(ms, done_cnt, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act, 1.0f, 1.0f)
-                       : epilogue_planes_t<1, false, false, 0>(ms, done_cnt, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act, 1.0f, 1.0f);
-    return do_skip ? epilogue_planes_t<2, true, false, 0>(ms, done_cnt, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act, 1.0f, 1.0f)
-                   : epilogue_planes_t<2, false, false, 0>(ms, done_cnt, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act, 1.0f, 1.0f);
+    // the planes are only read back as the next layer's skip source (by this very thread): no
+    // shared-memory fence, no barrier; the A operand is handed off per 64-column half
+    (void)next_skip;
+    if (p.gnn_act == GNNB_ACT_RELU) {
+        if (do_skip) epilogue_planes_a_t<1, true>(ms, done_cnt, tmem_base, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act);
+        else epilogue_planes_a_t<1, false>(ms, done_cnt, tmem_base, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act);
+    } else {
+        if (do_skip) epilogue_planes_a_t<2, true>(ms, done_cnt, tmem_base, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act);
+        else epilogue_planes_a_t<2, false>(ms, done_cnt, tmem_base, tmem_d, XP, P.pl.N, P.pl.bias, p.gnn_act);
+    }
+    return 0;
 #undef PNA_PHASE
 }
 
@@ -1277,6 +1337,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
     if (tid == 0) {
         ms.slot_log2 = (uint32_t)p.slot_log2;
         ms.slot_stride = (uint32_t)p.slot_stride;
+        ms.timing = p.timing;
         for (int i = 0; i < MAX_NSLOT; i++) {
             tc::mbar_init(&ms.bar_full[i], 1);
             tc::mbar_init(&ms.bar_empty[i], 1);
@@ -1564,7 +1625,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
             for (int l = 0; l < p.num_layers; l++) {
                 const bool last_layer = l == p.num_layers - 1;
                 pna_layer_workers(p, ms, l, tmem_base, XP, reinterpret_cast<float *>(ADJ), CNT, done_cnt,
-                                  my_deg, nb, g_r0, g_r1, last_layer, p.skip && l != 0 && !last_layer, t_prev);
+                                  my_deg, nb, g_r0, g_r1, last_layer, p.skip && l != 0 && !last_layer,
+                                  p.skip && l + 1 < p.num_layers - 1, t_prev);
                 GNNB_PHASE(7)
             }
             worker_sync();           // pooling reads the other threads' rows; the counters are dead
@@ -1783,19 +1845,21 @@ int fused_tc_prepare(gnnb_model *m)
                 const int gw = std::min(32, (fi - 32 * g + 15) / 16 * 16);
                 q.gw[g] = gw;
                 const int Kg = 4 * gw;
-                // K' = 64 h + 16 q + j  <->  statistic q of feature 32 g + 16 h + j (lib:1857-1875: the
-                // 12F block is [identity | amplification | attenuation] x [max | min | mean | std] x F)
+                // K' = 64 h + 32 fh + 8 q + j  <->  statistic q of feature 32 g + 16 h + 8 fh + j
+                // (lib:1857-1875: the 12F block is [identity | amplification | attenuation] x
+                // [max | min | mean | std] x F)
                 for (int sc = 0; sc < 3; sc++) {
                     std::vector<float> Wg((size_t)fo * Kg, 0.0f);
                     for (int o = 0; o < fo; o++)
                         for (int h = 0; h < gw / 16; h++)
                             for (int st = 0; st < 4; st++)
-                                for (int j = 0; j < 16; j++) {
-                                    const int f = 32 * g + 16 * h + j;
-                                    if (f < fi)
-                                        Wg[(size_t)o * Kg + 64 * h + 16 * st + j] =
-                                            post_w[(size_t)o * 13 * fi + fi + (size_t)(sc * 4 + st) * fi + f];
-                                }
+                                for (int fh = 0; fh < 2; fh++)
+                                    for (int j = 0; j < 8; j++) {
+                                        const int f = 32 * g + 16 * h + 8 * fh + j;
+                                        if (f < fi)
+                                            Wg[(size_t)o * Kg + 64 * h + 32 * fh + 8 * st + j] =
+                                                post_w[(size_t)o * 13 * fi + fi + (size_t)(sc * 4 + st) * fi + f];
+                                    }
                     PnaPending::Lin l = add(Wg.data(), fo, fo, Kg, Kg, 0);
                     (sc == 0 ? q.gid : sc == 1 ? q.gamp : q.gatt)[g] = l;
                 }
@@ -1851,8 +1915,8 @@ int fused_tc_prepare(gnnb_model *m)
     if (rc == GNNB_OK) rc = plan->flag.ensure(sizeof(int));
     if (rc == GNNB_OK) rc = plan->pending.ensure((size_t)kNumSMs * HEAD_G * PLD * sizeof(float));
     if (rc == GNNB_OK && getenv("GNNB_FUSED_TIMING") != nullptr) {
-        rc = plan->timing.ensure(16 * sizeof(unsigned long long));
-        if (rc == GNNB_OK) cudaMemset(plan->timing.ptr, 0, 16 * sizeof(unsigned long long));
+        rc = plan->timing.ensure(32 * sizeof(unsigned long long));
+        if (rc == GNNB_OK) cudaMemset(plan->timing.ptr, 0, 32 * sizeof(unsigned long long));
     }
     if (rc != GNNB_OK) { delete plan; return rc; }
     const float *base = plan->images.as<float>();
@@ -1985,9 +2049,14 @@ int fused_tc_status(gnnb_model *m, int *status)
     if (plan == nullptr) return GNNB_OK;
     GNNB_CUDA(cudaMemcpy(status, plan->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost));
     if (plan->timing.ptr != nullptr) {
-        unsigned long long t[16];
+        unsigned long long t[32];
         GNNB_CUDA(cudaMemcpy(t, plan->timing.ptr, sizeof(t), cudaMemcpyDeviceToHost));
         GNNB_CUDA(cudaMemset(plan->timing.ptr, 0, sizeof(t)));
+        if (t[19])
+            fprintf(stderr, "[gnnb fused-tc issuer] %llu GEMMs: waiting for the A operand %.1f%%, for weight "
+                            "units %.1f%% of %.3g cycles inside gemm_issue (%.0f per GEMM)\n",
+                    t[19], 100.0 * (double)t[16] / (double)t[18], 100.0 * (double)t[17] / (double)t[18],
+                    (double)t[18], (double)t[18] / (double)t[19]);
         // (the row passes include their waits for the MMAs of the phase they read)
         const char *names[16] = {"stage", "adj+planes", "agg->A pass", "hidden/self pass", "pool", "head",
                                  "-", "output pass", "pna:x->A", "pna:wait pre", "pna:A_u->smem",
