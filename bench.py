@@ -727,7 +727,8 @@ def measure_large(ctx: Ctx, w, nodes: int, steps: int, warmup: int, cpu_baseline
         comp_ms = ctx.max(ev[2].elapsed_time(ev[3]) / iters)
         recv_bytes = ctx.max(float(st["halo_rows"] * Fb))
         exchange = {
-            "transport": runner.transport, "halo_rows_max_rank": int(ctx.max(float(st["halo_rows"]))),
+            "transport": runner.transport, "transport_autotune_ms": st.get("autotune_ms"),
+            "halo_rows_max_rank": int(ctx.max(float(st["halo_rows"]))),
             "halo_frac_of_remote_rows": ctx.max(float(st["halo_frac_of_remote_rows"])),
             "recv_bytes_per_layer_max_rank": int(recv_bytes),
             "full_allgather_bytes_per_layer": int((n - n // world) * Fb),

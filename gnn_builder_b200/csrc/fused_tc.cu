@@ -167,7 +167,14 @@ constexpr int STEP_COLS = 256 / NWARPS;      // columns of its rows a warp conve
 #endif
 constexpr int CH = GNNB_TC_CHUNK;            // accumulator columns a thread holds at a time (16 keeps 16 warps under 96 registers)
 static_assert((CH == 16 || CH == 32) && CH <= STEP_COLS, "row passes work on 16- or 32-column chunks");
-constexpr int READY_ARRIVALS = NWARPS;       // every worker warp arrives once per 64-column half
+// Hand-off arrivals: one per worker WARP and 64-column half (lane 0, after the warp has converged).
+// -DGNNB_TC_THREAD_ARRIVALS=1 makes every worker THREAD arrive itself instead -- slower (several
+// hundred cycles per phase on one mbarrier word), but an ordering compute-sanitizer's racecheck can
+// follow: the debug build for tools/r2 racecheck runs (profiles/r2_sanitizer.txt).
+#ifndef GNNB_TC_THREAD_ARRIVALS
+#define GNNB_TC_THREAD_ARRIVALS 0
+#endif
+constexpr int READY_ARRIVALS = GNNB_TC_THREAD_ARRIVALS ? NTHREADS : NWARPS;
 // The accumulator is double buffered: MMA phase i writes D[i & 1] (an accumulating phase stays on
 // the buffer of the phase it adds to), so the row pass that reads phase i's result can overlap the
 // first MMAs of phase i + 1.
@@ -647,17 +654,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 __device__ __forceinline__ void handoff_half(Misc &ms, int h)
 {
     tc::tc_fence_before();
+#if GNNB_TC_THREAD_ARRIVALS
+    mbar_arrive(&ms.bar_ready[h]);
+#else
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&ms.bar_ready[h]);
+#endif
 }
 __device__ __forceinline__ void handoff_both(Misc &ms)
 {
     tc::tc_fence_before();
+#if GNNB_TC_THREAD_ARRIVALS
+    mbar_arrive(&ms.bar_ready[0]);
+    mbar_arrive(&ms.bar_ready[1]);
+#else
     __syncwarp();
     if ((threadIdx.x & 31) == 0) {
         mbar_arrive(&ms.bar_ready[0]);
         mbar_arrive(&ms.bar_ready[1]);
     }
+#endif
 }
 // wait for both halves of the current MMA phase (every worker polls: no CTA barrier)
 __device__ __forceinline__ void wait_done_both(Misc &ms, uint32_t &done_cnt)

@@ -383,7 +383,7 @@ class LargeGraphGCN:
             "n_local": n_local, "halo_rows": plan.n_halo,
             "halo_frac_of_remote_rows": plan.n_halo / max(1, self.part.n_total - n_local),
             "send_rows": int(plan.send_off[-1]), "hub_rows": plan.hub_rows,
-            "transport": self.transport,
+            "transport": self.transport, "autotune_ms": getattr(self, "autotune_ms", None),
         }
         return self
 
@@ -407,10 +407,39 @@ class LargeGraphGCN:
         if self.ext is None:
             self.ext = [B.empty((plan.n_ext * fmax,)) for _ in range(3)]
             self.transport = "nccl" if W > 1 else "none"
-            if W > 1:
-                self.send_buf = B.empty((max(1, int(plan.send_off[-1])) * fmax,))
         else:
             self.transport = "p2p"
+        if W > 1 and (self.transport == "nccl" or self.transport_req == "auto"):
+            self.send_buf = B.empty((max(1, int(plan.send_off[-1])) * fmax,))
+        if self.transport == "p2p" and self.transport_req == "auto":
+            self._autotune(fmax)
+
+    def _autotune(self, F: int):
+        """transport "auto": both transports work on the same ext buffers, so time the exchange of
+        one layer with each (device time, max over ranks) and keep the faster one -- peer stores
+        win when few ranks share the fabric, NCCL's all-to-all may win when many do"""
+        import torch
+
+        B, best = self.backend, {}
+        for tr in ("p2p", "nccl"):
+            self.transport = tr
+            for _ in range(2):
+                self._exchange(0, F)
+                self._arrived()
+            torch.cuda.synchronize()
+            self.dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                self._exchange(0, F)
+                self._arrived()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / 3.0], device=self.ext[0].device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            best[tr] = float(t.item())
+        self.transport = min(best, key=best.get)
+        self.autotune_ms = best
 
     def _setup_p2p(self, fmax: int):
         """ext buffers + flags in CUDA-IPC memory; every rank maps its peers' and learns where in
