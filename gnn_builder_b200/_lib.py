@@ -49,7 +49,7 @@ EXPORTS = [
     "gnnb_global_add_pool", "gnnb_global_mean_pool", "gnnb_global_max_pool",
     "gnnb_partition_tables", "gnnb_degree_inv_sqrt", "gnnb_gcn_conv_partition",
     "gnnb_pool_partial",
-    "gnnb_halo_pack", "gnnb_halo_signal", "gnnb_halo_wait", "gnnb_ipc_alloc", "gnnb_ipc_open",
+    "gnnb_halo_pack", "gnnb_halo_pack_ranges", "gnnb_halo_signal", "gnnb_halo_wait", "gnnb_ipc_alloc", "gnnb_ipc_open",
     "gnnb_ipc_close", "gnnb_ipc_free", "gnnb_mark_hub_sources", "gnnb_gcn_conv_halo",
 ]
 # include/gnnb_b200_debug.h: tcgen05 probes in libgnnb_b200_debug.so (tests / tools only)
@@ -117,6 +117,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     for k in ("add", "mean", "max"):
         getattr(lib, f"gnnb_global_{k}_pool").argtypes = [ci, ci, vp, vp, ci]
     lib.gnnb_halo_pack.argtypes = [vp, ci, ci, vp, vp, vp, ci, ci, vp]
+    lib.gnnb_halo_pack_ranges.argtypes = [vp, ci, ci, vp, vp, vp, vp, ci, ci, vp]
     lib.gnnb_halo_signal.argtypes = [vp, ci, C.c_uint64, vp]
     lib.gnnb_halo_wait.argtypes = [vp, ci, C.c_uint64, vp, vp]
     lib.gnnb_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]
@@ -125,7 +126,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.gnnb_ipc_free.argtypes = [vp]
     lib.gnnb_mark_hub_sources.argtypes = [vp, ci, ci, ci, C.c_int64, C.POINTER(ci), vp]
     lib.gnnb_gcn_conv_halo.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci,
-                                       ci, ci, ci, vp]
+                                       ci, ci, ci, ci, ci, vp]
     lib.gnnb_partition_tables.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]
     lib.gnnb_degree_inv_sqrt.argtypes = [vp, vp, ci, vp]
     lib.gnnb_pool_partial.argtypes = [vp, C.c_int64, ci, vp, vp]

@@ -268,31 +268,30 @@ __global__ void __launch_bounds__(256) agg_heavy_chunk_kernel(const AggArgs a)
     }
 }
 
-// one warp per heavy row: chunk sums added in chunk order, then the row is finished
+// One CTA per heavy row: its 8 warps add contiguous ranges of the row's chunk sums (a hub with
+// 100 000 neighbors has 782 of them: one warp walking them alone took ~100 us, a constant that
+// did not shrink with the GPU count), the 8 range sums are then added in warp order through shared
+// memory and the row is finished -- a fixed order, so the result does not depend on scheduling.
 template <int VEC, int MODE>
 __global__ void __launch_bounds__(256) agg_heavy_combine_kernel(const AggArgs a)
 {
-    const int lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
-    const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    const int warp_stride = gridDim.x * warps_per_block;
-    for (int h = warp_global; h < a.n_heavy; h += warp_stride) {
+    extern __shared__ float ranges[];   // [8][F]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int h = blockIdx.x; h < a.n_heavy; h += gridDim.x) {
         const int v = __ldg(a.heavy_rows + h);
         const int deg_v = __ldg(a.in_deg + v);
         const int len_v = a.counts != nullptr ? __ldg(a.counts + v) : deg_v;
         const int nch = (len_v + kHeavyChunk - 1) / kHeavyChunk;
         const float *src = a.heavy_partial + (size_t)__ldg(a.heavy_chunk_base + h) * a.F;
         const float dinv_v = (MODE == AGG_GCN) ? __ldg(a.dinv + v + a.row_base) : 0.0f;
+        const int per = (nch + 7) / 8;
+        const int j0 = min(nch, warp * per), j1 = min(nch, j0 + per);
         for (int c = lane * VEC; c < a.F; c += 32 * VEC) {
             Vec<VEC> acc;
-            if (a.accumulate) {
-                acc.load_rw(a.out + (size_t)v * a.ldo + c);
-            } else {
 #pragma unroll
-                for (int i = 0; i < VEC; i++) acc.v[i] = 0.0f;
-            }
-            int j = 0;
-            for (; j + 4 <= nch; j += 4) {     // four independent loads in flight, added in order
+            for (int i = 0; i < VEC; i++) acc.v[i] = 0.0f;
+            int j = j0;
+            for (; j + 4 <= j1; j += 4) {     // four independent loads in flight, added in order
                 Vec<VEC> t[4];
 #pragma unroll
                 for (int q = 0; q < 4; q++) t[q].load_rw(src + (size_t)(j + q) * a.F + c);
@@ -301,14 +300,33 @@ __global__ void __launch_bounds__(256) agg_heavy_combine_kernel(const AggArgs a)
 #pragma unroll
                     for (int i = 0; i < VEC; i++) acc.v[i] += t[q].v[i];
             }
-            for (; j < nch; j++) {
+            for (; j < j1; j++) {
                 Vec<VEC> t;
                 t.load_rw(src + (size_t)j * a.F + c);
 #pragma unroll
                 for (int i = 0; i < VEC; i++) acc.v[i] += t.v[i];
             }
-            finish_row<VEC, MODE, false>(a, v, deg_v, dinv_v, c, acc);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) ranges[warp * a.F + c + i] = acc.v[i];
         }
+        __syncthreads();
+        if (warp == 0) {
+            for (int c = lane * VEC; c < a.F; c += 32 * VEC) {
+                Vec<VEC> acc;
+                if (a.accumulate) {
+                    acc.load_rw(a.out + (size_t)v * a.ldo + c);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; i++) acc.v[i] = 0.0f;
+                }
+#pragma unroll
+                for (int w = 0; w < 8; w++)
+#pragma unroll
+                    for (int i = 0; i < VEC; i++) acc.v[i] += ranges[w * a.F + c + i];
+                finish_row<VEC, MODE, false>(a, v, deg_v, dinv_v, c, acc);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -343,9 +361,9 @@ template <int VEC, int MODE>
 void launch_heavy_mode(const AggArgs &a, cudaStream_t s)
 {
     const int cap = kNumSMs * 8;   // 8 resident CTAs per SM, grid-stride beyond
-    const int g1 = min((a.heavy_chunks + 7) / 8, cap), g2 = min((a.n_heavy + 7) / 8, cap);
+    const int g1 = min((a.heavy_chunks + 7) / 8, cap), g2 = min(a.n_heavy, cap);
     agg_heavy_chunk_kernel<VEC, MODE><<<g1, 256, 0, s>>>(a);
-    agg_heavy_combine_kernel<VEC, MODE><<<g2, 256, 0, s>>>(a);
+    agg_heavy_combine_kernel<VEC, MODE><<<g2, 256, sizeof(float) * 8 * (size_t)a.F, s>>>(a);
 }
 
 template <int VEC>

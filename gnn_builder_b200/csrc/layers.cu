@@ -550,7 +550,8 @@ struct PartitionCache {
     DeviceBuf wt, img, agg, pool_tmp, pool_ptr;
     int64_t pool_n = -1;
     HeavyCache whole;     // gnnb_gcn_conv_partition (one CSR)
-    HeavyCache part[2];   // owned-source / halo-source part of a split CSR
+    HeavyCache part[32];  // owned-source / halo-source parts of a split CSR, per row block
+    int part_next = 0;
 };
 thread_local PartitionCache g_part;
 
@@ -572,8 +573,9 @@ struct PackArgs {
     const float *x;
     int ldx, F, n_peers;
     const int32_t *send_idx;
-    long long off[kMaxPeers + 1];   // rows for peer p: send_idx[off[p] .. off[p+1])
-    float *dst[kMaxPeers];          // where they go: a local send buffer or the peer's halo region
+    long long start[kMaxPeers], count[kMaxPeers];   // rows for peer p: send_idx[start[p] .. +count[p])
+    float *dst[kMaxPeers];          // where row i of that range goes: dst[p] + i F (a local send
+                                    // buffer or the peer's halo region)
 };
 // A warp moves PACK_ROWS rows per iteration: all their loads are issued before the first store, so
 // every warp keeps PACK_ROWS x 512 bytes (F = 128) in flight and a grid of ONE CTA per SM already
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(256) halo_pack_kernel(const PackArgs a)
     const bool v4 = (a.F % 4 == 0) && (a.ldx % 4 == 0);
     for (int pp = 0; pp < a.n_peers; pp++) {
         const int p = (pp + wid) % a.n_peers;
-        const long long base = a.off[p], n_p = a.off[p + 1] - base;
+        const long long base = a.start[p], n_p = a.count[p];
         float *const dst_p = a.dst[p];
         for (long long i0 = (long long)wid * PACK_ROWS; i0 < n_p; i0 += (long long)n_warps * PACK_ROWS) {
             const float *src[PACK_ROWS];
@@ -675,7 +677,7 @@ extern "C" int gnnb_partition_tables(const int32_t *edge_list_local, int row_beg
     GNNB_REQUIRE(num_edges_local == 0 || is_device_pointer(edge_list_local),
                  "gnnb_partition_tables takes device pointers");
     g_part.whole.key = nullptr;
-    g_part.part[0].key = g_part.part[1].key = nullptr;
+    for (HeavyCache &hc : g_part.part) hc.key = nullptr;
     return build_partition_tables(edge_list_local, row_begin, n_local, num_edges_local,
                                   in_degree_local, offsets_local, neighbor_table_global, g_part.ws,
                                   (cudaStream_t)stream, nullptr);
@@ -759,29 +761,47 @@ extern "C" int gnnb_pool_partial(const float *x, int64_t n, int F, float *out, v
 // while the aggregation of the owned-source edges runs (phase 1 below); the halo-source edges,
 // the normalisation and the tcgen05 transform follow on arrival (phase 2).
 
-extern "C" int gnnb_halo_pack(const float *x, int ldx, int F, const int32_t *send_idx,
-                              const int64_t *send_off, float *const *dst, int n_peers, int max_ctas,
-                              void *stream)
+extern "C" int gnnb_halo_pack_ranges(const float *x, int ldx, int F, const int32_t *send_idx,
+                                     const int64_t *start, const int64_t *count, float *const *dst,
+                                     int n_peers, int max_ctas, void *stream)
 {
     GNNB_REQUIRE(n_peers >= 0 && n_peers <= kMaxPeers, "halo pack: at most 16 peers");
-    GNNB_REQUIRE(F > 0 && ldx >= F && send_off != nullptr && dst != nullptr, "halo pack: bad arguments");
+    GNNB_REQUIRE(F > 0 && ldx >= F && start != nullptr && count != nullptr && dst != nullptr,
+                 "halo pack: bad arguments");
     PackArgs a{};
     a.x = x; a.ldx = ldx; a.F = F; a.n_peers = n_peers; a.send_idx = send_idx;
-    for (int p = 0; p <= n_peers; p++) a.off[p] = send_off[p];
+    long long total = 0, longest = 0;
     for (int p = 0; p < n_peers; p++) {
-        GNNB_REQUIRE(send_off[p + 1] >= send_off[p], "halo pack: offsets must be non-decreasing");
+        GNNB_REQUIRE(start[p] >= 0 && count[p] >= 0, "halo pack: negative range");
+        a.start[p] = start[p];
+        a.count[p] = count[p];
         a.dst[p] = dst[p];
-        GNNB_REQUIRE(send_off[p + 1] == send_off[p] || (dst[p] != nullptr && (reinterpret_cast<uintptr_t>(dst[p]) & 15) == 0),
+        GNNB_REQUIRE(count[p] == 0 || (dst[p] != nullptr && (reinterpret_cast<uintptr_t>(dst[p]) & 15) == 0),
                      "halo pack: destination missing or not 16-byte aligned");
+        total += count[p];
+        longest = count[p] > longest ? count[p] : longest;
     }
-    const long long total = a.off[n_peers];
     if (total == 0) return GNNB_OK;
-    long long grid = (total + 8 * PACK_ROWS - 1) / (8 * PACK_ROWS);
+    long long grid = (longest + 8 * PACK_ROWS - 1) / (8 * PACK_ROWS);
     const long long cap = max_ctas > 0 ? max_ctas : kNumSMs;   // one CTA per SM: see the kernel
     if (grid > cap) grid = cap;
     halo_pack_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(a);
     GNNB_CUDA(cudaGetLastError());
     return GNNB_OK;
+}
+
+extern "C" int gnnb_halo_pack(const float *x, int ldx, int F, const int32_t *send_idx,
+                              const int64_t *send_off, float *const *dst, int n_peers, int max_ctas,
+                              void *stream)
+{
+    GNNB_REQUIRE(n_peers >= 0 && n_peers <= kMaxPeers && send_off != nullptr, "halo pack: bad arguments");
+    int64_t start[kMaxPeers], count[kMaxPeers];
+    for (int p = 0; p < n_peers; p++) {
+        GNNB_REQUIRE(send_off[p + 1] >= send_off[p], "halo pack: offsets must be non-decreasing");
+        start[p] = send_off[p];
+        count[p] = send_off[p + 1] - send_off[p];
+    }
+    return gnnb_halo_pack_ranges(x, ldx, F, send_idx, start, count, dst, n_peers, max_ctas, stream);
 }
 
 extern "C" int gnnb_halo_signal(uint64_t *const *peer_flags, int n_peers, uint64_t value, void *stream)
@@ -862,11 +882,13 @@ extern "C" int gnnb_gcn_conv_halo(int n_local, int n_ext, const float *x_ext, fl
                                   const int32_t *halo_counts, const int32_t *halo_nbr,
                                   const float *dinv_ext, const float *weight, const float *bias,
                                   const float *skip_local, int emb_in, int emb_out, int act, int phase,
-                                  int hub_bit, void *stream)
+                                  int hub_bit, int row_begin, int row_count, void *stream)
 {
     GNNB_REQUIRE(n_local >= 0 && n_ext >= n_local, "bad row counts");
     GNNB_REQUIRE(emb_in > 0 && emb_out > 0 && act >= 0 && act <= GNNB_ACT_COS, "bad dims");
     GNNB_REQUIRE(phase >= 1 && phase <= 3, "phase: 1 owned-source edges, 2 halo edges + transform, 3 both");
+    if (row_count <= 0) { row_begin = 0; row_count = n_local; }
+    GNNB_REQUIRE(row_begin >= 0 && row_begin + row_count <= n_local, "row block outside the owned rows");
     if (n_local == 0) return GNNB_OK;
     GNNB_REQUIRE(is_device_pointer(x_ext) && is_device_pointer(y_local), "gnnb_gcn_conv_halo takes device pointers");
     const bool has_halo = halo_counts != nullptr && n_ext > n_local;
@@ -874,30 +896,42 @@ extern "C" int gnnb_gcn_conv_halo(int n_local, int n_ext, const float *x_ext, fl
     const int ldw = round_up(emb_out, 4), lda = round_up(emb_in, 4);
     GNNB_TRY(g_part.agg.ensure(sizeof(float) * (size_t)n_local * lda));
     AggArgs a{};
-    a.mode = AGG_GCN; a.x = x_ext; a.ldx = emb_in; a.F = emb_in; a.out = g_part.agg.as<float>();
-    a.ldo = lda; a.dinv = dinv_ext; a.n = n_local; a.row_base = 0;
+    a.mode = AGG_GCN; a.x = x_ext; a.ldx = emb_in; a.F = emb_in;
+    a.out = g_part.agg.as<float>() + (size_t)row_begin * lda;
+    a.ldo = lda; a.dinv = dinv_ext; a.n = row_count;
+    a.row_base = row_begin;      // owned row v is ext row v: self row and dinv are indexed v + row_base
     a.heavy_threshold = heavy_threshold(); a.hub_bit = hub_bit ? 1 : 0;
-    auto run_part = [&](int which, const int32_t *off, const int32_t *cnt, const int32_t *nbr,
-                        bool accumulate, bool finish) -> int {
-        HeavyCache &hc = g_part.part[which];
-        GNNB_TRY(heavy_rows_of(hc, cnt, n_local, s));
+    auto cache_of = [&](const int32_t *lengths) -> HeavyCache & {
+        for (HeavyCache &hc : g_part.part)
+            if (hc.key == lengths && hc.n == row_count) return hc;
+        HeavyCache &hc = g_part.part[g_part.part_next];
+        g_part.part_next = (g_part.part_next + 1) % 32;
+        hc.key = nullptr;
+        return hc;
+    };
+    auto run_part = [&](const int32_t *off, const int32_t *cnt, const int32_t *nbr, bool accumulate,
+                        bool finish) -> int {
+        HeavyCache &hc = cache_of(cnt + row_begin);
+        GNNB_TRY(heavy_rows_of(hc, cnt + row_begin, row_count, s));
         GNNB_TRY(heavy_setup(g_part.ws, hc.list.n_chunks, emb_in));
         AggArgs b = a;
-        b.offsets = off; b.nbr = nbr; b.in_deg = cnt;   // GCN fast mode reads the full degree from dinv only
+        b.offsets = off + row_begin; b.nbr = nbr;
+        b.in_deg = cnt + row_begin;   // GCN fast mode reads the full degree from dinv only
         b.set_heavy(hc.list, g_part.ws.heavy_partial.as<float>());
         b.accumulate = accumulate ? 1 : 0; b.no_finish = finish ? 0 : 1;
         return launch_agg(b, false, s, nullptr);
     };
-    if (phase & 1) GNNB_TRY(run_part(0, own_offsets, own_counts, own_nbr, false, !has_halo));
+    if (phase & 1) GNNB_TRY(run_part(own_offsets, own_counts, own_nbr, false, !has_halo));
     if (!(phase & 2)) return GNNB_OK;
-    if (has_halo) GNNB_TRY(run_part(1, halo_offsets, halo_counts, halo_nbr, true, true));
+    if (has_halo) GNNB_TRY(run_part(halo_offsets, halo_counts, halo_nbr, true, true));
     GNNB_TRY(g_part.wt.ensure(sizeof(float) * (size_t)emb_in * ldw));
     GNNB_TRY(launch_transpose_weight(weight, g_part.wt.as<float>(), emb_out, emb_in, ldw, s, nullptr));
     GNNB_TRY(g_part.img.ensure(sizeof(float) * gemm_tc_image_floats(emb_in, emb_out)));
     GNNB_TRY(gemm_tc_build_image(g_part.wt.as<float>(), ldw, emb_in, emb_out, g_part.img.as<float>(), s));
-    GemmArgs g = simple_gemm(a.out, lda, emb_in, g_part.wt.as<float>(), ldw, bias, y_local, emb_out,
-                             n_local, emb_out, act);
-    g.skip = skip_local; g.ldskip = emb_in;
+    GemmArgs g = simple_gemm(a.out, lda, emb_in, g_part.wt.as<float>(), ldw, bias,
+                             y_local + (size_t)row_begin * emb_out, emb_out, row_count, emb_out, act);
+    g.skip = skip_local != nullptr ? skip_local + (size_t)row_begin * emb_in : nullptr;
+    g.ldskip = emb_in;
     g.img1 = g_part.img.as<float>();
     GNNB_TRY(launch_gemm(g, false, s, nullptr));
     return GNNB_OK;

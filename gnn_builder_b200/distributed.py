@@ -149,6 +149,23 @@ class HaloPlan:
         self.send_off = np.concatenate([[0], np.cumsum(self.send_counts)]).astype(np.int64)
         self.recv_off = np.concatenate([[0], np.cumsum(self.halo_counts)]).astype(np.int64)
         self.hub_rows = 0
+        self._send_idx_host = None
+
+    def block_ranges(self, n_blocks: int):
+        """Owned rows cut into ``n_blocks`` contiguous blocks.  Returns (row_bounds [B+1], lo [B][W]):
+        the rows of block b that peer p needs are send_idx[send_off[p] + lo[b][p] .. send_off[p] +
+        lo[b+1][p]) -- every peer's list is ascending, so a block is a contiguous piece of it."""
+        if self._send_idx_host is None:
+            self._send_idx_host = self.send_idx.cpu().numpy()
+        W = len(self.send_counts)
+        bounds = np.linspace(0, self.n_local, n_blocks + 1).astype(np.int64)
+        bounds[1:-1] = (bounds[1:-1] + 127) // 128 * 128      # whole 128-row GEMM tiles per block
+        bounds = np.minimum(bounds, self.n_local)
+        lo = np.zeros((n_blocks + 1, W), np.int64)
+        for p in range(W):
+            lst = self._send_idx_host[int(self.send_off[p]): int(self.send_off[p + 1])]
+            lo[:, p] = np.searchsorted(lst, bounds, side="left")
+        return bounds, lo
 
     def ext_ids(self, rank: int):
         """global node id of every ext row"""
@@ -187,6 +204,7 @@ class CudaBackend:
 
         self.pack_ctas = int(os.environ.get("GNNB_HALO_PACK_CTAS", 0))
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_blocks = [torch.cuda.Event() for _ in range(16)]
         self._owned, self._opened = [], []
 
     def _p(self, t):
@@ -213,6 +231,12 @@ class CudaBackend:
     def comm_ctx(self):
         return self.torch.cuda.stream(self.comm)
 
+    def fork_block(self, b: int):
+        """the comm stream waits for what the compute stream has enqueued so far (block b done)"""
+        ev = self._ev_blocks[b % len(self._ev_blocks)]
+        ev.record(self.torch.cuda.current_stream())
+        self.comm.wait_event(ev)
+
     def partition_tables(self, coo_local, row_begin, n_local):
         e = int(coo_local.shape[0])
         ind, off = self.empty((n_local,), "int32"), self.empty((n_local,), "int32")
@@ -236,13 +260,13 @@ class CudaBackend:
         return n.value
 
     def gcn_layer_halo(self, x_ext, y_local, plan: HaloPlan, dinv_ext, W, b, skip, act, phase,
-                       emb_in, emb_out):
+                       emb_in, emb_out, row_begin: int = 0, row_count: int = 0):
         self._lib.check(self.lib.gnnb_gcn_conv_halo(
             plan.n_local, plan.n_ext, self._p(x_ext), self._p(y_local), self._p(plan.own_off),
             self._p(plan.own_cnt), self._p(plan.own_nbr), self._p(plan.halo_off),
             self._p(plan.halo_cnt), self._p(plan.halo_nbr), self._p(dinv_ext), self._p(W),
             self._p(b), self._p(skip), emb_in, emb_out, act, phase, 1 if plan.hub_rows else 0,
-            self._stream()))
+            int(row_begin), int(row_count), self._stream()))
 
     def halo_pack(self, x_own, F: int, plan: HaloPlan, dst_ptrs, max_ctas: int = 0):
         """dst_ptrs: one raw device address per peer (0 where nothing is sent)"""
@@ -251,6 +275,15 @@ class CudaBackend:
         dst = (C.c_void_p * W)(*[C.c_void_p(int(p)) for p in dst_ptrs])
         self._lib.check(self.lib.gnnb_halo_pack(self._p(x_own), F, F, self._p(plan.send_idx), off,
                                                 dst, W, max_ctas or self.pack_ctas, self._stream()))
+
+    def halo_pack_ranges(self, x_own, F: int, plan: HaloPlan, starts, counts, dst_ptrs):
+        """rows send_idx[starts[p] .. +counts[p]) -> dst_ptrs[p] (raw device addresses), every peer"""
+        W = len(dst_ptrs)
+        st = (C.c_int64 * W)(*[int(v) for v in starts])
+        cn = (C.c_int64 * W)(*[int(v) for v in counts])
+        dst = (C.c_void_p * W)(*[C.c_void_p(int(p)) for p in dst_ptrs])
+        self._lib.check(self.lib.gnnb_halo_pack_ranges(self._p(x_own), F, F, self._p(plan.send_idx), st,
+                                                       cn, dst, W, self.pack_ctas, self._stream()))
 
     def pack_rows(self, x_own, F: int, plan: HaloPlan, send):
         """send[send_off[p] + i] = x_own[send_idx[...]]: the rows of every peer, contiguous (NCCL)"""
@@ -340,6 +373,9 @@ class LargeGraphGCN:
         import os
 
         self.hub_l2_mb = int(os.environ.get("GNNB_HUB_L2_MB", 40)) if hub_l2_mb is None else hub_l2_mb
+        # p2p transport: a layer's owned rows are computed in this many blocks and the rows the
+        # peers need from a finished block are pushed while the next block is being computed
+        self.n_blocks = max(1, min(16, int(os.environ.get("GNNB_HALO_BLOCKS", 4))))
         params = model.named_parameter_arrays()
         names = list(params)
         nh = d["mlp_num_linear"]
@@ -379,11 +415,13 @@ class LargeGraphGCN:
         if self.hub_l2_mb > 0 and hasattr(B, "mark_hubs") and plan.n_ext * fmax * 4 > (96 << 20):
             plan.hub_rows = B.mark_hubs(plan.nbr_all, plan.n_ext, fmax * 4, self.hub_l2_mb << 20)
         self._setup_buffers(fmax)
+        self._blocks = plan.block_ranges(self.n_blocks) if self.transport == "p2p" else None
         self.stats = {
             "n_local": n_local, "halo_rows": plan.n_halo,
             "halo_frac_of_remote_rows": plan.n_halo / max(1, self.part.n_total - n_local),
             "send_rows": int(plan.send_off[-1]), "hub_rows": plan.hub_rows,
             "transport": self.transport, "autotune_ms": getattr(self, "autotune_ms", None),
+            "send_blocks": self.n_blocks if self.transport == "p2p" else 1,
         }
         return self
 
@@ -534,6 +572,8 @@ class LargeGraphGCN:
                 x_local = B.to_device(x_local.astype(np.float32))
             self.input_view().copy_(x_local)
         L = d["num_layers"]
+        pipelined = self.world > 1 and self.transport == "p2p" and self._blocks is not None
+        pushed = False    # layer k's halo is already on its way (pushed block by block during layer k-1)
         for k, (W, b) in enumerate(self.layers):
             fi, fo = self.dims[k], self.dims[k + 1]
             cur, nxt = self.ext[self._buf(k)], self.ext[self._buf(k + 1)]
@@ -542,13 +582,42 @@ class LargeGraphGCN:
             do_skip = bool(d["skip"]) and k != 0 and k != L - 1
             skip = cur[: n_local * fi] if do_skip else None
             args = (x_ext, y_local, plan, self.dinv_ext, W, b, skip, d["gnn_act"])
-            if self.world > 1:   # (every rank takes part in the exchange, even with an empty halo)
-                self._exchange(k, fi)
-                B.gcn_layer_halo(*args, 1, fi, fo)      # owned-source edges: overlaps the exchange
-                self._arrived()
-                B.gcn_layer_halo(*args, 2, fi, fo)      # halo-source edges, normalise, transform
-            else:
+            if self.world == 1:
                 B.gcn_layer_halo(*args, 3, fi, fo)
+            else:   # (every rank takes part in the exchange, even with an empty halo)
+                if pushed:
+                    self._arrived()
+                    phase = 3
+                else:
+                    self._exchange(k, fi)
+                    B.gcn_layer_halo(*args, 1, fi, fo)      # owned-source edges: overlaps the exchange
+                    self._arrived()
+                    phase = 2                               # halo-source edges, normalise, transform
+                pushed = False
+                if pipelined and k < L - 1:
+                    # block by block; the rows the peers need from a finished block travel (comm
+                    # stream, NVLink stores into the peers' layer-(k+1) input buffers) while the
+                    # next block is computed
+                    bounds, lo = self._blocks
+                    self.epoch += 1
+                    for blk in range(len(bounds) - 1):
+                        r0, r1 = int(bounds[blk]), int(bounds[blk + 1])
+                        if r1 > r0:
+                            B.gcn_layer_halo(*args, phase, fi, fo, r0, r1 - r0)
+                        B.fork_block(blk)
+                        with B.comm_ctx():
+                            starts = [int(plan.send_off[p] + lo[blk][p]) for p in range(self.world)]
+                            counts = [int(lo[blk + 1][p] - lo[blk][p]) for p in range(self.world)]
+                            dst = [0 if p == self.rank or counts[p] == 0 else
+                                   self._peer_ext[self._buf(k + 1)][p]
+                                   + 4 * fo * (n_local + self._row_at_peer[p] + int(lo[blk][p]))
+                                   for p in range(self.world)]
+                            B.halo_pack_ranges(y_local, fo, plan, starts, counts, dst)
+                    with B.comm_ctx():
+                        B.halo_signal(self._peer_flag, self.epoch)
+                    pushed = True
+                else:
+                    B.gcn_layer_halo(*args, phase, fi, fo)
             if capture is not None and capture[0] == k:
                 self.captured = y_local[: min(capture[1], n_local) * fo].view(-1, fo).clone()
         emb = self.ext[self._buf(L)][: n_local * self.dims[L]].view(n_local, self.dims[L])

@@ -240,6 +240,12 @@ int gnnb_pool_partial(const float *x, int64_t n, int F, float *out, void *stream
  * for one NVLink direction and leaves the rest of every SM to the kernel running beside it. */
 int gnnb_halo_pack(const float *x, int ldx, int F, const int32_t *send_idx, const int64_t *send_off,
                    float *const *dst, int n_peers, int max_ctas, void *stream);
+/* the same with an explicit sub-range per peer: rows send_idx[start[p] .. start[p] + count[p]) go to
+ * dst[p][0 .. count[p]) -- one block of owned rows at a time, so the sends of a finished block
+ * travel while the next block is still being computed */
+int gnnb_halo_pack_ranges(const float *x, int ldx, int F, const int32_t *send_idx,
+                          const int64_t *start, const int64_t *count, float *const *dst, int n_peers,
+                          int max_ctas, void *stream);
 /* system-scope release store of `value` to peer_flags[p] (HOST array of n_peers device pointers,
  * NULL entries skipped): "this rank's rows for epoch `value` have landed" */
 int gnnb_halo_signal(uint64_t *const *peer_flags, int n_peers, uint64_t value, void *stream);
@@ -263,13 +269,15 @@ int gnnb_mark_hub_sources(int32_t *neighbor_table, int num_entries, int num_sour
  * counts per owned row, neighbor entries = ext indices).  phase 1: aggregate the owned-source
  * edges (needs no halo: overlaps the exchange); phase 2: add the halo-source edges, normalise
  * (lib:1246-1278) and transform, y_local[n_local][emb_out] = act(agg.W^T + b (+ skip_local));
- * phase 3: both.  dinv_ext[n_ext] = 1/sqrt(1 + in-degree) of every ext row. */
+ * phase 3: both.  dinv_ext[n_ext] = 1/sqrt(1 + in-degree) of every ext row.  row_begin /
+ * row_count restrict the call to one block of owned rows (row_count <= 0: all of them); every
+ * pointer still addresses row 0. */
 int gnnb_gcn_conv_halo(int n_local, int n_ext, const float *x_ext, float *y_local,
                        const int32_t *own_offsets, const int32_t *own_counts, const int32_t *own_nbr,
                        const int32_t *halo_offsets, const int32_t *halo_counts,
                        const int32_t *halo_nbr, const float *dinv_ext, const float *weight,
                        const float *bias, const float *skip_local, int emb_in, int emb_out, int act,
-                       int phase, int hub_bit, void *stream);
+                       int phase, int hub_bit, int row_begin, int row_count, void *stream);
 
 #ifdef __cplusplus
 }

@@ -51,7 +51,9 @@ class NumpyBackend:
     def pack_rows(self, x_own, F, plan, send):
         send[:] = x_own.view(-1, F)[plan.send_idx.long()]
 
-    def gcn_layer_halo(self, x_ext, y_local, plan, dinv_ext, W, b, skip, act, phase, fi, fo):
+    def gcn_layer_halo(self, x_ext, y_local, plan, dinv_ext, W, b, skip, act, phase, fi, fo,
+                       row_begin=0, row_count=0):
+        assert row_count in (0, plan.n_local), "the checker backend runs whole layers (nccl transport)"
         """numpy/torch restatement of gnnb_gcn_conv_halo on the ext index space"""
         import torch
         n_local = plan.n_local
