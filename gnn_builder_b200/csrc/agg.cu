@@ -360,7 +360,7 @@ int launch_lpr(const AggArgs &a, int lpr, int grid, cudaStream_t s)
 template <int VEC, int MODE>
 void launch_heavy_mode(const AggArgs &a, cudaStream_t s)
 {
-    const int cap = kNumSMs * 8;   // 8 resident CTAs per SM, grid-stride beyond
+    const int cap = a.short_ctas ? (1 << 30) : kNumSMs * 8;   // 8 resident CTAs per SM, grid-stride beyond
     const int g1 = min((a.heavy_chunks + 7) / 8, cap), g2 = min(a.n_heavy, cap);
     agg_heavy_chunk_kernel<VEC, MODE><<<g1, 256, 0, s>>>(a);
     agg_heavy_combine_kernel<VEC, MODE><<<g2, 256, sizeof(float) * 8 * (size_t)a.F, s>>>(a);
@@ -402,7 +402,8 @@ int launch_agg(const AggArgs &a_in, bool strict, cudaStream_t s, int *launches)
     while (lpr < 32 && lpr * vec < a.F) lpr *= 2;
     const int rows_per_block = 8 * (32 / lpr);
     int64_t grid64 = ceil_div64(a.n, rows_per_block);
-    const int64_t cap = (int64_t)kNumSMs * 8 * 4;  // 8 resident CTAs/SM x 4 waves, grid-stride
+    const int64_t cap = a.short_ctas ? (int64_t)1 << 30
+                                     : (int64_t)kNumSMs * 8 * 4;  // 8 resident CTAs/SM x 4 waves, grid-stride
     int grid = (int)(grid64 < cap ? grid64 : cap);
     int rc;
     if (vec == 4)

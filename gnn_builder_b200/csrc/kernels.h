@@ -121,6 +121,9 @@ struct AggArgs {
                            // rows' owned-source or halo-source edges); in_deg still feeds the mean
     int accumulate;        // start every row sum from what `out` already holds (second CSR part)
     int no_finish;         // store the plain partial sum: no self term / normalisation (first part)
+    int short_ctas;        // 1: one pass per CTA instead of a capped grid-stride grid, so that the CTAs
+                           // of a higher-priority kernel (the halo pack on the exchange stream) are
+                           // placed as these retire instead of waiting for the whole kernel
     int hub_bit;           // 1: bit 31 of a neighbor entry marks a hub source (high out-degree);
                            // its row is loaded with an L2 evict_last policy, every other row with
                            // evict_first, so the hub rows stay resident in the 126 MB L2

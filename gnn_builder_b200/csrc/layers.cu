@@ -901,6 +901,8 @@ extern "C" int gnnb_gcn_conv_halo(int n_local, int n_ext, const float *x_ext, fl
     a.ldo = lda; a.dinv = dinv_ext; a.n = row_count;
     a.row_base = row_begin;      // owned row v is ext row v: self row and dinv are indexed v + row_base
     a.heavy_threshold = heavy_threshold(); a.hub_bit = hub_bit ? 1 : 0;
+    // block mode (opt-in): the halo pack of the previous row block runs beside these kernels
+    a.short_ctas = row_count < n_local ? 1 : 0;
     auto cache_of = [&](const int32_t *lengths) -> HeavyCache & {
         for (HeavyCache &hc : g_part.part)
             if (hc.key == lengths && hc.n == row_count) return hc;

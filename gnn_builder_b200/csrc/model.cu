@@ -40,6 +40,25 @@ bool is_device_pointer(const void *p)
 
 namespace {
 
+// Every entry point runs on the handle's device and leaves the caller's current device as it
+// found it (a host thread that drives several GPUs, or torch's notion of the current device,
+// must not be switched behind its back).
+struct DeviceScope {
+    int prev = -1;
+    explicit DeviceScope(int dev)
+    {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != dev && cudaSetDevice(dev) == cudaSuccess) prev = cur;
+        else if (cur != dev) cudaGetLastError();
+    }
+    ~DeviceScope()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceScope(const DeviceScope &) = delete;
+    DeviceScope &operator=(const DeviceScope &) = delete;
+};
+
 void add_param(gnnb_model *m, const std::string &name, std::vector<int> shape)
 {
     ParamSlot p;
@@ -192,7 +211,7 @@ extern "C" int gnnb_model_create(const gnnb_model_desc *desc, int device, gnnb_m
     GNNB_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0) GNNB_CUDA(cudaGetDevice(&device));
     GNNB_REQUIRE(device < ndev, "no such CUDA device");
-    GNNB_CUDA(cudaSetDevice(device));
+    DeviceScope on_device(device);
     gnnb_model *m = new gnnb_model();
     m->d = d;
     m->device = device;
@@ -218,7 +237,7 @@ extern "C" int gnnb_model_create(const gnnb_model_desc *desc, int device, gnnb_m
 extern "C" int gnnb_model_destroy(gnnb_model_t *m)
 {
     if (!m) return GNNB_OK;
-    cudaSetDevice(m->device);
+    DeviceScope on_device(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     fused_release(m);
     fused_tc_release(m);
@@ -288,7 +307,7 @@ extern "C" int gnnb_model_finalize(gnnb_model_t *m)
             set_error("parameter not set: " + p.name);
             return GNNB_ERR_STATE;
         }
-    GNNB_CUDA(cudaSetDevice(m->device));
+    DeviceScope on_device(m->device);
     const gnnb_model_desc &d = m->d;
     Packer pk;
     std::vector<PendingLinear> head_p;
@@ -407,7 +426,7 @@ static int edge_flag_check(gnnb_model_t *m);
 extern "C" int gnnb_model_synchronize(gnnb_model_t *m)
 {
     GNNB_REQUIRE(m != nullptr, "null model");
-    GNNB_CUDA(cudaSetDevice(m->device));
+    DeviceScope on_device(m->device);
     GNNB_CUDA(cudaStreamSynchronize(m->stream));
     if (m->last_path == GNNB_PATH_LAYERWISE) GNNB_TRY(edge_flag_check(m));
     if (m->last_path == GNNB_PATH_FUSED) {
@@ -649,7 +668,6 @@ static int check_ready(gnnb_model_t *m)
         set_error("gnnb_model_finalize() has not been called");
         return GNNB_ERR_STATE;
     }
-    GNNB_CUDA(cudaSetDevice(m->device));
     return GNNB_OK;
 }
 
@@ -702,7 +720,9 @@ extern "C" int gnnb_model_run_batch_async(gnnb_model_t *m, const float *x, const
                                           float *out, void *stream)
 {
     GNNB_TRY(check_ready(m));
+    DeviceScope on_device(m->device);
     GNNB_REQUIRE(n_graphs >= 0 && total_nodes >= 0 && total_edges >= 0, "negative size");
+    GNNB_REQUIRE(node_ptr != nullptr && edge_ptr != nullptr && out != nullptr, "null argument");
     if (n_graphs == 0) return GNNB_OK;
     GNNB_REQUIRE(is_device_pointer(x) || total_nodes == 0, "run_batch_async needs device pointers");
     cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
@@ -727,6 +747,7 @@ extern "C" int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32
                                     float *out)
 {
     GNNB_TRY(check_ready(m));
+    DeviceScope on_device(m->device);
     GNNB_REQUIRE(n_graphs >= 0, "negative n_graphs");
     if (n_graphs == 0) return GNNB_OK;
     GNNB_REQUIRE(node_ptr && edge_ptr && out, "null argument");
@@ -981,6 +1002,7 @@ extern "C" int gnnb_model_run_graph(gnnb_model_t *m, const float *node_features,
 extern "C" int gnnb_model_get_node_embeddings(gnnb_model_t *m, float *dst, int64_t total_nodes)
 {
     GNNB_TRY(check_ready(m));
+    DeviceScope on_device(m->device);
     GNNB_REQUIRE(dst != nullptr, "null destination");
     if (m->last_path != GNNB_PATH_LAYERWISE || m->last_emb == nullptr ||
         total_nodes != m->last_emb_rows) {
@@ -1008,7 +1030,7 @@ extern "C" int gnnb_model_set_profile(gnnb_model_t *m, int on)
 extern "C" int gnnb_model_profile_read(gnnb_model_t *m, float *ms, int *counts)
 {
     GNNB_REQUIRE(m != nullptr && ms != nullptr && counts != nullptr, "null argument");
-    GNNB_CUDA(cudaSetDevice(m->device));
+    DeviceScope on_device(m->device);
     GNNB_CUDA(cudaStreamSynchronize(m->stream));
     GNNB_CUDA(cudaDeviceSynchronize());
     for (int i = 0; i < PROF_NCAT; i++) { ms[i] = 0.0f; counts[i] = 0; }

@@ -373,9 +373,13 @@ class LargeGraphGCN:
         import os
 
         self.hub_l2_mb = int(os.environ.get("GNNB_HUB_L2_MB", 40)) if hub_l2_mb is None else hub_l2_mb
-        # p2p transport: a layer's owned rows are computed in this many blocks and the rows the
-        # peers need from a finished block are pushed while the next block is being computed
-        self.n_blocks = max(1, min(16, int(os.environ.get("GNNB_HALO_BLOCKS", 4))))
+        # Opt-in (GNNB_HALO_BLOCKS = 2..16, p2p transport): a layer's owned rows are computed in
+        # that many blocks and the rows the peers need from a finished block are pushed while the
+        # next block is computed.  Measured at 2 GPUs on the 2M-node graph it does not pay (blocks
+        # 1 / 4 / 8: 5.35 / 5.46 / 5.81 ms per step against 5.21 ms for the default scheme below --
+        # smaller kernels, and the pack's CTAs queue behind the aggregation's), so the default
+        # keeps one exchange per layer, overlapped with the aggregation of the owned-source edges.
+        self.n_blocks = max(0, min(16, int(os.environ.get("GNNB_HALO_BLOCKS", 0))))
         params = model.named_parameter_arrays()
         names = list(params)
         nh = d["mlp_num_linear"]
@@ -415,13 +419,14 @@ class LargeGraphGCN:
         if self.hub_l2_mb > 0 and hasattr(B, "mark_hubs") and plan.n_ext * fmax * 4 > (96 << 20):
             plan.hub_rows = B.mark_hubs(plan.nbr_all, plan.n_ext, fmax * 4, self.hub_l2_mb << 20)
         self._setup_buffers(fmax)
-        self._blocks = plan.block_ranges(self.n_blocks) if self.transport == "p2p" else None
+        self._blocks = (plan.block_ranges(self.n_blocks)
+                        if self.transport == "p2p" and self.n_blocks >= 2 else None)
         self.stats = {
             "n_local": n_local, "halo_rows": plan.n_halo,
             "halo_frac_of_remote_rows": plan.n_halo / max(1, self.part.n_total - n_local),
             "send_rows": int(plan.send_off[-1]), "hub_rows": plan.hub_rows,
             "transport": self.transport, "autotune_ms": getattr(self, "autotune_ms", None),
-            "send_blocks": self.n_blocks if self.transport == "p2p" else 1,
+            "send_blocks": self.n_blocks if self._blocks is not None else 1,
         }
         return self
 

@@ -112,8 +112,13 @@ int gnnb_model_run_graph(gnnb_model_t *m, const float *node_features, const int3
 int gnnb_model_run_batch(gnnb_model_t *m, const float *x, const int32_t *edge_list,
                          const int64_t *node_ptr, const int64_t *edge_ptr, int n_graphs,
                          float *out);
-/* Device buffers only; enqueues on `stream` (a cudaStream_t; NULL = the handle's stream) and
- * returns without synchronising.  total_nodes/total_edges = node_ptr[G]/edge_ptr[G]. */
+/* Device buffers only; enqueues on `stream` (a cudaStream_t; NULL = the handle's stream).
+ * total_nodes/total_edges = node_ptr[G]/edge_ptr[G].  The fused path returns without
+ * synchronising.  The layerwise path may block: scratch buffers grow with cudaMalloc the first
+ * time a batch size is seen, and a batch of large graphs (> 50 000 nodes on average) reads two
+ * counters back (heavy-row and hub-row selection).  Errors the device detects (an edge endpoint
+ * outside its graph, a tile over capacity) are reported by gnnb_model_synchronize.  Every entry
+ * point leaves the caller's current CUDA device unchanged. */
 int gnnb_model_run_batch_async(gnnb_model_t *m, const float *x, const int32_t *edge_list,
                                const int64_t *node_ptr, const int64_t *edge_ptr, int n_graphs,
                                int64_t total_nodes, int64_t total_edges, float *out, void *stream);

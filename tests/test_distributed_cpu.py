@@ -204,3 +204,38 @@ def test_shard_ranges_balance_and_cover():
         assert ((p[:, 1] >= lo) & (p[:, 1] < hi)).all()
     with pytest.raises(ValueError):
         RowPartition(65, 4)
+
+
+def test_halo_plan_block_ranges():
+    """the per-block send ranges of the pipelined halo push: every peer's list is cut at the block
+    bounds, blocks are whole 128-row GEMM tiles, and together they cover each list exactly once"""
+    sys.path.insert(0, str(ROOT))
+    import torch
+
+    from gnn_builder_b200.data import make_powerlaw_graph
+    from gnn_builder_b200.distributed import HaloPlan, RowPartition
+
+    n, world, rank = 4096, 4, 1
+    _, coo = make_powerlaw_graph(n, 6, 4, seed=3, max_degree=200)
+    part = RowPartition(n, world)
+    loc = part.local_edges(coo, rank)
+    r0, r1 = part.rows(rank)
+    dst = loc[:, 1] - r0
+    order = np.argsort(dst, kind="stable")
+    ind = torch.from_numpy(np.bincount(dst, minlength=part.n_local).astype(np.int32))
+    plan = HaloPlan(ind, torch.from_numpy(loc[order, 0].copy()), rank, part, dist=None)
+    # pretend peers 0, 2, 3 asked for sorted subsets of the owned rows
+    rng = np.random.default_rng(0)
+    lists = [np.sort(rng.choice(part.n_local, size=k, replace=False)) for k in (300, 0, 517, 64)]
+    plan.send_counts = [len(x) for x in lists]
+    plan.send_off = np.concatenate([[0], np.cumsum(plan.send_counts)]).astype(np.int64)
+    plan.send_idx = torch.from_numpy(np.concatenate(lists).astype(np.int32))
+    for nb in (1, 3, 4, 16):
+        bounds, lo = plan.block_ranges(nb)
+        assert bounds[0] == 0 and bounds[-1] == part.n_local and (np.diff(bounds) >= 0).all()
+        assert all(b % 128 == 0 for b in bounds[1:-1])
+        for p, lst in enumerate(lists):
+            assert lo[0][p] == 0 and lo[-1][p] == len(lst)
+            for b in range(nb):
+                piece = lst[lo[b][p]: lo[b + 1][p]]
+                assert ((piece >= bounds[b]) & (piece < bounds[b + 1])).all()
