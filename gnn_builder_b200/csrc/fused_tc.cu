@@ -1159,17 +1159,22 @@ __device__ __forceinline__ int pna_layer_workers(const TcParams &p, Misc &ms, in
                     v[24 + j] = var * rsqrtf(var);                    // sqrt(var), 2 ulp; NaN for in-degree 0
                 }
                 PNA_PHASE(11)
-                // the previous group's GEMMs must have finished reading the A operand
-                if (g > 0 && h == 0) wait_done_both(ms, done_cnt);
+                // the previous group's MMAs that read THIS half of the A operand must be done (the
+                // issuer commits done[h] per half: atom-major order)
+                if (g > 0) {
+                    tc::mbar_wait(&ms.bar_done[h], done_cnt & 1);
+                    tc::tc_fence_after();
+                }
                 PNA_PHASE(12)
                 split_store(tmem_base, lane_base, 64 * h + 32 * hh, v);
                 tc::tmem_st_wait();
-            } else if (g > 0 && h == 0) {
-                wait_done_both(ms, done_cnt);
+            } else if (g > 0) {
+                tc::mbar_wait(&ms.bar_done[h], done_cnt & 1);
             }
             handoff_half(ms, h);
             PNA_PHASE(13)
         }
+        if (g > 0) done_cnt++;
     }
     wait_done_both(ms, done_cnt);
     PNA_PHASE(12)
@@ -1229,6 +1234,79 @@ __device__ __forceinline__ int pna_layer_workers(const TcParams &p, Misc &ms, in
 #undef PNA_PHASE
 }
 
+// The three GEMMs of one feature group (D_id += s.W_id^T, D_amp (+)= s.W_amp^T, D_att (+)= s.W_att^T)
+// issued ATOM-MAJOR: all MMAs that read A-operand half 0 (K' [0, 64)) first, then done[0] is
+// committed, then half 1 -- so the workers may overwrite half 0 with the next group's statistics
+// while the tensor pipe is still busy with half 1.  Unit order in the weight stream: per atom,
+// per linear (id, amp, att): hi unit, mid unit.
+__device__ __forceinline__ void pna_group_issue(Misc &ms, uint32_t ring, uint32_t &cons, uint32_t tmem_base,
+                                                const PnaLayer &P, int g, uint32_t &ready_cnt)
+{
+    const bool leader = tc::elect_one();
+    const uint32_t slot_log2 = ms.slot_log2, slot_stride = ms.slot_stride;
+    const uint32_t idesc = tc::make_idesc_bf16(TM, P.foP, 0);
+    const uint32_t ahi = tmem_base + TM_AHI, amid = tmem_base + TM_ALO;
+    const int KA = P.gid[g].KA;          // 1 (16-feature group, K' = 64) or 2
+    for (int ka = 0; ka < 2; ka++) {
+        tc::mbar_wait(&ms.bar_ready[ka], ready_cnt & 1);
+        tc::tc_fence_after();
+        if (ka < KA) {
+            const uint32_t col = (uint32_t)(ka * 32);
+#pragma unroll 1
+            for (int lin = 0; lin < 3; lin++) {
+                const uint32_t tmem_d = tmem_base + (uint32_t)(lin * P.foP);
+                // D_id holds the self block already; D_amp / D_att start with the first group
+                const uint32_t first = (lin == 0 || g > 0 || ka > 0) ? 1u : 0u;
+                for (int part = 0; part < 2; part++) {     // hi unit, then mid unit
+                    const uint32_t sl = cons & ((1u << slot_log2) - 1u);
+                    tc::mbar_wait(&ms.bar_full[sl], (cons >> slot_log2) & 1);
+                    tc::tc_fence_after();
+                    const uint64_t bd = tc::make_desc(ring + sl * slot_stride);
+                    if (leader) {
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; k4++) {
+                            if (part == 0) {
+                                tc::mma_bf16_ts(tmem_d, ahi + col + 8 * k4, bd + (uint64_t)(2 * k4), idesc,
+                                                k4 == 0 ? first : 1u);
+                                tc::mma_bf16_ts(tmem_d, amid + col + 8 * k4, bd + (uint64_t)(2 * k4), idesc, 1u);
+                            } else {
+                                tc::mma_bf16_ts(tmem_d, ahi + col + 8 * k4, bd + (uint64_t)(2 * k4), idesc, 1u);
+                            }
+                        }
+                        tc::mma_commit(&ms.bar_empty[sl]);
+                    }
+                    cons++;
+                }
+            }
+        }
+        if (leader) tc::mma_commit(&ms.bar_done[ka]);
+    }
+    ready_cnt++;
+}
+// the weight units of one group in that order (producer warp)
+__device__ __forceinline__ void pna_group_produce(Misc &ms, uint32_t ring, uint32_t &prod, const PnaLayer &P,
+                                                  int g, size_t copy_off, bool leader)
+{
+    const uint32_t slot_log2 = ms.slot_log2, slot_stride = ms.slot_stride;
+    const uint32_t bytes = (uint32_t)P.foP * tc::ROW_BYTES;
+    const int KA = P.gid[g].KA;
+    for (int ka = 0; ka < KA; ka++)
+        for (int lin = 0; lin < 3; lin++) {
+            const TLinear &L = lin == 0 ? P.gid[g] : lin == 1 ? P.gamp[g] : P.gatt[g];
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(L.img) + copy_off +
+                                       (size_t)ka * 2 * bytes;
+            for (int part = 0; part < 2; part++) {
+                const uint32_t sl = prod & ((1u << slot_log2) - 1u), use = prod >> slot_log2;
+                if (use > 0) tc::mbar_wait(&ms.bar_empty[sl], (use - 1) & 1);
+                if (leader) {
+                    tc::mbar_expect_tx(&ms.bar_full[sl], bytes);
+                    tc::bulk_g2s_addr(ring + sl * slot_stride, src + (size_t)part * bytes, bytes, &ms.bar_full[sl]);
+                }
+                prod++;
+            }
+        }
+}
+
 // the same layer on the MMA-issuing warp
 __device__ __forceinline__ void pna_layer_issue(const TcParams &p, Misc &ms, int l, uint32_t ring,
                                                 uint32_t &cons, uint32_t tmem_base, uint32_t &ready_cnt)
@@ -1238,11 +1316,7 @@ __device__ __forceinline__ void pna_layer_issue(const TcParams &p, Misc &ms, int
     gemm_issue(ms, ring, cons, tmem_base, c_att, P.pa, false, ready_cnt, true, false);
     gemm_issue(ms, ring, cons, tmem_base, c_b, P.pb, false, ready_cnt, false, false);
     gemm_issue(ms, ring, cons, tmem_base, 0u, P.ps, false, ready_cnt, false, true);
-    for (int g = 0; g < P.ng; g++) {
-        gemm_issue(ms, ring, cons, tmem_base, 0u, P.gid[g], true, ready_cnt, true, false);
-        gemm_issue(ms, ring, cons, tmem_base, (uint32_t)P.foP, P.gamp[g], g > 0, ready_cnt, false, false);
-        gemm_issue(ms, ring, cons, tmem_base, c_att, P.gatt[g], g > 0, ready_cnt, false, true);
-    }
+    for (int g = 0; g < P.ng; g++) pna_group_issue(ms, ring, cons, tmem_base, P, g, ready_cnt);
     gemm_issue(ms, ring, cons, tmem_base, c_b, P.pl, false, ready_cnt);
 }
 // ... and the weight units it consumes, in the same order (producer warp)
@@ -1253,11 +1327,7 @@ __device__ __forceinline__ void pna_layer_produce(const TcParams &p, Misc &ms, i
     produce_linear(ms, ring, prod, P.pa, copy_off, leader);
     produce_linear(ms, ring, prod, P.pb, copy_off, leader);
     produce_linear(ms, ring, prod, P.ps, copy_off, leader);
-    for (int g = 0; g < P.ng; g++) {
-        produce_linear(ms, ring, prod, P.gid[g], copy_off, leader);
-        produce_linear(ms, ring, prod, P.gamp[g], copy_off, leader);
-        produce_linear(ms, ring, prod, P.gatt[g], copy_off, leader);
-    }
+    for (int g = 0; g < P.ng; g++) pna_group_produce(ms, ring, prod, P, g, copy_off, leader);
     produce_linear(ms, ring, prod, P.pl, copy_off, leader);
 }
 #endif   // GNNB_TC_BF2
