@@ -1009,7 +1009,7 @@ __device__ __forceinline__ void pna_build_nbr(const uint32_t *CNT, int row, int 
     nb.lo = 0ull; nb.hi = 0ull; nb.n = 0;
     const uint32_t *cw = CNT + row * (TM / 4);
     for (int w = g_r0 >> 2; w < (g_r1 + 3) >> 2; w++) {
-        const uint32_t word = cw[w];
+        const uint32_t word = cw[(w + row) & 31];      // (skewed layout, see the edge pass)
         if (word == 0u) continue;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
@@ -1039,7 +1039,7 @@ __device__ __forceinline__ void pna_for_each_neighbor(const PnaNbr &nb, const ui
     }
     const uint32_t *cw = CNT + row * (TM / 4);
     for (int w = g_r0 >> 2; w < (g_r1 + 3) >> 2; w++) {
-        uint32_t word = cw[w];
+        uint32_t word = cw[(w + row) & 31];
         if (word == 0u) continue;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
@@ -1159,22 +1159,20 @@ __device__ __forceinline__ int pna_layer_workers(const TcParams &p, Misc &ms, in
                     v[24 + j] = var * rsqrtf(var);                    // sqrt(var), 2 ulp; NaN for in-degree 0
                 }
                 PNA_PHASE(11)
-                // the previous group's MMAs that read THIS half of the A operand must be done (the
-                // issuer commits done[h] per half: atom-major order)
-                if (g > 0) {
-                    tc::mbar_wait(&ms.bar_done[h], done_cnt & 1);
-                    tc::tc_fence_after();
-                }
+                // the MMAs that read THIS half of the A operand must be done: the previous group's
+                // (the issuer commits done[h] per half: atom-major order), for group 0 the S GEMM
+                tc::mbar_wait(&ms.bar_done[h], done_cnt & 1);
+                tc::tc_fence_after();
                 PNA_PHASE(12)
                 split_store(tmem_base, lane_base, 64 * h + 32 * hh, v);
                 tc::tmem_st_wait();
-            } else if (g > 0) {
+            } else {
                 tc::mbar_wait(&ms.bar_done[h], done_cnt & 1);
             }
             handoff_half(ms, h);
             PNA_PHASE(13)
         }
-        if (g > 0) done_cnt++;
+        done_cnt++;
     }
     wait_done_both(ms, done_cnt);
     PNA_PHASE(12)
@@ -1313,8 +1311,10 @@ __device__ __forceinline__ void pna_layer_issue(const TcParams &p, Misc &ms, int
 {
     const PnaLayer &P = p.pna[l];
     const uint32_t c_att = 2u * (uint32_t)P.foP, c_b = 3u * (uint32_t)P.foP;
+    // A_u and B_v first (the workers wait for these two), S as a phase of its own: it is only needed
+    // by the combine pass, so it runs while the workers copy A_u and gather group 0's statistics
     gemm_issue(ms, ring, cons, tmem_base, c_att, P.pa, false, ready_cnt, true, false);
-    gemm_issue(ms, ring, cons, tmem_base, c_b, P.pb, false, ready_cnt, false, false);
+    gemm_issue(ms, ring, cons, tmem_base, c_b, P.pb, false, ready_cnt, false, true);
     gemm_issue(ms, ring, cons, tmem_base, 0u, P.ps, false, ready_cnt, false, true);
     for (int g = 0; g < P.ng; g++) pna_group_issue(ms, ring, cons, tmem_base, P, g, ready_cnt);
     gemm_issue(ms, ring, cons, tmem_base, c_b, P.pl, false, ready_cnt);
@@ -1598,7 +1598,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fused_tc_kernel(const __grid_c
                     } else {
                         const int ls = sd.x + b, ld = sd.y + b;
                         const uint32_t sh = 8u * (uint32_t)(ls & 3);
-                        const uint32_t old = atomicAdd(&CNT[ld * (TM / 4) + (ls >> 2)], 1u << sh);
+                        // PNA reads the counters row by row (thread per row): word w of row d sits at
+                        // position (w + d) & 31 so that the 32 rows of a warp hit 32 different banks
+                        const int wpos = conv == GNNB_CONV_PNA ? (((ls >> 2) + ld) & 31) : (ls >> 2);
+                        const uint32_t old = atomicAdd(&CNT[ld * (TM / 4) + wpos], 1u << sh);
                         if (((old >> sh) & 0xffu) == 0xffu) atomicExch(p.error_flag, 1);
                         atomicAdd(&ms.deg[ld], 1);
                     }
