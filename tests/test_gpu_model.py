@@ -327,6 +327,26 @@ def test_fused_tc_pna_variants(gnnb, orc, variant):
         assert rel_err(out, ref) < TOL, (variant, rel_err(out, ref))
 
 
+def test_pna_beyond_the_fused_limits_runs_layerwise(gnnb, orc):
+    """PNA wider than the fused kernel's tensor-memory budget (hidden 128 > 96), or with more input
+    features than output features, takes the layerwise kernels under AUTO -- same results"""
+    import dataclasses
+
+    from conftest import workload_by_name
+    from gnn_builder_b200.models import build_model
+
+    for over in (dict(hidden_dim=128), dict(hidden_dim=32, in_dim=40)):
+        w = dataclasses.replace(workload_by_name("c4_pna_lipo"), **over)
+        model = build_model(w, pna_delta=w.pna_delta, seed=5)
+        params = model.named_parameter_arrays()
+        batch = gnnb.make_molecular_batch(300, w.mu_nodes, w.mu_edges, w.in_dim, seed=6)
+        ref = orc.model_forward_batch(model.describe(), list(params.values()), batch)
+        with gnnb.Engine(model) as eng:
+            out = eng.run(batch)
+            assert eng.last_kernel == "layerwise", (over, eng.last_kernel)
+            assert rel_err(out, ref) < TOL, over
+
+
 def test_fused_pna_zero_in_degree_and_multi_edges(gnnb, orc):
     """the fused PNA path keeps the reference's semantics per graph: std = NaN for in-degree 0
     (0/0, lib:702) -- which ReLU turns into 0 and sigmoid keeps --, duplicate edges count twice in
