@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call 13 (1 GPU): the record -- smoke, full bench (+ reference arm), ncu captures,
+# Round-2 record run on ONE GPU (gpurun --timeout 2400 -- bash tools/record_run_1gpu.sh): the record -- smoke, full bench (+ reference arm), ncu captures,
 # launch list, compute-sanitizer (default build, then the per-thread-arrival debug build)
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call 16 (8 GPUs): what the driver runs at round end -- multi-GPU tests, then the
+# Round-2 record run on an 8-GPU box (gpurun --gpus 8 -- bash tools/record_run_ngpu.sh): what the driver runs at round end -- multi-GPU tests, then the
 # default bench at N = 8, 4, 2 (C2 + extra.c4 + extra.c5 in one line each)
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
