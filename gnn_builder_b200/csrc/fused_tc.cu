@@ -3,52 +3,57 @@
 //
 //   aggregation     AGG = ADJ . X       kind::f16 MMAs.  ADJ is the tile's 128x128 block-diagonal
 //                                       matrix of in-edge multiplicities (bf16, exact), X the layer
-//                                       input split into three bf16 planes (hi+mid+lo = 24 bits,
-//                                       tc.cuh), fp32 accumulation in tensor memory: fp32-grade.
-//   node transform  D = A . W^T         kind::tf32 MMAs, error-compensated 3xTF32 (tc.cuh), the A
-//                                       operand (hi/lo parts) read from TENSOR MEMORY, the weight
-//                                       atoms streamed L2 -> shared memory with cp.async.bulk.
+//                                       input as two bf16 planes (hi + mid, both rounded to
+//                                       nearest), fp32 accumulation in tensor memory.
+//   node transform  D = A . W^T         "bf16x2": every fp32 operand v ~= hi + mid (two bf16 values,
+//                                       |v - hi - mid| <= 2^-18 |v|) and a product is
+//                                       A_hi.W_hi + A_mid.W_hi + A_hi.W_mid as three kind::f16 MMAs
+//                                       of K = 16.  The A operand is read from TENSOR MEMORY as PACKED
+//                                       bf16 pairs (K elements 2j, 2j+1 in the low / high half of
+//                                       column j: layout pinned by tools/tmem_bf16_probe.py,
+//                                       profiles/r2_tmem_bf16_layout_probe.txt); the weight atoms
+//                                       stream L2 -> shared memory with cp.async.bulk.
+// The north star asks for <= 1e-4 relative: round 1's 3xTF32 (three kind::tf32 MMAs of K = 8 per
+// product, ~2^-21) measured 5e-6 and spent twice the tensor-pipe time and weight bytes; bf16x2
+// measures 9.6e-6 worst over all configs and variants (tools/fused_error.py).  -DGNNB_TC_BF2=0
+// rebuilds the 3xTF32 kernel (three planes, A_hi / A_lo as fp32 cells) for A/B runs; the comments
+// below describe the default.
 //
 // Every other step is "thread per row": the thread that owns TMEM lane r (row r of the tile) moves
 // its row accumulator -> registers (tcgen05.ld) -> bias / skip / activation / GCN-SAGE scaling ->
 // either back to tensor memory as the next A operand (tcgen05.st) or to the bf16 planes of the next
-// layer input (conflict-free 16-byte shared-memory stores).  No gather loops, no neighbor tables,
-// no shared-memory traffic for activations, and no bank conflicts anywhere on the layer path.
+// layer input (16-byte shared-memory stores).  GCN / GIN / SAGE: no gather loops, no neighbor
+// tables, no shared-memory traffic for activations.
 //
-// Per CTA (one per SM, 256 threads, 128-row tile of packed graphs):
+// Per CTA (one per SM; 8 worker warps + a weight-producer warp + an MMA-issuing warp; a tile =
+// up to 128 rows of whole graphs):
 //   shared memory   ADJ  32 KB   bf16 [dst][src], K-major SWIZZLE_128B (A operand of the aggregation)
-//                   XP   96 KB   three bf16 planes [node][feature], MN-major SWIZZLE_128B (B operand)
-//                   RING 64 KB   4 slots of 16 KB for weight atoms (TMA bulk copies, mbarriers)
+//                                (PNA: 50 KB of fp32 A_u rows instead)
+//                   XP   64 KB   two bf16 planes [node][feature], MN-major SWIZZLE_128B (B operand)
+//                   RING 64 KB   4 slots of 16 KB for weight atoms (PNA with N <= 80: 8 x 10 KB)
 //                   CNT  16 KB   u8 edge multiplicities built with shared-memory atomics
-//   tensor memory   512 columns: D accumulator [0,128), A_hi [128,256), A_lo [256,384)
-// One elected thread issues the bulk copies and all MMAs; completion flows through mbarriers
-// (tcgen05.commit).  The weight stream is continuous across GEMMs: while a GEMM drains, the first
-// atoms of the next one (known statically: next linear of the layer / next layer / head / next tile)
-// are already in flight.
+//   tensor memory   512 columns: D0 [0,128), D1 [128,256), A_hi [384,448), A_mid [448,512);
+//                   a PNA layer lays D_id | D_amp | D_att | B_v out in [0,384) itself
+// The producer warp issues the bulk copies, the issuing warp all MMAs (warp-uniform code, elected
+// lane); completion flows through mbarriers (tcgen05.commit).  The weight stream is continuous
+// across GEMMs, layers, the head and tiles.
 //
 // GCN   planes hold dinv (.) X, ADJ gets +I, the row result is scaled by dinv_v: lib:1246-1278
 // GIN   ADJ gets +I, eps * x_v is added in registers: lib:1519-1529; hidden layer stays in TMEM
 // SAGE  mean = (ADJ . X) / deg, two transforms accumulate in the same TMEM tile: lib:2180-2207
-// Pooling reads the planes (warp per graph); the MLP head runs on the tensor cores for 128 pooled
-// graphs at a time (pending buffer in L2), cpp:454-530.
+// PNA   factorised pre-transform, max / min / mean / std gathered thread-per-row from shared
+//       memory, the three degree scalers as per-row scalars in front of three accumulators
+//       (pna_layer_* below): lib:1750-2157
+// Pooling reads the last layer's fp32 rows (warp per graph); the MLP head runs on the tensor cores
+// for 128 pooled graphs at a time (pending buffer in L2), cpp:454-530.
 //
 // Non-finite activations would leak between the graphs of a tile through 0 * Inf inside the
 // aggregation MMA (the reference keeps graphs independent), so every value written to the planes
-// is checked and the batch is re-run on the layerwise path if any is Inf/NaN (status 3).
+// is checked and the batch is re-run on the layerwise path if any is Inf/NaN (status 3).  PNA has
+// no aggregation MMA: its NaN rows (in-degree 0, lib:702) stay in their graph.
 //
-// Supported: GCN, GIN and SAGE, layer widths a multiple of 16 up to 128; everything else uses
-// fused.cu / the layerwise path.
-//
-// Arithmetic of the node transform (GNNB_TC_BF2, default 1): "bf16x2".  The north star asks for
-// <= 1e-4 relative; round 1's 3xTF32 (three kind::tf32 MMAs per product, ~2^-21) measured 5e-6 and
-// spent 20x more tensor-pipe time than the budget needs.  With GNNB_TC_BF2 every fp32 operand is
-// split into two bf16 values  v ~= hi + mid  (both rounded to nearest, |v - hi - mid| <= 2^-18 |v|)
-// and a product is  A_hi.W_hi + A_mid.W_hi + A_hi.W_mid  as three kind::f16 MMAs, each covering
-// K = 16 instead of 8: half the tensor-pipe time and half the weight bytes streamed per linear.
-// The A operand sits in tensor memory as PACKED bf16 pairs (K elements 2j, 2j+1 in the low / high
-// half of column j; layout pinned by tools/tmem_bf16_probe.py, profiles/r2_tmem_bf16_layout_probe.txt)
-// and the layer input keeps two bf16 planes instead of three.  -DGNNB_TC_BF2=0 rebuilds the
-// 3xTF32 kernel for A/B runs.
+// Supported: GCN, GIN and SAGE with layer widths a multiple of 16 up to 128, PNA up to 96 (and
+// F_in <= F_out); everything else uses fused.cu / the layerwise path.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>

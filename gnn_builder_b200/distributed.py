@@ -375,10 +375,11 @@ class LargeGraphGCN:
         self.hub_l2_mb = int(os.environ.get("GNNB_HUB_L2_MB", 40)) if hub_l2_mb is None else hub_l2_mb
         # Opt-in (GNNB_HALO_BLOCKS = 2..16, p2p transport): a layer's owned rows are computed in
         # that many blocks and the rows the peers need from a finished block are pushed while the
-        # next block is computed.  Measured at 2 GPUs on the 2M-node graph it does not pay (blocks
-        # 1 / 4 / 8: 5.35 / 5.46 / 5.81 ms per step against 5.21 ms for the default scheme below --
-        # smaller kernels, and the pack's CTAs queue behind the aggregation's), so the default
-        # keeps one exchange per layer, overlapped with the aggregation of the owned-source edges.
+        # next block is computed.  Measured on the 2M-node graph it does not pay: at 2 GPUs blocks
+        # 1 / 4 / 8 give 5.35 / 5.46 / 5.81 ms per step against 5.21 ms for the default scheme
+        # below, at 8 GPUs blocks 2 / 4 give 3.01 / 3.08 ms against 2.85 ms -- smaller kernels, and
+        # the pack's CTAs queue behind the aggregation's -- so the default keeps one exchange per
+        # layer, overlapped with the aggregation of the owned-source edges.
         self.n_blocks = max(0, min(16, int(os.environ.get("GNNB_HALO_BLOCKS", 0))))
         params = model.named_parameter_arrays()
         names = list(params)
