@@ -533,8 +533,16 @@ def measure_molecular(ctx: Ctx, w, graphs_per_gpu: int, steps: int, warmup: int,
                     "fp32_fma_peak_tflops": fp32_peak_tflops,
                     "frac_of_fp32_fma_peak": achieved / fp32_peak_tflops}
         if on_tensor:
+            # the fused kernel's node transforms are bf16x2: three kind::f16 MMAs per product
             gemm_fl = gemm_flops_per_batch(w, batch)
-            executed = 3.0 * gemm_fl / (dom_ms * 1e-3) / 1e12      # TF32 MMA flops actually issued
+            executed = 3.0 * gemm_fl / (dom_ms * 1e-3) / 1e12
+            roofline["executed_bf16_mma_tflops"] = executed
+            roofline["executed_frac_of_bf16_peak"] = executed / ctx.tensor_peak
+            roofline["executed_note"] = ("node-transform MMAs only (3 bf16 MMAs of K = 16 per product); the "
+                                         "dense 128x128 tile aggregation MMAs are not counted")
+        elif dominant == "gemm":
+            # layerwise tcgen05 GEMM: 3xTF32 (three kind::tf32 MMAs per product)
+            executed = 3.0 * fl / (dom_ms * 1e-3) / 1e12
             roofline["executed_tf32_mma_tflops"] = executed
             if with_tf32_peak:
                 tf32 = measured_tf32_peak(torch)
@@ -760,7 +768,8 @@ def measure_large(ctx: Ctx, w, nodes: int, steps: int, warmup: int, cpu_baseline
         eng.set_profile(False)
         agg_ms = prof["aggregate"]["ms"] / 2 / L
         achieved = agg_bytes_layer / (agg_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "aggregate (agg_rows_kernel + agg_heavy_kernel)",
+        roofline = {"bound": "hbm",
+                    "kernel": "aggregate (agg_rows_kernel + agg_heavy_chunk_kernel + agg_heavy_combine_kernel)",
                     "achieved": achieved, "peak": ctx.hbm_peak, "unit": "GB/s",
                     "frac": achieved / ctx.hbm_peak, "traffic": None,
                     "kernel_ms": agg_ms, "algorithmic_bytes_per_layer": agg_bytes_layer,
@@ -830,7 +839,6 @@ def measure_large(ctx: Ctx, w, nodes: int, steps: int, warmup: int, cpu_baseline
             "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "exchange": exchange}
     if world == 1:
-        line["hub_rows_l2_resident"] = None
         eng.close()
         del dx, dcoo
     else:
