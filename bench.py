@@ -498,6 +498,20 @@ def measure_molecular(ctx: Ctx, w, graphs_per_gpu: int, steps: int, warmup: int,
     torch.cuda.synchronize()
     e2e_pg_s = ctx.max(time.perf_counter() - t0) / pg_steps
     ctx.barrier()
+    # ... and the same numpy arrays after Engine.pin_batch (cudaHostRegister in place, once)
+    t0 = time.perf_counter()
+    eng.pin_batch(batch)
+    eng.pin(out_pageable)
+    register_s = time.perf_counter() - t0
+    eng.run(batch, out=out_pageable)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(pg_steps):
+        eng.run(batch, out=out_pageable)
+    torch.cuda.synchronize()
+    e2e_reg_s = ctx.max(time.perf_counter() - t0) / pg_steps
+    eng.unpin()
+    ctx.barrier()
 
     # ---- live per-kernel-class timing for the roofline
     eng.set_profile(True)
@@ -589,7 +603,11 @@ def measure_molecular(ctx: Ctx, w, graphs_per_gpu: int, steps: int, warmup: int,
                 "pageable": {"value": total_graphs / e2e_pg_s, "unit": UNIT,
                              "ms_per_step": e2e_pg_s * 1e3, "h2d_gbs_per_gpu": h2d / e2e_pg_s / 1e9,
                              "note": "the same call on ordinary numpy arrays: the copies go "
-                                     "through the driver's staging buffers"}},
+                                     "through the driver's staging buffers"},
+                "registered": {"value": total_graphs / e2e_reg_s, "unit": UNIT,
+                               "ms_per_step": e2e_reg_s * 1e3, "register_ms_once": register_s * 1e3,
+                               "note": "the same numpy arrays after Engine.pin_batch "
+                                       "(cudaHostRegister in place, paid once)"}},
         "gpu_launches": int(launches_per_step * steps),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

@@ -35,7 +35,8 @@ class GnnbError(RuntimeError):
 
 # every symbol include/gnnb_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "gnnb_last_error", "gnnb_version", "gnnb_device_count",
+    "gnnb_last_error", "gnnb_version", "gnnb_device_count", "gnnb_host_register",
+    "gnnb_host_unregister",
     "gnnb_model_create", "gnnb_model_destroy", "gnnb_model_num_params", "gnnb_model_param_info",
     "gnnb_model_set_param", "gnnb_model_finalize", "gnnb_model_set_path", "gnnb_model_set_math",
     "gnnb_model_run_graph", "gnnb_model_run_batch", "gnnb_model_run_batch_async",
@@ -75,6 +76,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.gnnb_last_error.restype = C.c_char_p
     lib.gnnb_model_stream.restype = C.c_void_p
     lib.gnnb_model_stream.argtypes = [C.c_void_p]
+    lib.gnnb_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    lib.gnnb_host_unregister.argtypes = [C.c_void_p]
     lib.gnnb_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(C.c_void_p)]
     lib.gnnb_model_destroy.argtypes = [C.c_void_p]
     lib.gnnb_model_num_params.argtypes = [C.c_void_p]

@@ -186,6 +186,22 @@ extern "C" int gnnb_device_count(int *count)
     return GNNB_OK;
 }
 
+// Page-locks a caller-owned host buffer (cudaHostRegister) so that the host-buffer entry points copy
+// it at full PCIe rate and asynchronously; worth it for buffers that are passed more than once
+// (registration itself costs about as much as one pageable copy).
+extern "C" int gnnb_host_register(void *ptr, size_t bytes)
+{
+    GNNB_REQUIRE(ptr != nullptr && bytes > 0, "host register: null buffer");
+    GNNB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return GNNB_OK;
+}
+extern "C" int gnnb_host_unregister(void *ptr)
+{
+    GNNB_REQUIRE(ptr != nullptr, "host unregister: null buffer");
+    GNNB_CUDA(cudaHostUnregister(ptr));
+    return GNNB_OK;
+}
+
 // ============================================================================ model handle
 extern "C" int gnnb_model_create(const gnnb_model_desc *desc, int device, gnnb_model_t **out)
 {

@@ -46,6 +46,7 @@ class Engine:
         self.out_dim = int(desc["mlp_out"])
         self.in_dim = int(desc["in_dim"])
         self._h = C.c_void_p()
+        self._pinned = {}
         s = _desc_struct(desc, max_nodes, max_edges)
         _lib.check(self.lib.gnnb_model_create(C.byref(s), device, C.byref(self._h)))
         try:
@@ -127,6 +128,25 @@ class Engine:
             C.c_void_p(out.ctypes.data)))
         return out
 
+    def pin(self, *arrays: np.ndarray):
+        """Page-lock host arrays in place (cudaHostRegister) so that ``run`` / ``run_graph`` copy them
+        asynchronously at the full PCIe rate; for batches that are passed more than once.  The
+        arrays stay registered until ``unpin`` or ``close``; keep them alive meanwhile."""
+        for a in arrays:
+            if a is None or a.nbytes == 0 or a.ctypes.data in self._pinned:
+                continue
+            assert a.flags["C_CONTIGUOUS"], "pin() needs C-contiguous arrays"
+            _lib.check(self.lib.gnnb_host_register(C.c_void_p(a.ctypes.data), a.nbytes))
+            self._pinned[a.ctypes.data] = a
+
+    def pin_batch(self, batch: GraphBatch):
+        self.pin(batch.x, batch.coo, batch.node_ptr, batch.edge_ptr)
+
+    def unpin(self):
+        for ptr in list(self._pinned):
+            self.lib.gnnb_host_unregister(C.c_void_p(ptr))
+        self._pinned.clear()
+
     def run_graph(self, x: np.ndarray, coo: np.ndarray) -> np.ndarray:
         """One graph, the exact data ``<name>_top`` receives."""
         x = np.ascontiguousarray(x, np.float32)
@@ -168,6 +188,8 @@ class Engine:
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
+        if getattr(self, "_pinned", None):
+            self.unpin()
         if getattr(self, "_h", None) and self._h.value:
             self.lib.gnnb_model_destroy(self._h)
             self._h = C.c_void_p()

@@ -87,6 +87,13 @@ const char *gnnb_last_error(void);
 int gnnb_version(void);
 int gnnb_device_count(int *count);
 
+/* Page-lock / release a caller-owned HOST buffer (cudaHostRegister): the host-buffer entry points
+ * below then copy it asynchronously at the full PCIe rate (45 GB/s against ~8.5 GB/s for pageable
+ * memory on the bench box).  Registration costs about one pageable copy, so it pays for buffers
+ * that are passed more than once. */
+int gnnb_host_register(void *ptr, size_t bytes);
+int gnnb_host_unregister(void *ptr);
+
 /* ---- model handle: replaces <name>_top (model.h.jinja:67-79, cpp:686-766) ----------------- */
 /* device < 0 selects the current CUDA device */
 int gnnb_model_create(const gnnb_model_desc *desc, int device, gnnb_model_t **out);

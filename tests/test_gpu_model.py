@@ -484,3 +484,24 @@ def test_layerwise_path_rejects_out_of_range_edges(gnnb):
                 assert np.isfinite(eng.run(gnnb.GraphBatch.from_graphs([good]))).all()
         with pytest.raises(gnnb._lib.GnnbError, match="outside"):
             layers.compute_degree_tables(bad[1], 6)
+
+
+def test_pinning_caller_buffers_in_place(gnnb):
+    """Engine.pin_batch page-locks the caller's numpy arrays (cudaHostRegister): same results, the
+    arrays are usable as before, unpin / close release them"""
+    import ctypes as C
+
+    w, model, _ = model_and_params("c2_gin_qm9")
+    batch = gnnb.make_molecular_batch(3000, w.mu_nodes, w.mu_edges, w.in_dim, seed=12)
+    with gnnb.Engine(model) as eng:
+        ref = eng.run(batch).copy()
+        eng.pin_batch(batch)
+        eng.pin_batch(batch)                       # idempotent
+        assert len(eng._pinned) == 4
+        assert np.array_equal(eng.run(batch), ref)
+        batch.x[0, 0] += 1.0                       # still ordinary writable memory
+        assert not np.array_equal(eng.run(batch), ref)
+        eng.unpin()
+        assert not eng._pinned
+        batch.x[0, 0] -= 1.0
+        assert np.array_equal(eng.run(batch), ref)
