@@ -507,9 +507,12 @@ static int run_layerwise(gnnb_model *m, const float *x, const int32_t *coo, cons
     int32_t *nbr = m->nbr.as<int32_t>();
     if (d.num_layers > 0) {
         ProfScope ps(m->prof, PROF_TABLES, s);
+        // the out-degree table (lib:1051-1083) is only read by the optional hub-row hints
+        const bool want_out_deg = !strict && hub_l2_budget() > 0 && d.conv_type != GNNB_CONV_PNA &&
+                                  n_graphs > 0 && T64 / n_graphs > 50000;
         GNNB_TRY(build_tables(coo, n_graphs > 1 ? node_ptr : nullptr, edge_ptr, node_base, edge_base,
-                              n_graphs, T, E, in_deg, m->out_deg.as<int32_t>(), offsets, nbr,
-                              nullptr, m->tws, s, launches, m->edge_flag.as<int>()));
+                              n_graphs, T, E, in_deg, want_out_deg ? m->out_deg.as<int32_t>() : nullptr,
+                              offsets, nbr, nullptr, m->tws, s, launches, m->edge_flag.as<int>()));
     }
     const float *dinv = nullptr;
     if (d.conv_type == GNNB_CONV_GCN && !strict && d.num_layers > 0) {

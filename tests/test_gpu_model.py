@@ -505,3 +505,17 @@ def test_pinning_caller_buffers_in_place(gnnb):
         assert not eng._pinned
         batch.x[0, 0] -= 1.0
         assert np.array_equal(eng.run(batch), ref)
+
+
+def test_layerwise_tables_from_sorted_keys_match_the_atomic_path(gnnb):
+    """edge lists of >= 2^20 edges take their in-degrees from run lengths of the sorted destination
+    keys, smaller ones from atomics: the layerwise path is bit-stable across batch composition, so
+    one 30k-graph batch (1.1M edges) must give the bits its two halves give"""
+    w, model, _ = model_and_params("c2_gin_qm9")
+    batch = gnnb.make_molecular_batch(30000, w.mu_nodes, w.mu_edges, w.in_dim, seed=17)
+    assert batch.total_edges >= (1 << 20) and batch.slice(0, 15000).total_edges < (1 << 20)
+    for math in (gnnb.MATH_FAST, gnnb.MATH_STRICT):
+        with gnnb.Engine(model, path=gnnb.PATH_LAYERWISE, math=math) as eng:
+            whole = eng.run(batch)
+            halves = np.concatenate([eng.run(batch.slice(0, 15000)), eng.run(batch.slice(15000, 30000))])
+        assert np.array_equal(whole, halves), math
