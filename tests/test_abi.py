@@ -201,3 +201,26 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("version ")
+
+
+def test_bench_deadline_guard_prints_the_headline(tmp_path):
+    """bench.py's guard around the extras: if they overrun (a hung collective, a dead peer) rank 0
+    still prints ONE JSON line -- the headline with the reason under `extra` -- and exits 0"""
+    import json
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, time; sys.path.insert(0, %r)\n"
+        "import bench\n"
+        "line = {'metric': 'graphs_per_sec', 'value': 1.0}\n"
+        "extra = {'c4_pna_lipo': {'value': 2.0}}\n"
+        "bench.Deadline(0.3, lambda why: dict(line, extra=dict(extra, error=why)), rank=0)\n"
+        "time.sleep(30)\n" % str(ROOT))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["value"] == 1.0 and d["extra"]["error"] == "deadline exceeded"
+    assert d["extra"]["c4_pna_lipo"]["value"] == 2.0
