@@ -205,7 +205,10 @@ int gnnb_simple_conv(int num_nodes, int num_edges, const float *x_in, float *x_o
                      const int32_t *edge_list, const int32_t *neighbor_table_offsets,
                      const int32_t *neighbor_table, const int32_t *in_degree_table,
                      const int32_t *out_degree_table, int emb, int math);
-/* lib:1891-2157 (transform 2F->F, apply 13F->emb_out, final emb_out->emb_out) */
+/* lib:1891-2157 (transform 2F->F, apply 13F->emb_out, final emb_out->emb_out).  Like the reference's
+ * float build, a node with in-degree 0 gets std = sqrt(0/0 + 1e-5) = NaN (lib:702), so its output row
+ * is NaN (PyG clamps the degree instead; parity here is with the reference).  The model paths keep the
+ * same semantics: ReLU maps such rows to 0, other activations keep the NaN. */
 int gnnb_pna_conv(int num_nodes, int num_edges, const float *x_in, float *x_out,
                   const int32_t *edge_list, const int32_t *neighbor_table_offsets,
                   const int32_t *neighbor_table, const int32_t *in_degree_table,
