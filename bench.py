@@ -452,8 +452,6 @@ def measure_molecular(ctx: Ctx, w, graphs_per_gpu: int, steps: int, warmup: int,
     for _ in range(warmup):
         step_device()
     eng.synchronize()
-    launches_per_step = eng.last_launches
-    path_used = eng.last_kernel
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(1.2)  # nvidia-smi needs about a second before its first sample
@@ -466,6 +464,8 @@ def measure_molecular(ctx: Ctx, w, graphs_per_gpu: int, steps: int, warmup: int,
             step_device()
         ev1.record(stream)
     eng.synchronize()
+    launches_per_step = eng.last_launches      # (kernels of the last timed step: our own count)
+    path_used = eng.last_kernel
     ctx.barrier()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
@@ -687,8 +687,6 @@ def measure_large(ctx: Ctx, w, nodes: int, steps: int, warmup: int, cpu_baseline
     for _ in range(warmup):
         step()
     sync()
-    if world == 1:
-        launches = eng.last_launches
     sampler.start()
     time.sleep(1.2)  # nvidia-smi needs about a second before its first sample
     ctx.barrier()
@@ -701,6 +699,8 @@ def measure_large(ctx: Ctx, w, nodes: int, steps: int, warmup: int, cpu_baseline
         ev1.record(stream)
     sync()
     torch.cuda.synchronize()
+    if world == 1:
+        launches = eng.last_launches
     t1w = time.time()
     clocks = sampler.stop(t0w, t1w)
     ms_per_step = ctx.max(ev0.elapsed_time(ev1) / steps)
